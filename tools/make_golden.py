@@ -1,0 +1,97 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz from the reference's shipped fixtures (run in the build container only;
+/root/reference does not exist on the GPU box).  Usage: python tools/make_golden.py [/root/reference]
+
+What is extracted (SURVEY.md 8c "golden vectors"):
+  cyl.npz : examples/cylinder/stability/direct/{BF_1cyl0.f00001, 1cyl.ma2, 1cyl.re2, Spectre_*.dat},
+            .../adjoint/Spectre_*.dat, .../postproc/sensitivity_budget_wavemaker/{dRe,dIm}1cyl0.f00001,
+            element->rank maps of the field files (partition KAT)
+  bfs.npz : examples/back_fstep/transient_growth/{BF_bfs0,pRebfs0,orebfs0}.f00001, bfs.ma2, bfs.re2
+All element data are re-ordered to ascending global element id.
+"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from nekstab_b200 import nekio  # noqa: E402
+
+REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+
+
+def runs_to_rank(ff):
+    rank = np.empty(ff.nelg, dtype=np.int16)
+    for r, run in enumerate(ff.rank_runs()):
+        rank[run - 1] = r
+    return rank
+
+
+def cyl():
+    d = f"{REF}/examples/cylinder/stability/direct"
+    a = f"{REF}/examples/cylinder/stability/adjoint"
+    p = f"{REF}/examples/cylinder/postproc/sensitivity_budget_wavemaker"
+    bf_raw = nekio.read_field(f"{d}/BF_1cyl0.f00001")
+    bf = bf_raw.sort_global()
+    re2 = nekio.read_re2(f"{d}/1cyl.re2")
+    ma2 = nekio.read_ma2(f"{d}/1cyl.ma2")
+    names = np.array(["E  ", "P  ", "v  ", "O  ", "W  "])
+    codes = re2.bc_codes()
+    bc = np.zeros(codes.shape, dtype=np.uint8)
+    for i, nme in enumerate(names):
+        bc[codes == nme] = i
+    dre = nekio.read_field(f"{p}/dRe1cyl0.f00001").sort_global()
+    dim = nekio.read_field(f"{p}/dIm1cyl0.f00001").sort_global()
+    bf40 = nekio.read_field(f"{REF}/examples/cylinder/baseflow/newton/BFRe40_1cyl0.f00001") \
+        if os.path.exists(f"{REF}/examples/cylinder/baseflow/newton/BFRe40_1cyl0.f00001") else None
+    out = dict(
+        lx1=bf.nx, X=bf.data["X"][:, :, 0], U=bf.data["U"][:, :, 0], P=bf.data["P"][:, 0],
+        vert=ma2.vert.astype(np.int32), key=ma2.key.astype(np.int32), d2=ma2.d2,
+        bc=bc, bc_names=names.astype("S3"),
+        dRe_U=dre.data["U"][:, :, 0].astype(np.float32), dRe_P=dre.data["P"][:, 0].astype(np.float32),
+        dIm_U=dim.data["U"][:, :, 0].astype(np.float32), dIm_P=dim.data["P"][:, 0].astype(np.float32),
+        mode_istep=dre.istep,
+        Spectre_Hd=nekio.read_spectre(f"{d}/Spectre_Hd.dat"),
+        Spectre_NSd=nekio.read_spectre(f"{d}/Spectre_NSd.dat"),
+        Spectre_NSd_conv=nekio.read_spectre(f"{d}/Spectre_NSd_conv.dat"),
+        Spectre_Ha=nekio.read_spectre(f"{a}/Spectre_Ha.dat"),
+        Spectre_NSa_conv=nekio.read_spectre(f"{a}/Spectre_NSa_conv.dat"),
+        rank_p6=runs_to_rank(bf_raw),
+    )
+    if bf40 is not None:
+        out["rank_p4"] = runs_to_rank(bf40)
+    np.savez_compressed(f"{OUT}/cyl.npz", **out)
+    print("cyl.npz", os.path.getsize(f"{OUT}/cyl.npz") / 1e6, "MB")
+
+
+def bfs():
+    d = f"{REF}/examples/back_fstep/transient_growth"
+    bf_raw = nekio.read_field(f"{d}/BF_bfs0.f00001")
+    bf = bf_raw.sort_global()
+    pre = nekio.read_field(f"{d}/pRebfs0.f00001").sort_global()
+    pim = nekio.read_field(f"{d}/pImbfs0.f00001").sort_global()
+    ore = nekio.read_field(f"{d}/orebfs0.f00001").sort_global()
+    re2 = nekio.read_re2(f"{d}/bfs.re2")
+    ma2 = nekio.read_ma2(f"{d}/bfs.ma2")
+    f32 = np.float32
+    out = dict(
+        lx1=bf.nx, re2_xyz=re2.xyz, X=bf.data["X"][:, :, 0].astype(f32), U=bf.data["U"][:, :, 0].astype(f32),
+        vert=ma2.vert.astype(np.int32), key=ma2.key.astype(np.int32), d2=ma2.d2,
+        bc_id=re2.bc_param(4).astype(np.uint8),
+        pRe_U=pre.data["U"][:, :, 0].astype(f32), pRe_P=pre.data["P"][:, 0].astype(f32),
+        pIm_absmax=np.abs(pim.data["U"]).max(),
+        ore_U=ore.data["U"][:, :, 0].astype(f32), ore_P=ore.data["P"][:, 0].astype(f32),
+        mode_istep=pre.istep, rank_p4=runs_to_rank(bf_raw),
+        rank_p6=runs_to_rank(nekio.read_field(f"{d}/pRebfs0.f00001")),
+        barkley=np.loadtxt(f"{REF}/examples/back_fstep/barkley2008_fig5.ref", ndmin=2)
+        if os.path.exists(f"{REF}/examples/back_fstep/barkley2008_fig5.ref") else np.zeros((0, 2)),
+    )
+    np.savez_compressed(f"{OUT}/bfs.npz", **out)
+    print("bfs.npz", os.path.getsize(f"{OUT}/bfs.npz") / 1e6, "MB")
+
+
+if __name__ == "__main__":
+    cyl()
+    bfs()

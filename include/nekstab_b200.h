@@ -1,0 +1,163 @@
+/* nekstab_b200.h -- C ABI of the B200-native hot path of nekStab.
+ *
+ * The hot path is nekStab's matrix-free Krylov loop whose matvec is one linearised Navier-Stokes
+ * time-stepper integration.  In the reference this is Fortran: external procedures with implicit
+ * interfaces that share state through COMMON blocks (core/NEKSTAB:6-55) and call Nek5000's
+ * `nek_advance` (core/matvec.f:222).  This header is what a thin ISO_C_BINDING module binds
+ * (nekstab_b200/fortran/nekstab_b200_c.f90; INTEGRATION.md shows the replaced Fortran bodies).
+ *
+ * Conventions
+ *  - plain C types only; all arrays are HOST pointers owned by the caller unless stated otherwise;
+ *    element data are Nek-ordered: a(ix,iy,iz,e), ix fastest, e = local element (Fortran column major);
+ *  - every function returns 0 on success, non-zero on error (message: nsb_last_error()); the Fortran
+ *    shim maps non-zero to `call nek_end`, the reference's only error convention
+ *    (core/krylov_subspace.f:53, core/krylov_decomposition.f:64-67);
+ *  - one context per process (= per GPU, = per MPI rank), not re-entrant, like the reference's
+ *    `save`d locals (core/matvec.f:98-99);
+ *  - Krylov vectors live in device memory and are addressed by integer *slots*; host copies are
+ *    made only by nsb_vec_upload / nsb_vec_download (the field-access sites listed in SURVEY.md 8b).
+ *  - there is NO CPU fallback: every entry point fails if no CUDA device is usable.
+ */
+#ifndef NEKSTAB_B200_H
+#define NEKSTAB_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ communicator (NCCL over NVLink)
+ * Replaces Nek5000's MPI wrappers reached from the path: gop/glsc3 (core/krylov_subspace.f:37-43),
+ * gslib gs_op under dssum, bcast/nekgsync (core/matvec.f:7,18).  Rank 0 creates the id, the host
+ * program broadcasts the 128 bytes with whatever it has (MPI_Bcast in Nek5000), every rank calls
+ * nsb_comm_init (with the CUDA device it will use) BEFORE nsb_init.  Single-GPU runs skip both calls. */
+int nsb_comm_unique_id(char id_out[128]);
+int nsb_comm_init(int rank, int nranks, const char id[128], int device);
+
+/* ------------------------------------------------------------------ setup
+ * nsb_init: what Nek5000 holds in SIZE/GEOM/SOLN/PARALLEL commons after nek_init, for the local
+ * elements of this rank: lx1,lxd,lx2 (SIZE), xm1/ym1/zm1 (GEOM), v1mask..v3mask (SOLN), glo_num =
+ * the global GLL node numbers Nek's setvert2d/3d produce for gs_setup [UPSTREAM navier8.f], nelgv.
+ * zm1/v3mask may be NULL when ldim == 2.  Builds metrics, mass/stiffness factors, mesh-2 and dealiasing
+ * metrics, Jacobi diagonals and the gather-scatter maps on the device. */
+int nsb_init(int ldim, int lx1, int lxd, int lx2, int nelv, long long nelgv,
+             const double* xm1, const double* ym1, const double* zm1,
+             const double* v1mask, const double* v2mask, const double* v3mask,
+             const long long* glo_num, int device);
+int nsb_finalize(void);
+const char* nsb_last_error(void);
+
+/* param(2) (viscosity = 1/Re), param(1) (density), param(22)/param(21) (tolhv / tolps, absolute),
+ * iteration caps (Nek: nmxh / nmxp). */
+int nsb_set_params(double viscosity, double density, double tol_v, double tol_p, int maxit_v, int maxit_p);
+/* bm1s: the energy weight with the sponge zeroed (core/usr_extra.f:102,116-118).  NULL -> bm1. */
+int nsb_set_weights(const double* bm1s);
+/* ubase, vbase, wbase (core/NEKSTAB: /nStab_bflows/; loaded at core/eigensolvers.f:180-186). */
+int nsb_set_baseflow(const double* ubase, const double* vbase, const double* wbase);
+/* spng_fun (core/NEKSTAB: /nStab_sponge/): perturbation forcing -spng_fun*u' (core/utils.f:172-177).
+ * NULL switches the sponge off (spng_str == 0). */
+int nsb_set_sponge(const double* spng_fun);
+/* prepare_linearized_solver (core/matvec.f:1-52): ctarg = compute_cfl(base flow, dt=1);
+ * dt = cfl_target/ctarg; nsteps = ceiling(end_time/dt); dt = end_time/nsteps. Stores dt, nsteps. */
+int nsb_prepare_linearized_solver(double end_time, double cfl_target, double* dt, int* nsteps, double* ctarg);
+int nsb_set_timestep(double dt, int nsteps);
+/* Nek5000's `ifvcor` (no outflow-type boundary => E = D B^-1 D^T has the constant null vector => `ortho` on the
+ * pressure right-hand side and solution) for the direct and the adjoint mask set: 1 / 0, or -1 to decide
+ * numerically from ||E 1|| (the default after nsb_init). */
+int nsb_set_ifvcor(int direct, int adjoint);
+
+/* ------------------------------------------------------------------ krylov_vector algebra
+ * One slot = one `type(krylov_vector)` (core/krylov_subspace.f:10-15): vx,vy,vz(n), pr(n2); the
+ * scalar `time` member stays on the host side.  theta (ldimt scalars) is not carried (ifheat=F). */
+int nsb_vec_alloc(int nslots);                                   /* (re)allocate the slab Q(1:nslots) */
+int nsb_vec_upload(int slot, const double* vx, const double* vy, const double* vz, const double* pr);
+int nsb_vec_download(int slot, double* vx, double* vy, double* vz, double* pr);
+int nsb_vec_copy(int dst, int src);                              /* krylov_copy  :190 */
+int nsb_vec_zero(int slot);                                      /* krylov_zero  :166 */
+int nsb_vec_cmult(int slot, double alpha);                       /* krylov_cmult :90  */
+int nsb_vec_add2(int p, int q);                                  /* krylov_add2  :116 */
+int nsb_vec_sub2(int p, int q);                                  /* krylov_sub2  :142 */
+int nsb_vec_inner_product(int p, int q, double* alpha);          /* krylov_inner_product :24 (NaN -> error) */
+int nsb_vec_norm(int p, double* alpha);                          /* krylov_norm :58 */
+int nsb_vec_normalize(int p, double* alpha);                     /* krylov_normalize :71 */
+/* krylov_matmul (core/krylov_subspace.f:214-258): slot_out = sum_i y(i) * Q(first+i), i<k */
+int nsb_basis_gemv(int k, int first_slot, const double* y, int slot_out);
+/* basis rotation of schur_condensation (core/eigensolvers.f:466-474): Q(:,1:k) <- Q(:,1:k) * S(k,k),
+ * S column-major with leading dimension lds. */
+int nsb_basis_rotate(int k, int first_slot, const double* S, int lds);
+/* update_hessenberg_matrix (core/krylov_decomposition.f:116-202): orthogonalise slot_f against
+ * Q(first..first+k-1) twice, accumulate coefficients, normalise; hcol[0..k-1] = H(1:k,k), hcol[k] = H(k+1,k).
+ * Classical Gram-Schmidt applied twice (DGKS) as two tall-skinny GEMV pairs. */
+int nsb_orthonormalize(int k, int first_slot, int slot_f, double* hcol);
+/* complex mode reconstruction of outpost_ks (core/eigensolvers.f:607-615): re/im slots =
+ * sum_i (yre(i), yim(i)) * Q(first+i) */
+int nsb_basis_gemv_complex(int k, int first_slot, const double* yre, const double* yim, int slot_re, int slot_im);
+
+/* ------------------------------------------------------------------ matvec (core/matvec.f:64-159) */
+enum {
+  NSB_DIRECT = 1,          /* forward_linearized_map   uparam(1) in [3.0,3.2)  core/matvec.f:163 */
+  NSB_ADJOINT = 2,         /* adjoint_linearized_map   uparam(1) in [3.2,3.3)  core/matvec.f:249 */
+  NSB_DIRECT_ADJOINT = 3,  /* transient_growth_map     uparam(1) in [3.3,3.4)  core/matvec.f:332 */
+  NSB_NEWTON = 4,          /* newton_linearized_map    floor(uparam(1)) == 2   core/matvec.f:381 (fixed points) */
+  NSB_FORCE_SENS = 5       /* ts_force_sensitivity_map floor(uparam(1)) == 4   core/matvec.f:357 */
+};
+int nsb_matvec(int mode, int slot_in, int slot_out);
+/* Adjoint problems may use different Dirichlet masks (outflow 'O' -> 'v', 1cyl.usr:126-132). NULL = same. */
+int nsb_set_adjoint_masks(const double* v1mask, const double* v2mask, const double* v3mask);
+
+/* ------------------------------------------------------------------ statistics of the last matvec / since reset */
+typedef struct nsb_stats {
+  long long steps;              /* linearised time steps taken */
+  long long helm_iters;         /* sum over components of Helmholtz CG iterations */
+  long long pres_iters;         /* pressure CG iterations */
+  long long kernel_launches;    /* CUDA kernels launched by this library */
+  double    step_ms;            /* device time in stepper (CUDA events) */
+} nsb_stats;
+int nsb_get_stats(nsb_stats* out, int reset);
+
+/* ------------------------------------------------------------------ operator-level entry points
+ * Mirrors of the Nek5000 routines on the path, taking HOST arrays (copied in and out) so that every
+ * kernel can be parity-tested against the oracle exactly like the reference routine would be.
+ * [UPSTREAM] hmholtz.f axhelm; dssum.f dssum; math.f glsc3; navier1.f opgradt, opdiv, cdabdtp;
+ * perturb.f advabp/advabp_adjoint; hmholtz.f hmholtz (Jacobi-PCG); navier1.f esolver (here Jacobi-PCG). */
+int nsb_op_axhelm(const double* u, double h1, double h2, double* w);
+int nsb_op_dssum(double* u);
+int nsb_op_glsc3(const double* a, const double* b, const double* c, double* out);
+int nsb_op_opgradt(const double* p, double* wx, double* wy, double* wz);
+int nsb_op_opdiv(const double* ux, const double* uy, const double* uz, double* q);
+int nsb_op_cdabdtp(const double* p, double* ep);
+int nsb_op_advab(int adjoint, const double* upx, const double* upy, const double* upz,
+                 double* fx, double* fy, double* fz);            /* mass-weighted, un-assembled */
+int nsb_op_hmholtz(double* ux, double* uy, double* uz, const double* rx, const double* ry, const double* rz,
+                   double h1, double h2, int* iters);            /* rhs un-assembled; returns du */
+int nsb_op_esolver(const double* g, double* phi, int* iters);
+int nsb_op_cfl(const double* ux, const double* uy, const double* uz, double dt, double* cfl);
+/* named geometry arrays for parity checks: "bm1","binvm1","jacm1","g1".."g6","bm2","ediag","hdiagA","vmult" */
+int nsb_get_field(const char* name, double* out, long long* count);
+long long nsb_n(void);   /* nelv*lx1^ldim */
+long long nsb_n2(void);  /* nelv*lx2^ldim */
+
+/* ------------------------------------------------------------------ host-side Krylov drivers (C++),
+ * mirroring the reference's Fortran drivers one to one; small dense work on host LAPACK
+ * (dgeev/dgees/dtrsen/dgels, core/lapack_wrapper.f:7-339).  H is column-major (ldh >= ksize+1). */
+int nsb_arnoldi_factorization(int mode, int first_slot, double* H, int ldh, int mstart, int mend, int ksize); /* core/krylov_decomposition.f:7 */
+/* krylov_schur (core/eigensolvers.f:141-388): returns Ritz values (sorted by decreasing magnitude),
+ * residuals, eigenvectors of H (column-major complex interleaved, k x k) and the count of converged. */
+int nsb_krylov_schur(int mode, int k_dim, int schur_tgt, double eigen_tol, double schur_del, int seed_slot,
+                     double* vals_re, double* vals_im, double* residual, double* vecs_reim, int* n_converged,
+                     int* schur_cnt, int max_restarts);
+int nsb_schur_condensation(int* mstart, double* H, int ldh, int first_slot, int ksize, int schur_tgt, double schur_del); /* :395 */
+int nsb_select_eigenvalues(int* selected, int* cnt, const double* vals_re, const double* vals_im, double delta, int nev, int n); /* :729 */
+/* ts_gmres (core/newton_krylov.f:175-297): solves matvec(mode) * sol = rhs; slots first..first+ksize hold the basis */
+int nsb_ts_gmres(int mode, int rhs_slot, int sol_slot, int first_slot, int work_slot, int maxiter, int ksize, double tol,
+                 int* calls, double* final_res);
+/* LAPACK wrappers exactly as core/lapack_wrapper.f (schur:7, ordschur:70, eig:129, lstsq:287). */
+int nsb_lapack_eig(const double* A, int n, double* vals_re, double* vals_im, double* vecs_reim);
+int nsb_lapack_schur(double* A, int n, double* vecs, double* vals_re, double* vals_im);
+int nsb_lapack_ordschur(double* T, double* Q, const int* selected, int n);
+int nsb_lapack_lstsq(const double* A, const double* b, double* x, int m, int n);
+int nsb_lapack_load(const char* path);   /* optional: library exporting LP64 dgeev_/dgees_/dtrsen_/dgels_ (or scipy_ prefixed) */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -252,6 +252,11 @@ class Case:
     tol_v: float = 1e-9
     spng_fun: Optional[np.ndarray] = None      # (nel, lx1^ldim) or None
     lglel: Optional[np.ndarray] = None         # global element ids (1-based) of the local elements
+    nelg: Optional[int] = None                 # global element count (None: this is the global mesh)
+    # Nek's ifvcor: no outflow-type boundary => pressure defined up to a constant (E singular) => `ortho`.
+    # None lets the library decide numerically from ||E 1||.
+    ifvcor: Optional[bool] = None
+    ifvcor_adjoint: Optional[bool] = None
     extra: Dict[str, np.ndarray] = field(default_factory=dict)
 
     @property
@@ -286,6 +291,7 @@ class Case:
         sel = np.nonzero(r == rank)[0]
         c = copy.copy(self)
         c.nel = sel.size
+        c.nelg = self.nelg or self.nel
         c.xyz = self.xyz[:, sel]
         c.glo = self.glo[sel]
         c.mask = self.mask[:, sel]
@@ -331,6 +337,7 @@ def cylinder_case(g: dict, lx1: Optional[int] = None, sponge: bool = True) -> Ca
     case = Case("cylinder_re50", 2, lx1, X.shape[1], X, glo, _mask_from_faces(dir_d, glo, lx1, 2),
                 g["key"].astype(np.int64), int(g["d2"]), U, re=50.0, end_time=1.0, tol_p=1e-7, tol_v=1e-9)
     case.extra["mask_adjoint"] = _mask_from_faces(dir_a, glo, lx1, 2)
+    case.ifvcor, case.ifvcor_adjoint = False, True
     if sponge:
         case.spng_fun = sponge_function([X[0], X[1]], [5.0, 0.0], [5.0, 0.0])
     return case
@@ -352,6 +359,7 @@ def bfs_case(g: dict, sponge: bool = True) -> Case:
     U = g["U"].reshape(-1, 2, lx1 * lx1).transpose(1, 0, 2).astype(np.float64)
     case = Case("bfs_re500", 2, lx1, X.shape[1], X, glo, _mask_from_faces(dirf, glo, lx1, 2),
                 g["key"].astype(np.int64), int(g["d2"]), U, re=500.0, end_time=1.0, tol_p=1e-8, tol_v=1e-8)
+    case.ifvcor = case.ifvcor_adjoint = True
     if sponge:
         case.spng_fun = sponge_function([X[0], X[1]], [5.0, 0.0], [10.0, 0.0])
     return case
@@ -382,6 +390,7 @@ def extrude(c2: Case, nz: int, lz: float, name: Optional[str] = None) -> Case:
     case = Case(name or (c2.name + f"_x{nz}"), 3, lx1, nz * nel2, np.ascontiguousarray(xyz), glo,
                 np.ascontiguousarray(mask), key, d2, np.ascontiguousarray(ub), re=c2.re,
                 end_time=c2.end_time, tol_p=c2.tol_p, tol_v=c2.tol_v)
+    case.ifvcor, case.ifvcor_adjoint = c2.ifvcor, c2.ifvcor_adjoint
     if c2.spng_fun is not None:
         case.spng_fun = np.ascontiguousarray(lift(c2.spng_fun))
     if "mask_adjoint" in c2.extra:
@@ -391,7 +400,7 @@ def extrude(c2: Case, nz: int, lz: float, name: Optional[str] = None) -> Case:
 
 
 def box_case(nex: int, ney: int, lx1: int, *, lxy=(2.0, 1.0), periodic_y=False, outflow=True, deform=0.05,
-             re=40.0, end_time=0.1, seed=0) -> Case:
+             shear=0.0, re=40.0, end_time=0.1, seed=0) -> Case:
     """Small synthetic 2-D channel-like box for unit tests: inflow 'v' at x=0, 'O' (or 'v') at x=L, walls 'W'
     (or periodic) in y, smoothly deformed interior so that all metric terms are exercised; base flow =
     a smooth, not divergence-free, field (parity tests only need a deterministic input)."""
@@ -409,7 +418,7 @@ def box_case(nex: int, ney: int, lx1: int, *, lxy=(2.0, 1.0), periodic_y=False, 
             y0 = lxy[1] * (ey + (z[:, None] + 1) / 2) / ney
             x0, y0 = np.broadcast_arrays(x0, y0)
             sx = np.sin(np.pi * x0 / lxy[0]); sy = np.sin(2 * np.pi * y0 / lxy[1])
-            X[0, e] = x0 + deform * sx * sy * lxy[0] / nex
+            X[0, e] = x0 + deform * sx * sy * lxy[0] / nex + shear * y0
             X[1, e] = y0 + (0.0 if periodic_y else deform * sx * np.sin(np.pi * y0 / lxy[1]) * lxy[1] / ney)
             dirf[e, 3] = ex == 0
             dirf[e, 1] = (ex == nex - 1) and not outflow
@@ -426,5 +435,7 @@ def box_case(nex: int, ney: int, lx1: int, *, lxy=(2.0, 1.0), periodic_y=False, 
     d2 = 1
     while d2 < nex * ney:
         d2 *= 2
-    return Case(f"box{nex}x{ney}", 2, lx1, nex * ney, X, glo, mask, key, d2, U, re=re, end_time=end_time,
+    case = Case(f"box{nex}x{ney}", 2, lx1, nex * ney, X, glo, mask, key, d2, U, re=re, end_time=end_time,
                 tol_p=1e-10, tol_v=1e-10)
+    case.ifvcor = not outflow
+    return case

@@ -1,0 +1,566 @@
+// api.cu -- the extern "C" surface declared in include/nekstab_b200.h.
+#include <cmath>
+#include <cstdarg>
+
+#include "nsb_internal.h"
+
+Ctx* g_ctx = nullptr;
+static char g_err[1024] = "";
+static int g_rank = 0, g_nranks = 1;
+static ncclComm_t g_comm = nullptr;
+static long long g_launches = 0;
+
+void nsb_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void nsb_count_launch(int n) { g_launches += n; if (g_ctx) g_ctx->stats.kernel_launches += n; }
+
+extern "C" const char* nsb_last_error(void) { return g_err; }
+
+#define REQUIRE_CTX()                                              \
+  Ctx* c = g_ctx;                                                  \
+  if (!c) { nsb_set_error("nsb_init has not been called"); return 1; }
+
+template <class T>
+static int dalloc(T** p, long long count) {
+  NSB_CUDA(cudaMalloc((void**)p, std::max<long long>(count, 1) * sizeof(T)));
+  NSB_CUDA(cudaMemset(*p, 0, std::max<long long>(count, 1) * sizeof(T)));
+  return 0;
+}
+static int h2d(Ctx* c, double* d, const double* h, long long n) {
+  NSB_CUDA(cudaMemcpyAsync(d, h, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  return 0;
+}
+static int d2h(Ctx* c, double* h, const double* d, long long n) {
+  NSB_CUDA(cudaMemcpyAsync(h, d, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  NSB_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ communicator
+extern "C" int nsb_comm_unique_id(char id_out[128]) {
+  ncclUniqueId id;
+  NSB_NCCL(ncclGetUniqueId(&id));
+  static_assert(sizeof(ncclUniqueId) <= 128, "ncclUniqueId larger than 128 bytes");
+  memset(id_out, 0, 128);
+  memcpy(id_out, &id, sizeof(id));
+  return 0;
+}
+extern "C" int nsb_comm_init(int rank, int nranks, const char id_in[128], int device) {
+  if (g_comm) { ncclCommDestroy(g_comm); g_comm = nullptr; }
+  g_rank = rank; g_nranks = nranks;
+  if (nranks > 1) {
+    NSB_CUDA(cudaSetDevice(device));
+    ncclUniqueId id;
+    memcpy(&id, id_in, sizeof(id));
+    NSB_NCCL(ncclCommInitRank(&g_comm, nranks, id, rank));
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ setup
+static int setup_masks(Ctx* c, int set, const double* m0, const double* m1, const double* m2) {
+  const double* hm[3] = {m0, m1, m2};
+  for (int d = 0; d < c->ldim; ++d) {
+    NSB_TRY(dalloc(&c->mask[set][d], c->n));
+    NSB_TRY(dalloc(&c->mbinv[set][d], c->n));
+    NSB_TRY(h2d(c, c->mask[set][d], hm[d], c->n));
+    NSB_TRY(vk_copy(c, c->mbinv[set][d], c->mask[set][d], c->n));
+    NSB_TRY(vk_mul(c, c->mbinv[set][d], c->binv, c->n));
+  }
+  NSB_TRY(dalloc(&c->dinvE[set], c->n2));
+  NSB_TRY(ek_ediag(c, set));
+  NSB_TRY(vk_dot3(c, c->dinvE[set], c->dinvE[set], nullptr, c->n2, c->red_out + 9));   // sum diag(E)^2 (scale for the test below)
+  NSB_TRY(vk_inv(c, c->dinvE[set], c->n2));
+  // all-Dirichlet / periodic velocity => E * 1 = 0 [UPSTREAM ifvcor]: test numerically
+  NSB_TRY(vk_fill(c, c->pk[4], 1.0, c->n2));
+  NSB_TRY(ek_gradt(c, c->pk[4], c->wk[2]));
+  NSB_TRY(gs_dssum(c, c->wk[2], c->ldim, c->n, nullptr));
+  double* sc = nullptr;
+  NSB_TRY(dalloc(&sc, c->n * 3));
+  for (int d = 0; d < c->ldim; ++d) NSB_TRY(vk_copy(c, sc + d * c->n, c->mbinv[set][d], c->n));
+  NSB_TRY(ek_div(c, c->wk[2], sc, c->pk[3], 1.0));
+  NSB_TRY(vk_dot3(c, c->pk[3], c->pk[3], nullptr, c->n2, c->red_out + 8));
+  NSB_TRY(vk_allreduce_sum(c, c->red_out + 8, 2));
+  double hv[2];
+  NSB_TRY(d2h(c, hv, c->red_out + 8, 2));
+  cudaFree(sc);
+  // ||E 1|| against ||diag(E)||: O(1e-2) with an outflow boundary, rounding level without
+  c->ifvcor[set] = std::sqrt(hv[0]) < 1e-9 * std::sqrt(hv[1]);
+  return 0;
+}
+
+extern "C" int nsb_finalize(void) {
+  Ctx* c = g_ctx;
+  if (!c) return 0;
+  cudaStreamSynchronize(c->stream);
+  gs_free(c);
+  double* ptrs[] = {c->xyz[0], c->xyz[1], c->xyz[2], c->R, c->jac, c->bm1, c->binv, c->mult, c->bm1s, c->G, c->RW2, c->bm2inv,
+                    c->Rd, c->hdiagA, c->hdiagB, c->dinvH, c->ub, c->spng, c->u, c->ulag[0], c->ulag[1], c->f[0], c->f[1],
+                    c->f[2], c->pr, c->prlag, c->pt, c->wk[0], c->wk[1], c->wk[2], c->wk[3], c->rk, c->pk[0], c->pk[1],
+                    c->pk[2], c->pk[3], c->pk[4], c->red_part, c->red_out, c->slab, c->hbuf, c->hpart};
+  for (double* p : ptrs) if (p) cudaFree(p);
+  for (int s = 0; s < 2; ++s) {
+    if (s == 1 && !c->has_adj_masks) break;
+    for (int d = 0; d < 3; ++d) { if (c->mask[s][d]) cudaFree(c->mask[s][d]); if (c->mbinv[s][d]) cudaFree(c->mbinv[s][d]); }
+    if (c->dinvE[s]) cudaFree(c->dinvE[s]);
+  }
+  if (c->cgs) cudaFree(c->cgs);
+  if (c->cgs_host) cudaFreeHost(c->cgs_host);
+  if (c->red_host) cudaFreeHost(c->red_host);
+  if (c->red_count) cudaFree(c->red_count);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  g_ctx = nullptr;
+  return 0;
+}
+
+extern "C" int nsb_init(int ldim, int lx1, int lxd, int lx2, int nelv, long long nelgv, const double* xm1,
+                        const double* ym1, const double* zm1, const double* v1mask, const double* v2mask,
+                        const double* v3mask, const long long* glo_num, int device) {
+  if (g_ctx) nsb_finalize();
+  if (ldim != 2 && ldim != 3) { nsb_set_error("ldim must be 2 or 3"); return 1; }
+  if (lx2 != lx1 - 2) { nsb_set_error("only the P_N-P_{N-2} formulation (lx2 = lx1-2) is supported, got lx1=%d lx2=%d", lx1, lx2); return 1; }
+  if (lxd != 3 * lx1 / 2) { nsb_set_error("lxd must be 3*lx1/2 (3/2-rule dealiasing), got lx1=%d lxd=%d", lx1, lxd); return 1; }
+  if (lx1 != 4 && lx1 != 6 && lx1 != 8) { nsb_set_error("lx1 must be 4, 6 or 8 (compiled instantiations)"); return 1; }
+  if (nelv <= 0) { nsb_set_error("nelv must be positive"); return 1; }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    nsb_set_error("no CUDA device available (%s): nekstab_b200 has no CPU fallback", cudaGetErrorString(e));
+    return 1;
+  }
+  NSB_CUDA(cudaSetDevice(device));
+  Ctx* c = new Ctx();
+  g_ctx = c;
+  c->device = device;
+  c->ldim = ldim; c->lx1 = lx1; c->lxd = lxd; c->lx2 = lx2; c->nel = nelv; c->nelg = nelgv;
+  c->np1 = (ldim == 3) ? lx1 * lx1 * lx1 : lx1 * lx1;
+  c->np2 = (ldim == 3) ? lx2 * lx2 * lx2 : lx2 * lx2;
+  c->npd = (ldim == 3) ? lxd * lxd * lxd : lxd * lxd;
+  c->n = (long long)nelv * c->np1; c->n2 = (long long)nelv * c->np2; c->nd = (long long)nelv * c->npd;
+  c->n2_glob = nelgv * c->np2;
+  c->vlen = c->n * ldim + c->n2;
+  c->rank = g_rank; c->nranks = g_nranks; c->comm = g_comm;
+  NSB_CUDA(cudaStreamCreate(&c->stream));
+  NSB_CUDA(cudaEventCreate(&c->ev0));
+  NSB_CUDA(cudaEventCreate(&c->ev1));
+  sem_build_constmats(lx1, lx2, lxd, &c->cm);
+  NSB_TRY(ek_upload_constants(c->cm));
+
+  const int D = ldim;
+  const double* hx[3] = {xm1, ym1, zm1};
+  for (int d = 0; d < D; ++d) {
+    if (!hx[d]) { nsb_set_error("coordinate array %d is NULL", d); return 1; }
+    NSB_TRY(dalloc(&c->xyz[d], c->n));
+    NSB_TRY(h2d(c, c->xyz[d], hx[d], c->n));
+  }
+  NSB_TRY(dalloc(&c->R, c->n * D * D));
+  NSB_TRY(dalloc(&c->jac, c->n));
+  NSB_TRY(dalloc(&c->bm1, c->n));
+  NSB_TRY(dalloc(&c->binv, c->n));
+  NSB_TRY(dalloc(&c->mult, c->n));
+  NSB_TRY(dalloc(&c->bm1s, c->n));
+  NSB_TRY(dalloc(&c->G, c->n * (D * (D + 1) / 2)));
+  NSB_TRY(dalloc(&c->RW2, c->n2 * D * D));
+  NSB_TRY(dalloc(&c->bm2inv, c->n2));
+  NSB_TRY(dalloc(&c->Rd, c->nd * D * D));
+  NSB_TRY(dalloc(&c->hdiagA, c->n));
+  NSB_TRY(dalloc(&c->hdiagB, c->n));
+  NSB_TRY(dalloc(&c->dinvH, c->n));
+  long long nred = std::max<long long>(nelv, NSB_MAX_BLOCKS) * NSB_MAX_RED;
+  NSB_TRY(dalloc(&c->red_part, nred));
+  NSB_TRY(dalloc(&c->red_out, NSB_MAX_RED * 4));
+  NSB_TRY(dalloc(&c->red_count, 4));
+  NSB_CUDA(cudaMallocHost((void**)&c->red_host, NSB_MAX_RED * 4 * sizeof(double)));
+  NSB_TRY(dalloc(&c->hbuf, 1 << 16));
+  NSB_TRY(st_alloc(c));
+
+  NSB_TRY(gs_setup(c, glo_num));
+  NSB_TRY(ek_geometry(c));
+  // positive Jacobian check + volumes
+  NSB_TRY(vk_dot3(c, c->bm1, nullptr, nullptr, c->n, c->red_out + 8));
+  NSB_TRY(vk_dot3(c, c->bm2inv, nullptr, nullptr, c->n2, c->red_out + 9));   // bm2inv holds bm2 at this point
+  NSB_TRY(vk_allreduce_sum(c, c->red_out + 8, 2));
+  double hv[2];
+  NSB_TRY(d2h(c, hv, c->red_out + 8, 2));
+  c->vol = hv[0]; c->vol2 = hv[1];
+  if (!(c->vol > 0) || !(c->vol2 > 0)) { nsb_set_error("non-positive mesh volume (%g, %g): check element orientation", c->vol, c->vol2); return 1; }
+  NSB_TRY(vk_inv(c, c->bm2inv, c->n2));
+  // multiplicity, assembled mass and its inverse, assembled diagonal of A
+  NSB_TRY(vk_fill(c, c->mult, 1.0, c->n));
+  NSB_TRY(gs_dssum(c, c->mult, 1, c->n, nullptr));
+  NSB_TRY(vk_inv(c, c->mult, c->n));
+  NSB_TRY(vk_copy(c, c->hdiagB, c->bm1, c->n));
+  NSB_TRY(gs_dssum(c, c->hdiagB, 1, c->n, nullptr));
+  NSB_TRY(vk_copy(c, c->binv, c->hdiagB, c->n));
+  NSB_TRY(vk_inv(c, c->binv, c->n));
+  NSB_TRY(gs_dssum(c, c->hdiagA, 1, c->n, nullptr));
+  NSB_TRY(vk_copy(c, c->bm1s, c->bm1, c->n));
+  if (!v1mask || !v2mask || (D == 3 && !v3mask)) { nsb_set_error("velocity masks must not be NULL"); return 1; }
+  NSB_TRY(setup_masks(c, 0, v1mask, v2mask, v3mask));
+  for (int d = 0; d < 3; ++d) { c->mask[1][d] = c->mask[0][d]; c->mbinv[1][d] = c->mbinv[0][d]; }
+  c->dinvE[1] = c->dinvE[0];
+  c->ifvcor[1] = c->ifvcor[0];
+  c->has_adj_masks = false;
+  NSB_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" int nsb_set_adjoint_masks(const double* m0, const double* m1, const double* m2) {
+  REQUIRE_CTX();
+  if (c->has_adj_masks) {
+    for (int d = 0; d < c->ldim; ++d) { cudaFree(c->mask[1][d]); cudaFree(c->mbinv[1][d]); }
+    cudaFree(c->dinvE[1]);
+    c->has_adj_masks = false;
+  }
+  if (!m0) {
+    for (int d = 0; d < 3; ++d) { c->mask[1][d] = c->mask[0][d]; c->mbinv[1][d] = c->mbinv[0][d]; }
+    c->dinvE[1] = c->dinvE[0];
+    c->ifvcor[1] = c->ifvcor[0];
+    return 0;
+  }
+  for (int d = 0; d < 3; ++d) { c->mask[1][d] = nullptr; c->mbinv[1][d] = nullptr; }
+  c->dinvE[1] = nullptr;
+  NSB_TRY(setup_masks(c, 1, m0, m1, m2));
+  c->has_adj_masks = true;
+  NSB_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" int nsb_set_params(double viscosity, double density, double tol_v, double tol_p, int maxit_v, int maxit_p) {
+  REQUIRE_CTX();
+  if (!(viscosity > 0) || !(density > 0)) { nsb_set_error("viscosity and density must be positive"); return 1; }
+  c->visc = viscosity; c->rho = density; c->tol_v = tol_v; c->tol_p = tol_p;
+  if (maxit_v > 0) c->maxit_v = maxit_v;
+  if (maxit_p > 0) c->maxit_p = maxit_p;
+  return 0;
+}
+extern "C" int nsb_set_weights(const double* bm1s) {
+  REQUIRE_CTX();
+  if (bm1s) NSB_TRY(h2d(c, c->bm1s, bm1s, c->n));
+  else NSB_TRY(vk_copy(c, c->bm1s, c->bm1, c->n));
+  NSB_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+extern "C" int nsb_set_baseflow(const double* u, const double* v, const double* w) {
+  REQUIRE_CTX();
+  if (!c->ub) NSB_TRY(dalloc(&c->ub, c->n * c->ldim));
+  const double* h[3] = {u, v, w};
+  for (int d = 0; d < c->ldim; ++d) {
+    if (!h[d]) { nsb_set_error("base-flow component %d is NULL", d); return 1; }
+    NSB_TRY(h2d(c, c->ub + d * c->n, h[d], c->n));
+  }
+  NSB_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+extern "C" int nsb_set_sponge(const double* spng) {
+  REQUIRE_CTX();
+  if (!spng) {
+    if (c->spng) { cudaFree(c->spng); c->spng = nullptr; }
+    return 0;
+  }
+  if (!c->spng) NSB_TRY(dalloc(&c->spng, c->n));
+  NSB_TRY(h2d(c, c->spng, spng, c->n));
+  NSB_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+extern "C" int nsb_set_timestep(double dt, int nsteps) {
+  REQUIRE_CTX();
+  if (!(dt > 0) || nsteps <= 0) { nsb_set_error("dt and nsteps must be positive"); return 1; }
+  c->dt = dt; c->nsteps = nsteps;
+  return 0;
+}
+extern "C" int nsb_set_ifvcor(int direct, int adjoint) {
+  REQUIRE_CTX();
+  if (direct >= 0) c->ifvcor[0] = direct != 0;
+  if (adjoint >= 0) c->ifvcor[1] = adjoint != 0;
+  else if (!c->has_adj_masks && direct >= 0) c->ifvcor[1] = c->ifvcor[0];
+  return 0;
+}
+extern "C" int nsb_prepare_linearized_solver(double end_time, double cfl_target, double* dt, int* nsteps, double* ctarg) {
+  REQUIRE_CTX();
+  if (!c->ub) { nsb_set_error("base flow not set"); return 1; }
+  if (cfl_target > 1.0) cfl_target = 0.5;   // core/matvec.f:21-24
+  NSB_TRY(ek_cfl(c, c->ub, c->red_out + 8));
+  NSB_TRY(vk_allreduce_max(c, c->red_out + 8, 1));
+  double ct;
+  NSB_TRY(d2h(c, &ct, c->red_out + 8, 1));
+  if (!(ct > 0)) { nsb_set_error("compute_cfl returned %g", ct); return 1; }
+  double dt0 = cfl_target / ct;
+  int ns = (int)std::ceil(end_time / dt0);
+  c->dt = end_time / ns; c->nsteps = ns;
+  if (dt) *dt = c->dt;
+  if (nsteps) *nsteps = ns;
+  if (ctarg) *ctarg = ct;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ vectors
+#define CHECK_SLOT(s)                                                                     \
+  if ((s) < 0 || (s) >= c->nslots) { nsb_set_error("slot %d out of range [0,%d)", (s), c->nslots); return 1; }
+
+extern "C" int nsb_vec_alloc(int nslots) {
+  REQUIRE_CTX();
+  if (nslots <= 0) { nsb_set_error("nslots must be positive"); return 1; }
+  if (c->slab) cudaFree(c->slab);
+  c->slab = nullptr;
+  NSB_TRY(dalloc(&c->slab, (long long)nslots * c->vlen));
+  c->nslots = nslots;
+  return 0;
+}
+extern "C" int nsb_vec_upload(int slot, const double* vx, const double* vy, const double* vz, const double* pr) {
+  REQUIRE_CTX(); CHECK_SLOT(slot);
+  double* v = slot_ptr(c, slot);
+  const double* h[3] = {vx, vy, vz};
+  for (int d = 0; d < c->ldim; ++d) {
+    if (!h[d]) { nsb_set_error("vec_upload: component %d is NULL", d); return 1; }
+    NSB_TRY(h2d(c, v + d * c->n, h[d], c->n));
+  }
+  if (pr) NSB_TRY(h2d(c, v + c->ldim * c->n, pr, c->n2));
+  else NSB_TRY(vk_fill(c, v + c->ldim * c->n, 0.0, c->n2));
+  NSB_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+extern "C" int nsb_vec_download(int slot, double* vx, double* vy, double* vz, double* pr) {
+  REQUIRE_CTX(); CHECK_SLOT(slot);
+  double* v = slot_ptr(c, slot);
+  double* h[3] = {vx, vy, vz};
+  for (int d = 0; d < c->ldim; ++d)
+    if (h[d]) NSB_TRY(d2h(c, h[d], v + d * c->n, c->n));
+  if (pr) NSB_TRY(d2h(c, pr, v + c->ldim * c->n, c->n2));
+  return 0;
+}
+extern "C" int nsb_vec_copy(int dst, int src) {
+  REQUIRE_CTX(); CHECK_SLOT(dst); CHECK_SLOT(src);
+  if (dst != src) NSB_TRY(vk_copy(c, slot_ptr(c, dst), slot_ptr(c, src), c->vlen));
+  return 0;
+}
+extern "C" int nsb_vec_zero(int slot) { REQUIRE_CTX(); CHECK_SLOT(slot); return vk_fill(c, slot_ptr(c, slot), 0.0, c->vlen); }
+extern "C" int nsb_vec_cmult(int slot, double a) { REQUIRE_CTX(); CHECK_SLOT(slot); return vk_scale(c, slot_ptr(c, slot), a, c->vlen); }
+extern "C" int nsb_vec_add2(int p, int q) { REQUIRE_CTX(); CHECK_SLOT(p); CHECK_SLOT(q); return vk_axpy(c, slot_ptr(c, p), 1.0, slot_ptr(c, q), c->vlen); }
+extern "C" int nsb_vec_sub2(int p, int q) { REQUIRE_CTX(); CHECK_SLOT(p); CHECK_SLOT(q); return vk_axpy(c, slot_ptr(c, p), -1.0, slot_ptr(c, q), c->vlen); }
+
+extern "C" int nsb_vec_inner_product(int p, int q, double* alpha) {
+  REQUIRE_CTX(); CHECK_SLOT(p); CHECK_SLOT(q);
+  NSB_TRY(vk_multidot(c, 1, q, p, c->hbuf));
+  NSB_TRY(d2h(c, alpha, c->hbuf, 1));
+  if (std::isnan(*alpha)) { nsb_set_error("krylov_inner_product: NaN (core/krylov_subspace.f:53 -> nek_end)"); return 2; }
+  return 0;
+}
+extern "C" int nsb_vec_norm(int p, double* alpha) {
+  NSB_TRY(nsb_vec_inner_product(p, p, alpha));
+  *alpha = std::sqrt(*alpha);
+  return 0;
+}
+extern "C" int nsb_vec_normalize(int p, double* alpha) {
+  NSB_TRY(nsb_vec_norm(p, alpha));
+  return nsb_vec_cmult(p, 1.0 / *alpha);
+}
+extern "C" int nsb_basis_gemv(int k, int first, const double* y, int out) {
+  REQUIRE_CTX(); CHECK_SLOT(first); CHECK_SLOT(first + k - 1); CHECK_SLOT(out);
+  if (out >= first && out < first + k) { nsb_set_error("basis_gemv: output slot inside the basis range"); return 1; }
+  NSB_TRY(h2d(c, c->hbuf, y, k));
+  return vk_gemv_out(c, k, first, c->hbuf, out);
+}
+extern "C" int nsb_basis_gemv_complex(int k, int first, const double* yre, const double* yim, int sre, int sim) {
+  NSB_TRY(nsb_basis_gemv(k, first, yre, sre));
+  return nsb_basis_gemv(k, first, yim, sim);
+}
+extern "C" int nsb_basis_rotate(int k, int first, const double* S, int lds) {
+  REQUIRE_CTX(); CHECK_SLOT(first); CHECK_SLOT(first + k - 1);
+  double* dS = nullptr;
+  NSB_TRY(dalloc(&dS, (long long)lds * k));
+  NSB_TRY(h2d(c, dS, S, (long long)lds * k));
+  int rc = vk_rotate(c, k, first, dS, lds);
+  cudaStreamSynchronize(c->stream);
+  cudaFree(dS);
+  return rc;
+}
+extern "C" int nsb_orthonormalize(int k, int first, int slot_f, double* hcol) {
+  REQUIRE_CTX(); CHECK_SLOT(first); CHECK_SLOT(first + k - 1); CHECK_SLOT(slot_f);
+  if (k + 1 > (1 << 15)) { nsb_set_error("orthonormalize: k too large"); return 1; }
+  double* h1 = c->hbuf;
+  double* h2 = c->hbuf + (1 << 15);
+  std::vector<double> a(k), b(k);
+  NSB_TRY(vk_multidot(c, k, first, slot_f, h1));            // h1 = Q^T W f
+  NSB_TRY(vk_multiaxpy(c, k, first, slot_f, h1, -1.0));     // f -= Q h1
+  NSB_TRY(vk_multidot(c, k, first, slot_f, h2));            // re-orthogonalisation (DGKS)
+  NSB_TRY(vk_multiaxpy(c, k, first, slot_f, h2, -1.0));
+  NSB_TRY(d2h(c, a.data(), h1, k));
+  NSB_TRY(d2h(c, b.data(), h2, k));
+  for (int i = 0; i < k; ++i) {
+    hcol[i] = a[i] + b[i];
+    if (std::isnan(hcol[i])) { nsb_set_error("orthonormalize: NaN coefficient"); return 2; }
+  }
+  return nsb_vec_normalize(slot_f, &hcol[k]);
+}
+
+// ------------------------------------------------------------------------------------------ matvec
+extern "C" int nsb_matvec(int mode, int sin, int sout) {
+  REQUIRE_CTX(); CHECK_SLOT(sin); CHECK_SLOT(sout);
+  if (sin == sout) { nsb_set_error("matvec: input and output slots must differ"); return 1; }
+  double* q = slot_ptr(c, sin);
+  double* f = slot_ptr(c, sout);
+  switch (mode) {
+    case NSB_DIRECT: return st_linearized_map(c, 0, q, f);
+    case NSB_ADJOINT: return st_linearized_map(c, 1, q, f);
+    case NSB_DIRECT_ADJOINT: {                       // transient_growth_map: core/matvec.f:332-349
+      NSB_TRY(st_linearized_map(c, 0, q, f));
+      // wrk lives in the stepper's own state: copy f to a scratch vector first
+      double* tmp = nullptr;
+      NSB_TRY(dalloc(&tmp, c->vlen));
+      NSB_TRY(vk_copy(c, tmp, f, c->vlen));
+      int rc = st_linearized_map(c, 1, tmp, f);
+      cudaStreamSynchronize(c->stream);
+      cudaFree(tmp);
+      return rc;
+    }
+    case NSB_NEWTON:                                 // (exp(TL) - I) q : core/matvec.f:397-400
+      NSB_TRY(st_linearized_map(c, 0, q, f));
+      return vk_axpy(c, f, -1.0, q, c->vlen);
+    case NSB_FORCE_SENS:                             // (I - exp(TL+)) q : core/matvec.f:366-371
+      NSB_TRY(st_linearized_map(c, 1, q, f));
+      NSB_TRY(vk_axpy(c, f, -1.0, q, c->vlen));
+      return vk_scale(c, f, -1.0, c->vlen);
+  }
+  nsb_set_error("matvec: unknown mode %d", mode);
+  return 1;
+}
+
+extern "C" int nsb_get_stats(nsb_stats* out, int reset) {
+  REQUIRE_CTX();
+  if (out) *out = c->stats;
+  if (reset) c->stats = nsb_stats{0, 0, 0, 0, 0.0};
+  return 0;
+}
+extern "C" long long nsb_n(void) { return g_ctx ? g_ctx->n : 0; }
+extern "C" long long nsb_n2(void) { return g_ctx ? g_ctx->n2 : 0; }
+
+// ------------------------------------------------------------------------------------------ operator-level entry points
+extern "C" int nsb_op_axhelm(const double* u, double h1, double h2, double* w) {
+  REQUIRE_CTX();
+  NSB_TRY(h2d(c, c->wk[0], u, c->n));
+  NSB_TRY(ek_axhelm(c, c->wk[0], c->wk[1], 1, h1, h2));
+  return d2h(c, w, c->wk[1], c->n);
+}
+extern "C" int nsb_op_dssum(double* u) {
+  REQUIRE_CTX();
+  NSB_TRY(h2d(c, c->wk[0], u, c->n));
+  NSB_TRY(gs_dssum(c, c->wk[0], 1, c->n, nullptr));
+  return d2h(c, u, c->wk[0], c->n);
+}
+extern "C" int nsb_op_glsc3(const double* a, const double* b, const double* w, double* out) {
+  REQUIRE_CTX();
+  NSB_TRY(h2d(c, c->wk[0], a, c->n));
+  NSB_TRY(h2d(c, c->wk[0] + c->n, b, c->n));
+  NSB_TRY(h2d(c, c->wk[1], w, c->n));
+  NSB_TRY(vk_dot3(c, c->wk[0], c->wk[0] + c->n, c->wk[1], c->n, c->red_out + 8));
+  NSB_TRY(vk_allreduce_sum(c, c->red_out + 8, 1));
+  return d2h(c, out, c->red_out + 8, 1);
+}
+extern "C" int nsb_op_opgradt(const double* p, double* wx, double* wy, double* wz) {
+  REQUIRE_CTX();
+  NSB_TRY(h2d(c, c->pk[4], p, c->n2));
+  NSB_TRY(ek_gradt(c, c->pk[4], c->wk[0]));
+  double* h[3] = {wx, wy, wz};
+  for (int d = 0; d < c->ldim; ++d) NSB_TRY(d2h(c, h[d], c->wk[0] + d * c->n, c->n));
+  return 0;
+}
+extern "C" int nsb_op_opdiv(const double* ux, const double* uy, const double* uz, double* q) {
+  REQUIRE_CTX();
+  const double* h[3] = {ux, uy, uz};
+  for (int d = 0; d < c->ldim; ++d) NSB_TRY(h2d(c, c->wk[0] + d * c->n, h[d], c->n));
+  NSB_TRY(ek_div(c, c->wk[0], nullptr, c->pk[4], 1.0));
+  return d2h(c, q, c->pk[4], c->n2);
+}
+extern "C" int nsb_op_cdabdtp(const double* p, double* ep) {
+  REQUIRE_CTX();
+  NSB_TRY(h2d(c, c->pk[4], p, c->n2));
+  NSB_TRY(ek_gradt(c, c->pk[4], c->wk[2]));
+  NSB_TRY(gs_dssum(c, c->wk[2], c->ldim, c->n, nullptr));
+  for (int d = 0; d < c->ldim; ++d) NSB_TRY(vk_mul(c, c->wk[2] + d * c->n, c->mbinv[0][d], c->n));
+  NSB_TRY(ek_div(c, c->wk[2], nullptr, c->pk[3], 1.0));
+  return d2h(c, ep, c->pk[3], c->n2);
+}
+extern "C" int nsb_op_advab(int adjoint, const double* upx, const double* upy, const double* upz, double* fx, double* fy,
+                            double* fz) {
+  REQUIRE_CTX();
+  if (!c->ub) { nsb_set_error("base flow not set"); return 1; }
+  const double* h[3] = {upx, upy, upz};
+  for (int d = 0; d < c->ldim; ++d) NSB_TRY(h2d(c, c->wk[0] + d * c->n, h[d], c->n));
+  NSB_TRY(ek_advab(c, adjoint, c->wk[0], c->ub, c->spng, c->wk[1]));
+  NSB_TRY(vk_scale(c, c->wk[1], -1.0, c->n * c->ldim));    // report +B[...] (+ sponge term) like advabp's ta arrays
+  double* o[3] = {fx, fy, fz};
+  for (int d = 0; d < c->ldim; ++d) NSB_TRY(d2h(c, o[d], c->wk[1] + d * c->n, c->n));
+  return 0;
+}
+extern "C" int nsb_op_hmholtz(double* ux, double* uy, double* uz, const double* rx, const double* ry, const double* rz,
+                              double h1, double h2, int* iters) {
+  REQUIRE_CTX();
+  const double* h[3] = {rx, ry, rz};
+  for (int d = 0; d < c->ldim; ++d) NSB_TRY(h2d(c, c->rk + d * c->n, h[d], c->n));
+  NSB_TRY(gs_dssum(c, c->rk, c->ldim, c->n, nullptr));
+  NSB_TRY(vk_mask_fields(c, c->rk, 0));
+  NSB_TRY(st_helmholtz(c, 0, h1, h2, iters));
+  double* o[3] = {ux, uy, uz};
+  for (int d = 0; d < c->ldim; ++d) NSB_TRY(d2h(c, o[d], c->wk[3] + d * c->n, c->n));
+  return 0;
+}
+extern "C" int nsb_op_esolver(const double* gin, double* phi, int* iters) {
+  REQUIRE_CTX();
+  NSB_TRY(h2d(c, c->pk[0], gin, c->n2));
+  NSB_TRY(st_pressure(c, 0, iters));
+  return d2h(c, phi, c->pk[1], c->n2);
+}
+extern "C" int nsb_op_cfl(const double* ux, const double* uy, const double* uz, double dt, double* cfl) {
+  REQUIRE_CTX();
+  const double* h[3] = {ux, uy, uz};
+  for (int d = 0; d < c->ldim; ++d) NSB_TRY(h2d(c, c->wk[0] + d * c->n, h[d], c->n));
+  NSB_TRY(ek_cfl(c, c->wk[0], c->red_out + 8));
+  NSB_TRY(vk_allreduce_max(c, c->red_out + 8, 1));
+  NSB_TRY(d2h(c, cfl, c->red_out + 8, 1));
+  *cfl *= dt;
+  return 0;
+}
+extern "C" int nsb_get_field(const char* name, double* out, long long* count) {
+  REQUIRE_CTX();
+  std::string s(name);
+  const double* src = nullptr;
+  long long cnt = c->n;
+  bool invert = false;
+  if (s == "bm1") src = c->bm1;
+  else if (s == "binvm1") src = c->binv;
+  else if (s == "jacm1") src = c->jac;
+  else if (s == "vmult") src = c->mult;
+  else if (s == "bm1s") src = c->bm1s;
+  else if (s == "hdiagA") src = c->hdiagA;
+  else if (s == "bm2") { src = c->bm2inv; cnt = c->n2; invert = true; }
+  else if (s == "ediag") { src = c->dinvE[0]; cnt = c->n2; invert = true; }
+  else if (s == "ediag_adj") { src = c->dinvE[1]; cnt = c->n2; invert = true; }
+  else if (s.size() == 2 && s[0] == 'g' && s[1] >= '1' && s[1] <= '6') {
+    int q = s[1] - '1';
+    if (q >= c->ldim * (c->ldim + 1) / 2) { nsb_set_error("get_field: %s not defined in %dD", name, c->ldim); return 1; }
+    src = c->G + (long long)q * c->n;
+  } else if (s == "ifvcor") {
+    if (out) out[0] = c->ifvcor[0] ? 1.0 : 0.0;
+    if (count) *count = 1;
+    return 0;
+  } else if (s == "vol") {
+    if (out) { out[0] = c->vol; }
+    if (count) *count = 1;
+    return 0;
+  }
+  if (!src) { nsb_set_error("get_field: unknown field '%s'", name); return 1; }
+  if (count) *count = cnt;
+  if (out) {
+    NSB_TRY(d2h(c, out, src, cnt));
+    if (invert) for (long long i = 0; i < cnt; ++i) out[i] = 1.0 / out[i];
+  }
+  return 0;
+}

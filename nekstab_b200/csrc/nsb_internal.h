@@ -1,0 +1,222 @@
+// nsb_internal.h -- process-wide context and launcher declarations of the nekstab_b200 CUDA library.
+#pragma once
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/nekstab_b200.h"
+
+#define NSB_MAXD 3
+#define NSB_MAX_RED 16          // scalars per reduction
+#define NSB_MAX_BLOCKS 4096     // upper bound on reduction grid sizes
+
+void nsb_set_error(const char* fmt, ...);
+
+#define NSB_CUDA(call)                                                                   \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess) {                                                             \
+      nsb_set_error("%s:%d CUDA error: %s (%s)", __FILE__, __LINE__, cudaGetErrorString(e_), #call); \
+      return 1;                                                                          \
+    }                                                                                    \
+  } while (0)
+#define NSB_NCCL(call)                                                                   \
+  do {                                                                                   \
+    ncclResult_t r_ = (call);                                                            \
+    if (r_ != ncclSuccess) {                                                             \
+      nsb_set_error("%s:%d NCCL error: %s (%s)", __FILE__, __LINE__, ncclGetErrorString(r_), #call); \
+      return 1;                                                                          \
+    }                                                                                    \
+  } while (0)
+#define NSB_TRY(call)          \
+  do {                         \
+    int r__ = (call);          \
+    if (r__) return r__;       \
+  } while (0)
+
+// Small dense SEM matrices, packed row-major with their true sizes (template sizes in kernels).
+struct ConstMats {
+  double D[144], Dt[144];                               // lx1 x lx1 derivative and transpose
+  double J12[120], J12t[120], D12[120], D12t[120];      // lx2 x lx1 (t: lx1 x lx2)
+  double Jd[216], Jdt[216], Dd[216], Ddt[216];          // lxd x lx1 (t: lx1 x lxd)
+  double w1[12], w2[12], wd[18];
+  double z1[12];
+};
+
+// Device-resident state of one conjugate-gradient recurrence (one per solved component).
+struct CGState {
+  double rtz1, rtz2, rho, alpha, beta, rnorm;
+  double tol, vol;
+  int iter, done, maxit, pad;
+};
+
+// Gather-scatter map (dssum): CSR segments of local copies of each shared node + halo lists.
+struct GSMap {
+  int nseg = 0;              // segments written back (local multiplicity > 1 or shared with another rank)
+  int* seg_off = nullptr;    // [nseg+1] into seg_idx
+  int* seg_idx = nullptr;    // local dof indices
+  // halo (multi-rank)
+  int nnbr = 0;
+  std::vector<int> nbr_rank, nbr_off;   // neighbour ranks, offsets into send/recv buffers (in shared nodes)
+  int nshared = 0;           // total entries of the send (= recv) buffer per field
+  int* send_seg = nullptr;   // [nshared] segment whose local sum goes to this send entry
+  int* rseg_off = nullptr;   // [nseg+1] into rseg_pos: recv-buffer positions contributing to a segment
+  int* rseg_pos = nullptr;
+  int* rseg_nbefore = nullptr;  // [nseg] how many of those come from lower ranks (summed before the local part)
+  double* sendbuf = nullptr; // [3*nshared]
+  double* recvbuf = nullptr;
+};
+
+struct Ctx {
+  int ldim = 0, lx1 = 0, lxd = 0, lx2 = 0, nel = 0;
+  long long nelg = 0;
+  int np1 = 0, np2 = 0, npd = 0;
+  long long n = 0, n2 = 0, nd = 0;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int rank = 0, nranks = 1;
+  ncclComm_t comm = nullptr;
+  ConstMats cm;
+
+  // geometry
+  double* xyz[3] = {nullptr, nullptr, nullptr};
+  double* R = nullptr;      // [d*d][n]    J*dr_i/dx_c at (i*d+c)
+  double* jac = nullptr;
+  double* bm1 = nullptr;
+  double* binv = nullptr;   // 1/dssum(bm1)
+  double* mult = nullptr;   // 1/multiplicity
+  double* bm1s = nullptr;   // inner-product weight
+  double* G = nullptr;      // [ng][n]  3D: 11,22,33,12,13,23 ; 2D: 11,22,12
+  double* mask[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};     // [adjoint?][comp]
+  double* mbinv[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};    // mask*binv
+  bool has_adj_masks = false;
+  double* RW2 = nullptr;    // [d*d][n2]  w2 * R interpolated to mesh 2
+  double* bm2inv = nullptr; // 1/bm2
+  double* Rd = nullptr;     // [d*d][nd]  wd * R interpolated to the dealiasing mesh
+  double* hdiagA = nullptr; // assembled diag of stiffness A
+  double* hdiagB = nullptr; // assembled bm1
+  double* dinvH = nullptr;  // 1/(h1*hdiagA + h2*hdiagB) for the current h2
+  double dinvH_h1 = -1, dinvH_h2 = -1;
+  double* dinvE[2] = {nullptr, nullptr};
+  double vol = 0, vol2 = 0;
+  long long n2_glob = 0;
+  bool ifvcor[2] = {false, false};
+  GSMap gs;
+
+  // parameters
+  double visc = 1.0, rho = 1.0, tol_v = 1e-9, tol_p = 1e-7;
+  int maxit_v = 1000, maxit_p = 20000;
+  double dt = 0;
+  int nsteps = 0;
+  int check_every_v = 4, check_every_p = 32;
+
+  // base flow, sponge
+  double* ub = nullptr;     // [d][n]
+  double* spng = nullptr;   // [n] or null
+
+  // stepper state (all device)
+  double* u = nullptr;      // [d][n]
+  double* ulag[2] = {nullptr, nullptr};
+  double* f[3] = {nullptr, nullptr, nullptr};   // explicit terms ring: f[0] current
+  double* pr = nullptr;     // [n2]
+  double* prlag = nullptr;
+  double* pt = nullptr;     // extrapolated pressure
+  double* wk[4] = {nullptr, nullptr, nullptr, nullptr};  // [d][n] work: rhs/residual, cg p, cg w, cg x
+  double* rk = nullptr;     // [d][n] cg r
+  double* pk[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // [n2] work: g/r, x, p, Ep, spare
+  CGState* cgs = nullptr;   // [4] device: 3 Helmholtz comps + pressure
+  CGState* cgs_host = nullptr;  // pinned
+
+  // reductions
+  double* red_part = nullptr;   // [NSB_MAX_BLOCKS*NSB_MAX_RED]
+  double* red_out = nullptr;    // [NSB_MAX_RED*4] device results
+  double* red_host = nullptr;   // pinned host copy
+  unsigned* red_count = nullptr;
+
+  // krylov slab
+  double* slab = nullptr;
+  int nslots = 0;
+  long long vlen = 0;       // d*n + n2
+  double* hbuf = nullptr;   // device coefficient buffer (>= 4096 doubles)
+  double* hpart = nullptr;  // partial multi-dot sums
+  long long hpart_cap = 0;
+
+  // stats
+  nsb_stats stats = {0, 0, 0, 0, 0.0};
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+extern Ctx* g_ctx;
+inline double* slot_ptr(Ctx* c, int s) { return c->slab + (long long)s * c->vlen; }
+
+// ---- host SEM (sem_host.cpp)
+void sem_zwgll(int n, double* z, double* w);
+void sem_zwgl(int n, double* z, double* w);
+void sem_deriv(int n, const double* x, double* D);                                // row-major D[i*n+l]
+void sem_interp(int nto, const double* xto, int nfrom, const double* xfrom, double* J);  // J[i*nfrom+l]
+void sem_build_constmats(int lx1, int lx2, int lxd, ConstMats* cm);
+
+// ---- gather-scatter (gs.cu)
+int gs_setup(Ctx* c, const long long* glo_num);
+int gs_free(Ctx* c);
+int gs_dssum(Ctx* c, double* u, int nfields, long long stride, const CGState* skip_if_done = nullptr);
+
+// ---- element kernels (elem_kernels.cu)
+int ek_upload_constants(const ConstMats& cm);
+int ek_geometry(Ctx* c);                      // metrics, G, bm1, mesh-2 and fine metrics, diag(A)
+int ek_axhelm(Ctx* c, const double* u, double* w, int nfields, double h1, double h2);
+// r[c] = b[c] + r[c] - (h1 A + h2 B) u[c]   (residual assembly of cresvipp)
+int ek_axhelm_resid(Ctx* c, const double* u, const double* b, double* r, int nfields, double h1, double h2);
+int ek_gradt(Ctx* c, const double* p, double* w);                       // w[d][n] = D^T p
+int ek_div(Ctx* c, const double* u, const double* scale /*[d][n] or null*/, double* q, double sign);
+int ek_advab(Ctx* c, int adjoint, const double* up, const double* ub, const double* spng, double* f);  // f = -adv - bm1*spng*up
+int ek_ediag(Ctx* c, int adj);
+int ek_cfl(Ctx* c, const double* u, double* cfl_dev);                  // max reduction into device scalar
+// CG building blocks
+int ek_hcg_dir_ax(Ctx* c, int ncomp, double h1, double h2);     // p = dinv r + beta p; w = H p; rho partial = sum p*w
+int ek_pcg_dir_gradt(Ctx* c, int adj);                           // p = dinvE r + beta p ; w = gradt(p)
+int ek_pcg_div(Ctx* c, int adj);                                 // Ep = div(mbinv w); rho = sum p Ep
+
+// ---- pointwise / reduction kernels (vec_kernels.cu)
+int vk_fill(Ctx* c, double* a, double v, long long n);
+int vk_copy(Ctx* c, double* dst, const double* src, long long n);
+int vk_scale(Ctx* c, double* a, double s, long long n);
+int vk_axpy(Ctx* c, double* y, double a, const double* x, long long n);        // y += a x
+int vk_mul(Ctx* c, double* a, const double* b, long long n);                     // a *= b
+int vk_inv(Ctx* c, double* a, long long n);                                      // a = 1/a
+int vk_lin2(Ctx* c, double* out, double a, const double* x, double b, const double* y, long long n);  // out = a x + b y
+int vk_sum(Ctx* c, const double* a, long long n, double* out_dev);               // deterministic sum -> device scalar
+int vk_dot3(Ctx* c, const double* a, const double* b, const double* w, long long n, double* out_dev);  // sum a*b*w (w may be null)
+int vk_allreduce_sum(Ctx* c, double* dev, int count);
+int vk_allreduce_max(Ctx* c, double* dev, int count);
+int vk_add_scalar_from_dev(Ctx* c, double* a, const double* s_dev, double factor, long long n);  // a += factor * (*s_dev)
+// stepper pointwise
+int vk_make_rhs(Ctx* c, double* b, int k, const double* ab, const double* bd);   // EXT/BDF assembly
+int vk_mask_fields(Ctx* c, double* r, int adj);                                   // r[c] *= mask[c]
+int vk_press_extrap(Ctx* c, int k);
+int vk_final_update(Ctx* c, int adj, double h2);   // u = u + du + mbinv*w ; p = pt + h2*phi
+// CG pointwise pieces
+int vk_hcg_init(Ctx* c, int ncomp);
+int vk_hcg_update(Ctx* c, int ncomp, int adj);
+int vk_pcg_init(Ctx* c, int adj);
+int vk_pcg_update(Ctx* c, int adj);
+int vk_dinvH(Ctx* c, double h1, double h2);
+// krylov
+int vk_multidot(Ctx* c, int k, int first_slot, int slot_f, double* h_dev);      // h = Q^T (W f)
+int vk_multiaxpy(Ctx* c, int k, int first_slot, int slot_f, const double* h_dev, double sign);  // f += sign * Q h
+int vk_gemv_out(Ctx* c, int k, int first_slot, const double* y_dev, int slot_out);
+int vk_rotate(Ctx* c, int k, int first_slot, const double* S_dev, int lds);
+
+// ---- solvers / stepper (stepper.cu)
+int st_alloc(Ctx* c);
+int st_helmholtz(Ctx* c, int adj, double h1, double h2, int* iters);   // solves for wk[3] (x) from rk (r, assembled+masked)
+int st_pressure(Ctx* c, int adj, int* iters);                          // solves E pk[1] = pk[0]
+int st_linearized_map(Ctx* c, int adjoint, const double* vin, double* vout);   // vin/vout device krylov vectors
+
+// ---- host krylov (host_krylov.cpp)
+void nsb_count_launch(int n = 1);

@@ -39,7 +39,7 @@ def prepare_linearized_solver(sem: SEM, ubase, end_time, cfl_target=0.5):
 
 class LinearizedStepper:
     def __init__(self, sem: SEM, ubase, re, spng_fun=None, tol_v=1e-9, tol_p=1e-7, solver="direct",
-                 max_iter_v=1000, max_iter_p=20000):
+                 max_iter_v=1000, max_iter_p=20000, ifvcor=None):
         self.s = sem
         d = sem.ldim
         self.ub = ubase.reshape((d,) + sem.eshape)
@@ -49,8 +49,11 @@ class LinearizedStepper:
         self.solver = solver
         self.max_iter_v, self.max_iter_p = max_iter_v, max_iter_p
         # all-Dirichlet/periodic velocity => E has the constant null vector [UPSTREAM ifvcor / ortho]
-        e1 = sem.cdabdtp(np.ones(sem.eshape2))
-        self.ifvcor = bool(np.abs(e1).max() < 1e-9 * np.abs(sem.w32).max())
+        # Nek decides from the boundary conditions; pass it when known, else test ||E 1|| numerically
+        if ifvcor is None:
+            e1 = sem.cdabdtp(np.ones(sem.eshape2))
+            ifvcor = bool(np.linalg.norm(e1) < 1e-9 * np.linalg.norm(sem.e_diag()))
+        self.ifvcor = bool(ifvcor)
         self._lu_h = {}
         self._lu_e = None
         self._ediag = None

@@ -1,0 +1,120 @@
+"""GPU parity tests, matvec level: the whole linearised-map (direct, adjoint, composite modes) against the
+oracle with solver-converged steps; north-star tolerance 1e-10 relative L2 per matvec (tight solver tolerances,
+no residual projection -- SURVEY.md 7 'parity under iterative solvers')."""
+import numpy as np
+import pytest
+
+from util import make_oracle, rel, small_cases, smooth_field
+
+pytestmark = pytest.mark.gpu
+CASES = small_cases()
+NAMES = ["box2d_n6_outflow", "box2d_n8_dirichlet", "box3d_n8_outflow", "box3d_n6_dirichlet", "box2d_n4_periodic"]
+
+
+def energy_rel(s, a, b):
+    d = a - b
+    num = sum(np.sum(d[k] ** 2 * s.bm1) for k in range(s.ldim))
+    den = sum(np.sum(b[k] ** 2 * s.bm1) for k in range(s.ldim))
+    return float(np.sqrt(num / den))
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_linearized_maps(name):
+    from nekstab_b200 import lib
+    from oracle.stepper import LinearizedStepper
+    c = CASES[name]
+    s = make_oracle(c)
+    g = lib.NekStabB200(c)
+    try:
+        nsteps, dt = 6, 2.0e-3
+        g.set_params(1.0 / c.re, 1.0, 1e-13, 1e-13, 3000, 100000)
+        g.set_timestep(dt, nsteps)
+        g.vec_alloc(4)
+        st = LinearizedStepper(s, c.ubase, c.re, c.spng_fun, solver="direct", ifvcor=c.ifvcor)
+        v0 = smooth_field(c, 21).reshape((c.ldim,) + s.eshape)
+        rng = np.random.default_rng(5)
+        p0 = 0.1 * rng.standard_normal(s.eshape2)
+        g.vec_upload(0, v0, p0)
+        for mode, adj in ((lib.DIRECT, False), (lib.ADJOINT, True)):
+            g.matvec(mode, 0, 1)
+            v, p = g.vec_download(1)
+            vo, po = st.linearized_map(v0, p0, nsteps, dt, adjoint=adj)
+            e = energy_rel(s, v.reshape(vo.shape), vo)
+            assert e < 1e-10, (name, mode, e)
+            pe = rel(p, po)
+            assert pe < 1e-7, (name, mode, pe)
+        # composite maps (core/matvec.f:332-402)
+        g.matvec(lib.DIRECT_ADJOINT, 0, 1)
+        v, p = g.vec_download(1)
+        v1, p1 = st.linearized_map(v0, p0, nsteps, dt, adjoint=False)
+        v2, p2 = st.linearized_map(v1, p1, nsteps, dt, adjoint=True)
+        assert energy_rel(s, v.reshape(v2.shape), v2) < 1e-10
+        g.matvec(lib.NEWTON, 0, 1)
+        v, p = g.vec_download(1)
+        assert energy_rel(s, v.reshape(v1.shape), v1 - v0) < 1e-9
+        st_ = g.stats()
+        assert st_["steps"] == 5 * nsteps and st_["kernel_launches"] > 0
+    finally:
+        g.close()
+
+
+def test_krylov_vector_algebra_and_arnoldi():
+    """krylov_* algebra, update_hessenberg_matrix (twice-MGS in the reference vs DGKS here) and
+    arnoldi_factorization: H and the basis against an oracle Arnoldi that uses the oracle stepper."""
+    from nekstab_b200 import lib
+    from oracle.krylov import arnoldi_factorization
+    from oracle.stepper import LinearizedStepper
+    c = CASES["box2d_n6_outflow"]
+    s = make_oracle(c)
+    g = lib.NekStabB200(c)
+    try:
+        nsteps, dt, k = 4, 2.5e-3, 5
+        g.set_params(1.0 / c.re, 1.0, 1e-13, 1e-13, 3000, 100000)
+        g.set_timestep(dt, nsteps)
+        g.vec_alloc(k + 3)
+        bm1s = s.bm1 * (c.spng_fun.reshape(s.eshape) == 0)
+        st = LinearizedStepper(s, c.ubase, c.re, c.spng_fun, solver="direct", ifvcor=c.ifvcor)
+        v0 = smooth_field(c, 33).reshape((c.ldim,) + s.eshape)
+        p0 = np.zeros(s.eshape2)
+        g.vec_upload(0, v0, p0)
+        nrm = g.normalize(0)
+        ref_nrm = np.sqrt(sum(np.sum(v0[d] ** 2 * bm1s) for d in range(c.ldim)))
+        assert abs(nrm - ref_nrm) < 1e-12 * ref_nrm
+        # algebra
+        g.vec_copy(1, 0); g.vec_cmult(1, 2.5); g.vec_add2(1, 0); g.vec_sub2(1, 0)
+        assert abs(g.inner_product(1, 0) - 2.5) < 1e-12
+        g.vec_zero(1)
+        assert g.norm(1) == 0.0
+        H = np.zeros((k + 1, k), order="F")
+        g.arnoldi_factorization(lib.DIRECT, 0, H, 1, k, k)
+
+        def mv(q):
+            return st.linearized_map(q[0], q[1], nsteps, dt)
+
+        Q0 = (v0 / ref_nrm, p0)
+        Qo, Ho = arnoldi_factorization(mv, Q0, k, bm1s)
+        assert np.abs(H - Ho).max() < 1e-9 * np.abs(Ho).max(), np.abs(H - Ho).max()
+        for j in range(k + 1):
+            v, p = g.vec_download(j)
+            assert rel(v, Qo[j][0]) < 1e-7, j
+        # orthonormality of the device basis under bm1s
+        for i in range(k + 1):
+            for j in range(i + 1):
+                ip = g.inner_product(i, j)
+                assert abs(ip - (1.0 if i == j else 0.0)) < 1e-12
+        # krylov_matmul and basis rotation
+        y = np.arange(1, k + 1, dtype=float)
+        g.basis_gemv(k, 0, y, k + 2)
+        v, p = g.vec_download(k + 2)
+        ref = sum(y[j] * Qo[j][0] for j in range(k))
+        assert rel(v, ref) < 1e-7
+        rngS = np.random.default_rng(1).standard_normal((k, k))
+        before = [g.vec_download(j) for j in range(k)]
+        g.basis_rotate(k, 0, rngS)
+        for j in range(k):
+            v, p = g.vec_download(j)
+            refv = sum(rngS[i, j] * before[i][0] for i in range(k))
+            refp = sum(rngS[i, j] * before[i][1] for i in range(k))
+            assert rel(v, refv) < 1e-12 and rel(p, refp) < 1e-12
+    finally:
+        g.close()

@@ -231,6 +231,28 @@ def mth_rand(ix, iy, iz, ieg, xl, fcoeff, if3d):
     return np.cos(r)
 
 
+def add_noise(case: "Case", lglel=None) -> np.ndarray:
+    """Deterministic noise seed of core/utils.f:344-408 (add_noise on zero fields): mth_rand per GLL point and
+    component, then direct-stiffness average (opdssum * vmult, dsavg) and Dirichlet masking (bcdirvc)."""
+    d, lx1, nel = case.ldim, case.lx1, case.nel
+    ieg = (np.arange(1, nel + 1) if lglel is None else np.asarray(lglel)).astype(np.float64)[:, None]
+    p = np.arange(lx1 ** d)
+    ix = (p % lx1 + 1).astype(np.float64)[None, :]
+    iy = ((p // lx1) % lx1 + 1).astype(np.float64)[None, :]
+    iz = (p // (lx1 * lx1) + 1).astype(np.float64)[None, :] if d == 3 else np.ones((1, lx1 ** d))
+    xl = [case.xyz[k] for k in range(d)]
+    coeffs = [(3.0e4, -1.5e3, 0.5e5), (2.3e4, 2.3e3, -2.0e5), (2.0e4, 1.0e3, 1.0e5)]
+    g = case.glo.ravel()
+    ng = int(g.max()) + 1
+    cnt = np.bincount(g, minlength=ng)
+    out = []
+    for k in range(d):
+        q = mth_rand(ix, iy, iz, ieg, xl, coeffs[k], d == 3)
+        avg = np.bincount(g, weights=q.ravel(), minlength=ng) / cnt
+        out.append(avg[g].reshape(nel, -1) * case.mask[k])
+    return np.stack(out)
+
+
 # ----------------------------------------------------------------------------- the case
 @dataclass
 class Case:

@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py -- linearised-NS DOF*timesteps/s of the nekStab matvec hot path on N B200s (one rank per GPU).
+
+Workload (BASELINE.json configs[4]): the shipped 2-D cylinder mesh (1996 elements, Re=50 base flow,
+tests/golden/cyl.npz) re-interpolated to lx1=8 and extruded into 10*N periodic z-layers (weak scaling: 19 960
+hexahedra = 1.02e7 grid points per GPU), lxd=12, lx2=6, BDF3/EXT3, dt from CFL 0.5, tolerances 1e-8/1e-8,
+seed = nekStab's deterministic noise (core/utils.f:344-408).  A "step" is one linearised time step: dealiased
+advection + 3 Helmholtz solves + one pressure solve (Jacobi-PCG on E, thousands of iterations) + projection.
+The timed region is one forward_linearized_map call (core/matvec.f:163) of K steps after a warm-up call of W steps.
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU oracle port instead (see cpu_reference()).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from nekstab_b200 import cases  # noqa: E402
+
+ITERS_FILE = os.path.join(ROOT, "profiles", "workload_iters.json")
+PEAKS_FILE = os.path.join(ROOT, "MEASURED_PEAKS.json")
+HBM_FALLBACK_GBS = 6650.0      # B200_PROFILING.md fallback
+
+# Algorithmic traffic model, words (8 B) per velocity grid point, 3-D lx1=8 (DESIGN.md "Kernels"):
+R2 = (6.0 / 8.0) ** 3           # n2/n
+FS = 1.0 - (6.0 / 8.0) ** 3     # surface-node fraction
+WORDS = {
+    # pressure-CG iteration pieces
+    "pcg_gradt": (3 + 9) * R2 + R2 + 3.0,            # read r,dinvE,pdir + 9 metrics (mesh 2); write pdir; write 3 fields
+    "dssum": 3 * 2 * FS + 0.5 * FS,                  # surface values R+W for 3 fields + int32 index
+    "pcg_div": 3.0 + 1.0 + (9 + 1 + 1) * R2,         # read 3 fields + mask*binv; 9 metrics + pdir read, Ep write (mesh 2)
+    "pcg_update": 8 * R2,                            # x,p,r,Ep,dinvE,bm2inv read; x,r write
+    # Helmholtz-CG iteration pieces (3 components batched)
+    "hcg_axhelm": 3 * (1 + 1 + 1 + 1) + 6 + 1 + 1,   # per comp r,p read, p,w write; 6 G + bm1 + dinv once
+    "hcg_dssum": 3 * 2 * FS + 0.5 * FS,
+    "hcg_update": 3 * (4 + 2) + 3 + 3,               # per comp x,p,r,w read x,r write; mask, dinv, mult, binv
+}
+
+
+def build_workload(ngpus: int, small: bool = False):
+    g = np.load(os.path.join(ROOT, "tests", "golden", "cyl.npz"))
+    if small:
+        c2 = cases.cylinder_case(g, lx1=8, sponge=False)
+        return cases.extrude(c2, 3, 2 * np.pi * 0.3, name="cyl3d_small")
+    c2 = cases.cylinder_case(g, lx1=8, sponge=False)          # sponge off for benchmarks
+    nz = 10 * ngpus
+    return cases.extrude(c2, nz, 2 * np.pi * ngpus, name=f"cyl3d_1996x{nz}_lx8")
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, device):
+        super().__init__(daemon=True)
+        self.device, self.stop_flag, self.rows = device, False, []
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.device}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([t.strip() for t in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def hbm_peak():
+    try:
+        with open(PEAKS_FILE) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def workload_iters():
+    try:
+        with open(ITERS_FILE) as f:
+            d = json.load(f)
+        return int(d["pres_iters_per_step"]), int(d["helm_iters_per_comp_per_step"])
+    except Exception:
+        return 2500, 12
+
+
+def cpu_reference(nsteps: int, nwarm: int, max_seconds: float = 240.0):
+    """Times the CPU oracle port (oracle/stepper.py, Jacobi-PCG mode = the algorithm the GPU path runs) on a
+    bounded sample of the workload: a compact patch of the same lx1=8 3-D mesh, each step forced to the
+    per-step Helmholtz / pressure iteration counts measured on the GPU for the full workload
+    (profiles/workload_iters.json), so the work per grid point per step matches.  Returns DOF*steps/s."""
+    from oracle.ops import SEM
+    from oracle.stepper import LinearizedStepper
+    try:
+        from threadpoolctl import threadpool_info
+        thr = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+    except Exception:
+        thr = os.cpu_count() or 1
+    g = np.load(os.path.join(ROOT, "tests", "golden", "cyl.npz"))
+    c2 = cases.cylinder_case(g, lx1=8, sponge=False)
+    order = np.argsort(c2.key, kind="stable")[:48]               # RSB key order => spatially compact patch
+    sub = c2.local_part(0, 1)
+    sel = np.sort(order)
+    sub.nel, sub.xyz, sub.glo, sub.mask = sel.size, c2.xyz[:, sel], c2.glo[sel], c2.mask[:, sel]
+    sub.key, sub.ubase = c2.key[sel], c2.ubase[:, sel]
+    sub.glo = cases._compress(sub.glo)
+    sub.extra = {}
+    c3 = cases.extrude(sub, 2, 2 * np.pi / 5.0)
+    s = SEM(3, 8, c3.xyz, c3.glo, c3.mask)
+    ip, iv = workload_iters()
+    st = LinearizedStepper(s, c3.ubase, c3.re, None, tol_v=0.0, tol_p=0.0, solver="pcg", max_iter_v=iv, max_iter_p=ip, ifvcor=False)
+    v = cases.add_noise(c3).reshape((3,) + s.eshape)
+    p = np.zeros(s.eshape2)
+    dt = 0.5 / s.cfl_sum(c3.ubase.reshape((3,) + s.eshape))
+    t_used, done, t_steps = 0.0, 0, []
+    for i in range(nwarm + nsteps):
+        t0 = time.perf_counter()
+        v, p = st.linearized_map(v, p, 1, dt)
+        el = time.perf_counter() - t0
+        t_used += el
+        if i >= nwarm:
+            t_steps.append(el)
+        done += 1
+        if t_used > max_seconds and len(t_steps) >= 1:
+            break
+    tstep = float(np.mean(t_steps))
+    value = c3.n / tstep
+    sample = (f"{c3.nel} hexahedra (48-element patch of the cylinder mesh x 2 layers, lx1=8, n={c3.n}); "
+              f"{len(t_steps)} timed step(s) after {min(nwarm, done - len(t_steps))} warm-up, each forced to {ip} pressure-CG and "
+              f"{iv} Helmholtz-CG iterations/component (the full workload's GPU-measured per-step counts); numpy/scipy oracle port")
+    return value, tstep, thr, sample, c3.n
+
+
+# ------------------------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--small", action="store_true", help="tiny 3-layer mesh (debugging only; not a valid bench line)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tol", type=float, default=1e-8)
+    args = ap.parse_args()
+    K, W = args.steps, max(args.warmup, 0)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        value, tstep, thr, sample, nsamp = cpu_reference(K, W)
+        line = {"impl": "reference", "metric": "linearized-NS DOF*timesteps/s", "value": value, "unit": "DOF*steps/s",
+                "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": tstep * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"cyl3d_1996x{10 * args.gpus}_lx8 (bounded sample)", "lx1": 8, "lxd": 12, "lx2": 6,
+                           "pressure_solver": "Jacobi-PCG", "sample_points": nsamp},
+                "cpu_baseline": {"value": value, "unit": "DOF*steps/s", "cores": thr, "kind": "port", "sample": sample},
+                "e2e": {"value": value, "unit": "DOF*steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from nekstab_b200 import lib
+    if world > 1:
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    t_setup = time.time()
+    gcase = build_workload(world, small=args.small)
+    seed = cases.add_noise(gcase)
+    if world > 1:
+        pr = cases.partition(gcase.key, world, gcase.d2)
+        sel = np.nonzero(pr == rank)[0]
+        case = gcase.local_part(rank, world)
+        seed = seed[:, sel]
+        ids = [lib.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        nid = ids[0]
+    else:
+        case, nid = gcase, None
+    n_glob = gcase.n
+    del gcase
+    ctx = lib.NekStabB200(case, device=local_rank, rank=rank, nranks=world, nccl_id=nid)
+    ctx.set_params(1.0 / case.re, 1.0, args.tol, args.tol, 2000, 100000)
+    dt, _, ctarg = ctx.prepare_linearized_solver(1.0, 0.5)
+    ctx.vec_alloc(3)
+    ctx.vec_upload(0, seed, None)
+    ctx.normalize(0)
+    t_setup = time.time() - t_setup
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def maxr(x):
+        if world > 1:
+            t = torch.tensor([x], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
+
+    # ---- warm-up call (W steps), then the timed call (K steps): inputs resident in HBM
+    if W > 0:
+        ctx.set_timestep(dt, W)
+        ctx.matvec(lib.DIRECT, 0, 1)
+    else:
+        ctx.vec_copy(1, 0)
+    ctx.set_timestep(dt, K)
+    ctx.stats(reset=True)
+    ctx.profile(1)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    ctx.matvec(lib.DIRECT, 1, 2)
+    barrier()
+    wall = time.perf_counter() - t0
+    sampler.stop_flag = True
+    st = ctx.stats()
+    prof = ctx.profile(0)
+    dev_ms = maxr(st["step_ms"])
+    value = n_glob * K / (dev_ms * 1e-3)
+
+    # ---- end to end: host buffers in, host buffers out, through the public C-ABI calls
+    v_h, p_h = ctx.vec_download(1)
+    vin = torch.from_numpy(v_h).pin_memory().numpy()
+    pin = torch.from_numpy(p_h).pin_memory().numpy()
+    barrier()
+    t0 = time.perf_counter()
+    ctx.vec_upload(1, vin, pin)
+    ctx.matvec(lib.DIRECT, 1, 2)
+    vout, pout = ctx.vec_download(2)
+    barrier()
+    e2e_s = maxr(time.perf_counter() - t0)
+    e2e_value = n_glob * K / e2e_s
+    vec_bytes = (vin.size + pin.size) * 8
+
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        n_loc = case.n
+        kern = {}
+        for kname, (ms, cnt) in prof.items():
+            wkey = kname if kname in WORDS else None
+            if cnt > 0 and wkey:
+                t = ms / cnt * 1e-3
+                gbs = WORDS[wkey] * 8.0 * n_loc / t / 1e9
+                kern[kname] = {"avg_ms": ms / cnt, "samples": cnt, "alg_GBs": gbs, "frac": gbs / peak}
+            elif cnt > 0:
+                kern[kname] = {"avg_ms": ms / cnt, "samples": cnt}
+        pc = [k for k in ("pcg_gradt", "dssum", "pcg_div", "pcg_update") if k in kern]
+        dom = max(pc, key=lambda k: kern[k]["avg_ms"]) if pc else None
+        iter_ms = sum(kern[k]["avg_ms"] for k in pc) if pc else None
+        iter_words = sum(WORDS[k] for k in pc) if pc else None
+        roof = None
+        if dom:
+            roof = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["alg_GBs"], "peak": peak, "unit": "GB/s",
+                    "frac": kern[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                    "alg_bytes_per_launch": WORDS[dom] * 8.0 * n_loc,
+                    "pressure_iteration": {"alg_GBs": iter_words * 8.0 * n_loc / (iter_ms * 1e-3) / 1e9,
+                                           "frac": iter_words * 8.0 * n_loc / (iter_ms * 1e-3) / 1e9 / peak, "ms": iter_ms,
+                                           "share_of_step": iter_ms * st["pres_iters"] / max(st["step_ms"], 1e-9)},
+                    "kernels": kern}
+        line = {"metric": "linearized-NS DOF*timesteps/s", "value": value, "unit": "DOF*steps/s", "n_gpus": world, "steps": K,
+                "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": case.name if world == 1 else f"cyl3d_1996x{10 * world}_lx8", "elements": int(n_glob // 512),
+                           "dof": int(n_glob), "lx1": 8, "lxd": 12, "lx2": 6, "dt": dt, "re": 50.0, "tol_v": args.tol,
+                           "tol_p": args.tol, "pressure_solver": "Jacobi-PCG (north-star)",
+                           "pres_iters_per_step": st["pres_iters"] / K, "helm_iters_per_comp_per_step": st["helm_iters"] / K / 3,
+                           "l2": "per-iteration working set (2 GB) >> L2 (126 MB): no flush needed", "parallelism": f"elements/{world}",
+                           "setup_s": t_setup, "wall_s_timed": wall},
+                "clocks": sampler.summary(), "gpu_launches": int(st["kernel_launches"]),
+                "e2e": {"value": e2e_value, "unit": "DOF*steps/s", "h2d_bytes_per_step": vec_bytes / K, "d2h_bytes_per_step": vec_bytes / K,
+                        "note": "one matvec call = K steps; vector copied in/out once per call"},
+                "roofline": roof}
+        if world == 1 and not args.small:
+            os.makedirs(os.path.dirname(ITERS_FILE), exist_ok=True)
+            try:
+                with open(ITERS_FILE, "w") as f:
+                    json.dump({"pres_iters_per_step": int(round(st["pres_iters"] / K)),
+                               "helm_iters_per_comp_per_step": int(round(st["helm_iters"] / K / 3)), "tol": args.tol, "steps": K}, f)
+            except Exception:
+                pass
+        if world == 1 and not args.no_cpu_baseline:
+            cv, ct, thr, sample, _ = cpu_reference(1, 0, max_seconds=60.0)
+            line["cpu_baseline"] = {"value": cv, "unit": "DOF*steps/s", "cores": thr, "kind": "port", "sample": sample}
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

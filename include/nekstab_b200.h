@@ -113,6 +113,11 @@ typedef struct nsb_stats {
   double    step_ms;            /* device time in stepper (CUDA events) */
 } nsb_stats;
 int nsb_get_stats(nsb_stats* out, int reset);
+/* Sampling kernel profiler (CUDA events on the launching stream around single launches, one sample set per host
+ * poll of a CG loop).  enable: 1 start (clears), 0 stop (clears), -1 just read.  Arrays of 8: accumulated ms and
+ * sample count per kind: 0 pressure-CG gradt, 1 dssum (ldim fields), 2 pressure-CG div, 3 pressure-CG vector update,
+ * 4 Helmholtz-CG axhelm, 5 Helmholtz-CG vector update, 6 advection, 7 Helmholtz dssum. */
+int nsb_profile(int enable, double* ms_sum, long long* count);
 
 /* ------------------------------------------------------------------ operator-level entry points
  * Mirrors of the Nek5000 routines on the path, taking HOST arrays (copied in and out) so that every

@@ -439,6 +439,18 @@ extern "C" int nsb_get_stats(nsb_stats* out, int reset) {
   if (reset) c->stats = nsb_stats{0, 0, 0, 0, 0.0};
   return 0;
 }
+extern "C" int nsb_profile(int enable, double* ms_sum, long long* count) {
+  REQUIRE_CTX();
+  if (enable > 0 && !c->prof_ev[0])
+    for (int i = 0; i < 16; ++i) NSB_CUDA(cudaEventCreate(&c->prof_ev[i]));
+  if (ms_sum) for (int i = 0; i < 8; ++i) ms_sum[i] = c->prof_ms[i];
+  if (count) for (int i = 0; i < 8; ++i) count[i] = c->prof_cnt[i];
+  if (enable >= 0) {
+    c->prof_on = enable;
+    for (int i = 0; i < 8; ++i) { c->prof_ms[i] = 0; c->prof_cnt[i] = 0; }
+  }
+  return 0;
+}
 extern "C" long long nsb_n(void) { return g_ctx ? g_ctx->n : 0; }
 extern "C" long long nsb_n2(void) { return g_ctx ? g_ctx->n2 : 0; }
 

@@ -146,6 +146,12 @@ struct Ctx {
   double* hpart = nullptr;  // partial multi-dot sums
   long long hpart_cap = 0;
 
+  // per-kernel sampling profiler (CUDA events on the launching stream; one sample set per host poll)
+  int prof_on = 0;
+  cudaEvent_t prof_ev[16] = {nullptr};
+  double prof_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long prof_cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
   // stats
   nsb_stats stats = {0, 0, 0, 0, 0.0};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;

@@ -66,6 +66,21 @@ static int cg_state_poll(Ctx* c, int first, int count, bool* all_done) {
   return 0;
 }
 
+// ---- sampling profiler: kinds 0 pcg_gradt, 1 dssum(3 fields), 2 pcg_div, 3 pcg_update, 4 hcg_axhelm, 5 hcg_update,
+//      6 advab, 7 helmholtz dssum.  Events bracket ONE launch each; elapsed times are read after the next host poll.
+static inline void prof_mark(Ctx* c, bool on, int slot) {
+  if (on) cudaEventRecord(c->prof_ev[slot], c->stream);
+}
+static void prof_collect(Ctx* c, const int* kinds, int nk, int first_slot) {
+  for (int i = 0; i < nk; ++i) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, c->prof_ev[first_slot + i], c->prof_ev[first_slot + i + 1]) == cudaSuccess) {
+      c->prof_ms[kinds[i]] += ms;
+      c->prof_cnt[kinds[i]] += 1;
+    }
+  }
+}
+
 // Solve (h1 A + h2 B) x_c = r_c for the ldim velocity components at once (independent CG recurrences sharing
 // every kernel launch) [UPSTREAM hmholtz.f hmholtz/cggo].  In: c->rk (assembled, masked). Out: c->wk[3].
 int st_helmholtz(Ctx* c, int adj, double h1, double h2, int* iters) {
@@ -76,14 +91,21 @@ int st_helmholtz(Ctx* c, int adj, double h1, double h2, int* iters) {
   bool done = false;
   int issued = 0;
   while (!done) {
+    const bool sample = c->prof_on && issued == 0;
     for (int it = 0; it < c->check_every_v; ++it) {
+      const bool sm = sample && it == 0;
+      prof_mark(c, sm, 0);
       NSB_TRY(ek_hcg_dir_ax(c, nc, h1, h2));
       if (c->nranks > 1) NSB_TRY(vk_cg_finalize_multi(c, c->cgs, nc, 2));
+      prof_mark(c, sm, 1);
       NSB_TRY(gs_dssum(c, c->wk[2], nc, c->n, nullptr));
+      prof_mark(c, sm, 2);
       NSB_TRY(vk_hcg_update(c, nc, adj));
+      prof_mark(c, sm, 3);
       ++issued;
     }
     NSB_TRY(cg_state_poll(c, 0, nc, &done));
+    if (sample) { const int kinds[3] = {4, 7, 5}; prof_collect(c, kinds, 3, 0); }
     if (issued > c->maxit_v + c->check_every_v) break;
   }
   int tot = 0;
@@ -110,15 +132,23 @@ int st_pressure(Ctx* c, int adj, int* iters) {
   bool done = false;
   int issued = 0;
   while (!done) {
+    const bool sample = c->prof_on != 0;
     for (int it = 0; it < c->check_every_p; ++it) {
+      const bool sm = sample && it == 0;       // first iteration of the batch: cannot be a skipped (converged) one
+      prof_mark(c, sm, 4);
       NSB_TRY(ek_pcg_dir_gradt(c, adj));
+      prof_mark(c, sm, 5);
       NSB_TRY(gs_dssum(c, c->wk[2], c->ldim, c->n, sp));
+      prof_mark(c, sm, 6);
       NSB_TRY(ek_pcg_div(c, adj));
       if (c->nranks > 1) NSB_TRY(vk_cg_finalize_multi(c, sp, 1, 2));
+      prof_mark(c, sm, 7);
       NSB_TRY(vk_pcg_update(c, adj));
+      prof_mark(c, sm, 8);
       ++issued;
     }
     NSB_TRY(cg_state_poll(c, 3, 1, &done));
+    if (sample) { const int kinds[4] = {0, 1, 2, 3}; prof_collect(c, kinds, 4, 4); }
     if (issued > c->maxit_p + c->check_every_p) break;
   }
   if (!(c->cgs_host[3].rnorm == c->cgs_host[3].rnorm)) { nsb_set_error("pressure CG produced NaN"); return 2; }
@@ -139,7 +169,9 @@ static int one_step(Ctx* c, int istep, int adj) {
   const double h1 = c->visc, h2 = c->rho * BD[k][0] / c->dt;
   // explicit term into the oldest ring slot, then rotate so that f[0] is current
   double* fnew = c->f[2];
+  prof_mark(c, c->prof_on, 10);
   NSB_TRY(ek_advab(c, adj, c->u, c->ub, c->spng, fnew));
+  prof_mark(c, c->prof_on, 11);
   c->f[2] = c->f[1]; c->f[1] = c->f[0]; c->f[0] = fnew;
   double* b = c->wk[0];
   NSB_TRY(vk_make_rhs(c, b, k, AB[k], BD[k]));
@@ -150,6 +182,7 @@ static int one_step(Ctx* c, int istep, int adj) {
   NSB_TRY(gs_dssum(c, r, D, c->n, nullptr));
   NSB_TRY(vk_mask_fields(c, r, adj));
   NSB_TRY(st_helmholtz(c, adj, h1, h2, nullptr));
+  if (c->prof_on) { const int kinds[1] = {6}; prof_collect(c, kinds, 1, 10); }   // Helmholtz polls => advab events are complete
   // uh = u + du into the oldest velocity buffer (ulag[1]); it becomes the new current field below
   double* un = c->ulag[1];
   NSB_TRY(vk_lin2(c, un, 1.0, c->u, 1.0, c->wk[3], dn));

@@ -81,6 +81,7 @@ _SIGS = {
     "nsb_orthonormalize": [C.c_int, C.c_int, C.c_int, _dp],
     "nsb_matvec": [C.c_int] * 3,
     "nsb_get_stats": [C.POINTER(Stats), C.c_int],
+    "nsb_profile": [C.c_int, _dp, _lp],
     "nsb_op_axhelm": [_dp, C.c_double, C.c_double, _dp],
     "nsb_op_dssum": [_dp],
     "nsb_op_glsc3": [_dp] * 4,
@@ -214,6 +215,13 @@ class NekStabB200:
         s = Stats()
         _ck(self.lib.nsb_get_stats(C.byref(s), int(reset)))
         return {k: getattr(s, k) for k, _ in Stats._fields_}
+
+    PROFILE_KINDS = ["pcg_gradt", "dssum", "pcg_div", "pcg_update", "hcg_axhelm", "hcg_update", "advab", "hcg_dssum"]
+
+    def profile(self, enable=-1):
+        ms = np.zeros(8); cnt = np.zeros(8, dtype=np.int64)
+        _ck(self.lib.nsb_profile(enable, _p(ms), _p(cnt)))
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.PROFILE_KINDS)}
 
     # ---- krylov vectors
     def vec_alloc(self, nslots):

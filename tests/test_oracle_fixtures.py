@@ -1,0 +1,107 @@
+"""Pins the CPU oracle against the reference's own shipped fixtures: the known-answer tests
+KAT-norm, KAT-steps, KAT-TG (direct and adjoint, BFS Re=500) and KAT-eig (cylinder Re=50 leading eigenpair).
+The fixtures are float32 field files produced at solver tolerances 1e-7..1e-9, so agreement is limited to ~1e-7
+(TG) and ~1e-6 (eig); the discriminating power of these levels is documented in SURVEY.md App. E."""
+import os
+
+import numpy as np
+import pytest
+
+from nekstab_b200 import cases
+from oracle.ops import SEM
+from oracle.stepper import LinearizedStepper, prepare_linearized_solver
+from util import GOLD
+
+
+@pytest.fixture(scope="module")
+def bfs():
+    g = np.load(os.path.join(GOLD, "bfs.npz"))
+    c = cases.bfs_case(g)
+    s = SEM(2, c.lx1, c.xyz, c.glo, c.mask)
+    return g, c, s
+
+
+@pytest.fixture(scope="module")
+def cyl():
+    g = np.load(os.path.join(GOLD, "cyl.npz"))
+    c = cases.cylinder_case(g)
+    s = SEM(2, c.lx1, c.xyz, c.glo, c.mask)
+    return g, c, s
+
+
+def _inner(s, a, b, w):
+    return float(sum(np.sum(a[d] * w * b[d]) for d in range(s.ldim)))
+
+
+def test_geometry_kats(bfs, cyl):
+    assert abs(bfs[2].vol - 110.0) < 1e-9                                   # BFS area
+    assert abs(cyl[2].vol - (66 * 32 - np.pi / 4)) < 2e-7                   # 66x32 box minus the D=1 cylinder
+    assert cyl[2].jac.min() > 2.4e-3
+
+
+def test_kat_steps(bfs, cyl):
+    for (g, c, s), ns in ((cyl, 100), (bfs, 172)):
+        dt, nsteps, ctarg = prepare_linearized_solver(s, c.ubase.reshape((2,) + s.eshape), c.end_time)
+        assert nsteps == ns and nsteps + 1 == int(g["mode_istep"])          # file header istep = nsteps+1
+    assert abs(prepare_linearized_solver(cyl[2], cyl[1].ubase.reshape((2,) + cyl[2].eshape), 1.0)[2] - 49.72) < 0.01
+
+
+def test_kat_norm(cyl):
+    g, c, s = cyl
+    bm1s = s.bm1 * (c.spng_fun.reshape(s.eshape) == 0)
+    dre = g["dRe_U"].astype(float).transpose(1, 0, 2, 3)
+    dim = g["dIm_U"].astype(float).transpose(1, 0, 2, 3)
+    assert abs(_inner(s, dre, dre, bm1s) + _inner(s, dim, dim, bm1s) - 1.0) < 5e-9
+    assert abs(_inner(s, dre, dre, s.bm1) + _inner(s, dim, dim, s.bm1) - 1.01835) < 1e-4   # plain bm1 is NOT the norm
+
+
+def test_kat_tg_direct_and_adjoint(bfs):
+    g, c, s = bfs
+    ub = c.ubase.reshape((2,) + s.eshape)
+    dt, nsteps, _ = prepare_linearized_solver(s, ub, c.end_time)
+    st = LinearizedStepper(s, ub, c.re, c.spng_fun, solver="direct", ifvcor=True)
+    bm1s = s.bm1 * (c.spng_fun.reshape(s.eshape) == 0)
+    pre = g["pRe_U"].astype(float).transpose(1, 0, 2, 3)
+    prp = s.to_m2(g["pRe_P"].astype(float))
+    ore = g["ore_U"].astype(float).transpose(1, 0, 2, 3)
+    assert float(g["pIm_absmax"]) == 0.0
+    assert abs(_inner(s, pre, pre, bm1s) - 1.0) < 1e-8
+    assert abs(_inner(s, ore, ore, bm1s) - 3.23700) < 1e-5
+    u, p = st.linearized_map(pre, prp, nsteps, dt)
+    err = np.sqrt(_inner(s, u - ore, u - ore, s.bm1) / _inner(s, ore, ore, s.bm1))
+    assert err < 3e-7, err                                                  # measured 1.3e-7 (float32 fixture)
+    assert abs(_inner(s, u, u, bm1s) - _inner(s, ore, ore, bm1s)) < 1e-6
+    orp = s.to_m2(g["ore_P"].astype(float))
+    assert np.linalg.norm(p - orp) / np.linalg.norm(orp) < 1e-5
+    ua, pa = st.linearized_map(u, p, nsteps, dt, adjoint=True)
+    lam = _inner(s, ua, pre, bm1s) / _inner(s, pre, pre, bm1s)
+    res = ua - lam * pre
+    assert abs(lam - 3.2370) < 1e-4
+    assert np.sqrt(_inner(s, res, res, bm1s) / _inner(s, ua, ua, bm1s)) < 3e-7   # M^T M p = lambda p
+
+
+def test_kat_eig(cyl):
+    g, c, s = cyl
+    ub = c.ubase.reshape((2,) + s.eshape)
+    dt, nsteps, _ = prepare_linearized_solver(s, ub, c.end_time)
+    st = LinearizedStepper(s, ub, c.re, c.spng_fun, solver="direct", ifvcor=False)
+    bm1s = s.bm1 * (c.spng_fun.reshape(s.eshape) == 0)
+    dre = g["dRe_U"].astype(float).transpose(1, 0, 2, 3)
+    dim = g["dIm_U"].astype(float).transpose(1, 0, 2, 3)
+    ur, _ = st.linearized_map(dre, s.to_m2(g["dRe_P"].astype(float)), nsteps, dt)
+    ui, _ = st.linearized_map(dim, s.to_m2(g["dIm_P"].astype(float)), nsteps, dt)
+    mu = g["Spectre_Hd"][0, 0] + 1j * g["Spectre_Hd"][0, 1]
+    q, Mq = dre + 1j * dim, ur + 1j * ui
+
+    def ip(a, b):
+        return sum(np.sum(np.conj(a[d]) * bm1s * b[d]) for d in range(2))
+
+    ray = ip(q, Mq) / ip(q, q)
+    assert abs(ray - mu) < 2e-7                                             # all 7 printed digits of Spectre_Hd.dat:1
+    r = Mq - mu * q
+    assert np.sqrt(abs(ip(r, r)) / abs(ip(Mq, Mq))) < 3e-6                  # measured 1.2e-6
+    rc = Mq - np.conj(mu) * q
+    assert np.sqrt(abs(ip(rc, rc)) / abs(ip(Mq, Mq))) > 1.0                 # the conjugate is NOT an eigenpair
+    # log-transform relation of Spectre_NSd.dat (core/eigensolvers.f:596-598)
+    lam = np.log(mu) / (dt * nsteps)
+    assert abs(lam.real - g["Spectre_NSd_conv"][0, 0]) < 2e-7 and abs(abs(lam.imag) - abs(g["Spectre_NSd_conv"][0, 1])) < 2e-7

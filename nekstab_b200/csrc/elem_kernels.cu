@@ -810,6 +810,7 @@ int ek_hcg_dir_ax(Ctx* c, int ncomp, double h1, double h2) {
 }
 
 int ek_gradt(Ctx* c, const double* p, double* w) {
+  if (c->ldim == 3) return pk_gradt(c, p, w);
   DISPATCH_DN(c, k_gradt<D, N, 0><<<c->nel, Cfg<D, N>::TPB, 0, c->stream>>>(p, w, c->RW2, nullptr, nullptr, nullptr, c->n, c->n2));
   nsb_count_launch();
   NSB_CUDA(cudaGetLastError());
@@ -818,6 +819,7 @@ int ek_gradt(Ctx* c, const double* p, double* w) {
 
 int ek_pcg_dir_gradt(Ctx* c, int adj) {
   // r = pk[0], pdir = pk[2], w = wk[2]
+  if (c->ldim == 3) return pk_pcg_dir_gradt(c, adj);
   DISPATCH_DN(c, k_gradt<D, N, 1><<<c->nel, Cfg<D, N>::TPB, 0, c->stream>>>(c->pk[0], c->wk[2], c->RW2, c->dinvE[adj], c->pk[2],
                                                                          c->cgs + 3, c->n, c->n2));
   nsb_count_launch();
@@ -829,6 +831,7 @@ int ek_div(Ctx* c, const double* u, const double* scale, double* q, double sign)
   const double* s0 = scale;
   const double* s1 = scale ? scale + c->n : nullptr;
   const double* s2 = (scale && c->ldim == 3) ? scale + 2 * c->n : nullptr;
+  if (c->ldim == 3) return pk_div(c, u, s0, s1, s2, q, sign);
   DISPATCH_DN(c, k_div<D, N, 0><<<c->nel, Cfg<D, N>::TPB, 0, c->stream>>>(u, s0, s1, s2, q, c->RW2, nullptr, nullptr, nullptr,
                                                                        nullptr, nullptr, 0, c->n, c->n2, sign));
   nsb_count_launch();
@@ -837,7 +840,8 @@ int ek_div(Ctx* c, const double* u, const double* scale, double* q, double sign)
 }
 
 int ek_pcg_div(Ctx* c, int adj) {
-  // w = wk[2] (dssum'd), Ep = pk[3], pdir = pk[2]
+  // w = wk[2] (dssum'd, or raw when the gather is fused), Ep = pk[3], pdir = pk[2]
+  if (c->ldim == 3) return pk_pcg_div(c, adj, c->fused_gs ? 1 : 0);
   DISPATCH_DN(c, k_div<D, N, 1><<<c->nel, Cfg<D, N>::TPB, 0, c->stream>>>(
                      c->wk[2], c->mbinv[adj][0], c->mbinv[adj][1], c->mbinv[adj][c->ldim == 3 ? 2 : 1], c->pk[3], c->RW2, c->pk[2],
                      c->cgs + 3, c->red_part, c->red_count, c->red_out, c->nranks == 1, c->n, c->n2, 1.0));

@@ -94,6 +94,7 @@ int gs_free(Ctx* c) {
   cudaFree(m.seg_off); cudaFree(m.seg_idx); cudaFree(m.send_seg); cudaFree(m.rseg_off); cudaFree(m.rseg_pos);
   cudaFree(m.rseg_nbefore); cudaFree(m.sendbuf); cudaFree(m.recvbuf);
   cudaFree(d_send_base); cudaFree(d_send_cnt); cudaFree(d_rseg_cnt);
+  cudaFree(m.surf_pts); cudaFree(m.nb_off); cudaFree(m.nb_idx);
   d_send_base = d_send_cnt = d_rseg_cnt = nullptr;
   m = GSMap();
   return 0;
@@ -169,9 +170,14 @@ int gs_setup(Ctx* c, const long long* glo) {
     for (int k : shared_u[r]) is_shared[k] = 1;
   std::vector<int> seg_of_u(nu, -1);
   std::vector<int> seg_off(1, 0), seg_idx;
-  for (int k = 0; k < nu; ++k) {
-    int cntk = ustart[k + 1] - ustart[k];
-    if (cntk > 1 || is_shared[k]) {
+  {
+    // order the segments by their smallest local dof: neighbouring threads then touch neighbouring memory
+    // (r1a ncu: with global-id order the 3-field dssum moved 2x the algorithmic bytes at 20 % of the HBM roofline)
+    std::vector<int> segk;
+    for (int k = 0; k < nu; ++k)
+      if (ustart[k + 1] - ustart[k] > 1 || is_shared[k]) segk.push_back(k);
+    std::sort(segk.begin(), segk.end(), [&](int a, int b) { return order[ustart[a]] < order[ustart[b]]; });
+    for (int k : segk) {
       seg_of_u[k] = (int)seg_off.size() - 1;
       for (int j = ustart[k]; j < ustart[k + 1]; ++j) seg_idx.push_back(order[j]);
       seg_off.push_back((int)seg_idx.size());
@@ -207,6 +213,37 @@ int gs_setup(Ctx* c, const long long* glo) {
   for (int s = 0; s < m.nseg; ++s) {
     for (auto& pr : rlist[s]) { rseg_pos.push_back(pr.first); rseg_cnt.push_back(pr.second); }
     rseg_off.push_back((int)rseg_pos.size());
+  }
+  // ---- per-element gather table (fused direct-stiffness sum; single rank only: no halo entries)
+  if (c->nranks == 1) {
+    const int N = c->lx1, D = c->ldim, np = c->np1;
+    std::vector<int> surf;
+    for (int p = 0; p < np; ++p) {
+      int i = p % N, j = (p / N) % N, kk = (D == 3) ? p / (N * N) : 1;
+      if (i == 0 || i == N - 1 || j == 0 || j == N - 1 || (D == 3 && (kk == 0 || kk == N - 1))) surf.push_back(p);
+    }
+    const int ns = (int)surf.size();
+    std::vector<int> uof(n);                       // dof -> index of its unique id
+    for (int k = 0; k < nu; ++k)
+      for (int j = ustart[k]; j < ustart[k + 1]; ++j) uof[order[j]] = k;
+    std::vector<int> nb_off((size_t)c->nel * (ns + 1)), nb_idx;
+    nb_idx.reserve((size_t)c->nel * ns * 2);
+    bool overflow = false;
+    for (int e = 0; e < c->nel; ++e) {
+      for (int s = 0; s < ns; ++s) {
+        nb_off[(size_t)e * (ns + 1) + s] = (int)nb_idx.size();
+        const int k = uof[(size_t)e * np + surf[s]];
+        for (int j = ustart[k]; j < ustart[k + 1]; ++j) nb_idx.push_back(order[j]);   // ascending dof order
+        if (nb_idx.size() > (size_t)2000000000) overflow = true;
+      }
+      nb_off[(size_t)e * (ns + 1) + ns] = (int)nb_idx.size();
+    }
+    if (!overflow) {
+      m.ns = ns;
+      NSB_TRY(upload(&m.surf_pts, surf));
+      NSB_TRY(upload(&m.nb_off, nb_off));
+      NSB_TRY(upload(&m.nb_idx, nb_idx));
+    }
   }
   NSB_TRY(upload(&m.seg_off, seg_off));
   NSB_TRY(upload(&m.seg_idx, seg_idx));

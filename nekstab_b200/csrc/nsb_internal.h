@@ -70,6 +70,13 @@ struct GSMap {
   int* rseg_nbefore = nullptr;  // [nseg] how many of those come from lower ranks (summed before the local part)
   double* sendbuf = nullptr; // [3*nshared]
   double* recvbuf = nullptr;
+  // per-element gather table for kernels that fuse the direct-stiffness sum into their load phase (single rank):
+  // for element e and surface slot s (local point surf_pts[s]): dofs nb_idx[nb_off[e*(ns+1)+s] .. nb_off[e*(ns+1)+s+1])
+  // = ALL copies of that node in ascending dof order (own copy included)
+  int ns = 0;
+  int* surf_pts = nullptr;
+  int* nb_off = nullptr;
+  int* nb_idx = nullptr;
 };
 
 struct Ctx {
@@ -95,6 +102,7 @@ struct Ctx {
   double* mask[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};     // [adjoint?][comp]
   double* mbinv[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};    // mask*binv
   bool has_adj_masks = false;
+  bool mask_same[2] = {false, false};   // all components share one mask (one mask*binv array is streamed instead of ldim)
   double* RW2 = nullptr;    // [d*d][n2]  w2 * R interpolated to mesh 2
   double* bm2inv = nullptr; // 1/bm2
   double* Rd = nullptr;     // [d*d][nd]  wd * R interpolated to the dealiasing mesh
@@ -114,6 +122,7 @@ struct Ctx {
   double dt = 0;
   int nsteps = 0;
   int check_every_v = 4, check_every_p = 32;
+  bool fused_gs = false;      // 3-D, single rank: k_div3 gathers the surface sums itself (no dssum in the pressure loop)
 
   // base flow, sponge
   double* ub = nullptr;     // [d][n]
@@ -187,6 +196,13 @@ int ek_cfl(Ctx* c, const double* u, double* cfl_dev);                  // max re
 int ek_hcg_dir_ax(Ctx* c, int ncomp, double h1, double h2);     // p = dinv r + beta p; w = H p; rho partial = sum p*w
 int ek_pcg_dir_gradt(Ctx* c, int adj);                           // p = dinvE r + beta p ; w = gradt(p)
 int ek_pcg_div(Ctx* c, int adj);                                 // Ep = div(mbinv w); rho = sum p Ep
+
+// ---- second-generation 3-D pressure-operator kernels (pcg_kernels.cu)
+int pk_upload_constants(const ConstMats& cm);
+int pk_gradt(Ctx* c, const double* p, double* w);
+int pk_pcg_dir_gradt(Ctx* c, int adj);
+int pk_div(Ctx* c, const double* u, const double* s0, const double* s1, const double* s2, double* q, double sign);
+int pk_pcg_div(Ctx* c, int adj, int fused);
 
 // ---- pointwise / reduction kernels (vec_kernels.cu)
 int vk_fill(Ctx* c, double* a, double v, long long n);

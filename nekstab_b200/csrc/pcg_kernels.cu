@@ -96,14 +96,18 @@ k_gradt3(const double* __restrict__ p, double* __restrict__ w, const double* __r
   using C0 = ColIn<0, N2, N2, N2>;
   using C1 = ColIn<1, N2, N2, N>;
   using C2 = ColIn<2, N2, N, N>;
-  __shared__ double sp[S2::size];
   __shared__ double sa[9][SA::size];
   __shared__ double sb[6][SB::size];
+  // products RW2[i][c]*p, one array per (i,c); consumed by the r stage before the s stage overwrites sb
+  double* sq = &sb[0][0];
+  static_assert(9 * S2::size <= 6 * SB::size, "sq alias");
   const int tid = threadIdx.x;
   if (MODE == 1 && cgs->done) return;
   const long long e2 = (long long)blockIdx.x * NP2;
   const long long e1 = (long long)blockIdx.x * NP1;
-  for (int q = tid; q < NP2; q += TPB) {
+  static_assert(NP2 <= TPB, "one mesh-2 point per thread");
+  if (tid < NP2) {
+    const int q = tid;
     double v;
     if (MODE == 1) {
       v = dinvE[e2 + q] * p[e2 + q] + cgs->beta * pdir[e2 + q];
@@ -111,7 +115,9 @@ k_gradt3(const double* __restrict__ p, double* __restrict__ w, const double* __r
     } else {
       v = p[e2 + q];
     }
-    sp[S2::lin(q)] = v;
+    const int o = S2::lin(q);
+#pragma unroll
+    for (int g = 0; g < 9; ++g) sq[g * S2::size + o] = RW2[(long long)g * n2 + e2 + q] * v;   // coalesced
   }
   __syncthreads();
   // ---- r stage: sa[i*3+c] = (i==0 ? D12^T : J12^T) applied along r to (RW2[i][c] * p)
@@ -119,11 +125,10 @@ k_gradt3(const double* __restrict__ p, double* __restrict__ w, const double* __r
   if (tid < 9 * C0::ncol) {
     const int t = tid;
     const int combo = t / C0::ncol, col = t - combo * C0::ncol;
-    const double* rw = RW2 + (long long)combo * n2 + e2 + col * N2;
-    const double* pin = sp + C0::base(col);
+    const double* pin = sq + combo * S2::size + C0::base(col);
     double v[N2];
 #pragma unroll
-    for (int l = 0; l < N2; ++l) v[l] = pin[l] * rw[l];
+    for (int l = 0; l < N2; ++l) v[l] = pin[l];
     double* po = sa[combo] + col * SA::PI;
     if (combo < 3) apply_store<N, N2>(cm.D12t, v, po, 1);
     else apply_store<N, N2>(cm.J12t, v, po, 1);
@@ -194,17 +199,17 @@ k_div3(const double* __restrict__ u, const double* __restrict__ scale0, const do
   if (MODE == 1 && cgs->done) return;
   const long long e2 = (long long)blockIdx.x * NP2;
   const long long e1 = (long long)blockIdx.x * NP1;
-  // ---- stage the three (scaled) components
-  for (int q = tid; q < NP1; q += TPB) {
-    const int o = S1::lin(q);
-    const double s0 = scale0 ? scale0[e1 + q] : 1.0;
-    const double s1 = scale1 ? scale1[e1 + q] : s0;
-    const double s2 = scale2 ? scale2[e1 + q] : s0;
-    su[o] = u[e1 + q] * s0;
-    su[S1::size + o] = u[n + e1 + q] * s1;
-    su[2 * S1::size + o] = u[2 * n + e1 + q] * s2;
-  }
   if (FUSED) {
+    // ---- stage the three (scaled) components, then overwrite the surface nodes with the gathered sums
+    for (int q = tid; q < NP1; q += TPB) {
+      const int o = S1::lin(q);
+      const double s0 = scale0 ? scale0[e1 + q] : 1.0;
+      const double s1 = scale1 ? scale1[e1 + q] : s0;
+      const double s2 = scale2 ? scale2[e1 + q] : s0;
+      su[o] = u[e1 + q] * s0;
+      su[S1::size + o] = u[n + e1 + q] * s1;
+      su[2 * S1::size + o] = u[2 * n + e1 + q] * s2;
+    }
     __syncthreads();
     const int* off = nb_off + (long long)blockIdx.x * (ns + 1);
     for (int s = tid; s < ns; s += TPB) {
@@ -225,17 +230,31 @@ k_div3(const double* __restrict__ u, const double* __restrict__ scale0, const do
       su[S1::size + o] = g1 * s1;
       su[2 * S1::size + o] = g2 * s2;
     }
+    __syncthreads();
   }
-  __syncthreads();
-  // ---- t stage: aJ = J12 u, aD = D12 u along t (same input column, two outputs)
+  // ---- t stage: aJ = J12 u, aD = D12 u along t (same input column, two outputs).  Without the fused gather the
+  //      column is read straight from global memory: lanes run over (j,i), so each of the N loads is coalesced.
   static_assert(3 * C2::ncol <= TPB, "one task per thread");
   if (tid < 3 * C2::ncol) {
     const int t = tid;
     const int c = t / C2::ncol, col = t - c * C2::ncol;
-    const double* pin = su + c * S1::size + C2::base(col);
     double v[N];
+    if (FUSED) {
+      const double* pin = su + c * S1::size + C2::base(col);
 #pragma unroll
-    for (int l = 0; l < N; ++l) v[l] = pin[l * C2::stride];
+      for (int l = 0; l < N; ++l) v[l] = pin[l * C2::stride];
+    } else {
+      const double* sc = (c == 0 || !scale1) ? scale0 : (c == 1 ? scale1 : scale2);
+      const double* pu = u + (long long)c * n + e1 + col;
+      if (sc) {
+        const double* ps = sc + e1 + col;
+#pragma unroll
+        for (int l = 0; l < N; ++l) v[l] = pu[l * N * N] * ps[l * N * N];
+      } else {
+#pragma unroll
+        for (int l = 0; l < N; ++l) v[l] = pu[l * N * N];
+      }
+    }
     // output (N2,N,N): same (j,i) base, plane stride N*PI
     apply_store<N2, N>(cm.J12, v, sa[c * 2] + C2::base(col), C2::stride);
     apply_store<N2, N>(cm.D12, v, sa[c * 2 + 1] + C2::base(col), C2::stride);
@@ -256,44 +275,27 @@ k_div3(const double* __restrict__ u, const double* __restrict__ scale0, const do
     if (which == 0) apply_store<N2, N>(cm.D12, v, sbuf + (c * 3 + 1) * SB::size + bo, SB::PI);
   }
   __syncthreads();
-  // ---- r stage + metric multiply, one (direction, component) pair per task:
-  //      part[dir*3+c] = RW2[dir][c] * (dir==0 ? D12 : J12) applied along r to {bJJ, bDJ, bJD}[dir]
+  // ---- r stage, one (direction, component) pair per task:
+  //      part[dir*3+c] = (dir==0 ? D12 : J12) applied along r to {bJJ, bDJ, bJD}[dir]; the metric multiply and the sum
+  //      over the 9 pairs happen in the final, coalesced pass
   static_assert(9 * C0::ncol <= TPB, "one task per thread");
   if (tid < 9 * C0::ncol) {
     const int grp = tid / C0::ncol, col = tid - grp * C0::ncol;
     const int dir = grp / 3, c = grp - dir * 3;
     const double* b0 = sbuf + (c * 3 + dir) * SB::size + C0::base(col);
-    const double* rw = RW2 + (long long)grp * n2 + e2 + col * N2;
-    double v[N], r[N2];
-#pragma unroll
-    for (int a = 0; a < N2; ++a) r[a] = rw[a];
+    double v[N];
 #pragma unroll
     for (int l = 0; l < N; ++l) v[l] = b0[l];
     double* po = &spart[grp][col * N2];
-    if (dir == 0) {
-#pragma unroll
-      for (int a = 0; a < N2; ++a) {
-        double sacc = 0.0;
-#pragma unroll
-        for (int l = 0; l < N; ++l) sacc = fma(cm.D12[a * N + l], v[l], sacc);
-        po[a] = r[a] * sacc;
-      }
-    } else {
-#pragma unroll
-      for (int a = 0; a < N2; ++a) {
-        double sacc = 0.0;
-#pragma unroll
-        for (int l = 0; l < N; ++l) sacc = fma(cm.J12[a * N + l], v[l], sacc);
-        po[a] = r[a] * sacc;
-      }
-    }
+    if (dir == 0) apply_store<N2, N>(cm.D12, v, po, 1);
+    else apply_store<N2, N>(cm.J12, v, po, 1);
   }
   __syncthreads();
   double rho[1] = {0.0};
   for (int q = tid; q < NP2; q += TPB) {
-    double acc = spart[0][q];
+    double acc = 0.0;
 #pragma unroll
-    for (int g = 1; g < 9; ++g) acc += spart[g][q];
+    for (int g = 0; g < 9; ++g) acc = fma(RW2[(long long)g * n2 + e2 + q], spart[g][q], acc);   // metrics: coalesced
     const double v = sign * acc;
     qout[e2 + q] = v;
     if (MODE == 1) rho[0] += pdir[e2 + q] * v;

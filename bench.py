@@ -185,7 +185,9 @@ def main():
     from nekstab_b200 import lib
     if world > 1:
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # torch.distributed is host plumbing only (id broadcast, barrier, max over ranks): gloo.  The data path (halo
+        # exchange, all-reduces) runs on the library's own NCCL communicator over NVLink (nsb_comm_init).
+        dist.init_process_group("gloo")
     t_setup = time.time()
     gcase = build_workload(world, small=args.small)
     seed = cases.add_noise(gcase)
@@ -216,7 +218,7 @@ def main():
 
     def maxr(x):
         if world > 1:
-            t = torch.tensor([x], dtype=torch.float64, device="cuda")
+            t = torch.tensor([x], dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             return float(t.item())
         return x

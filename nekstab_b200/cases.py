@@ -389,7 +389,7 @@ def bfs_case(g: dict, sponge: bool = True) -> Case:
 
 def extrude(c2: Case, nz: int, lz: float, name: Optional[str] = None) -> Case:
     """Config 5 recipe (SURVEY 8d): extrude a 2-D case into nz uniform periodic layers over [0,lz];
-    element eg3 = layer*nel2 + eg2, key3 = key2*nz + layer, z-invariant base flow with W=0."""
+    element eg3 = layer*nel2 + eg2, key3 = key2, z-invariant base flow with W=0."""
     lx1 = c2.lx1
     z, _ = sem.zwgll(lx1)
     nel2, np2 = c2.nel, c2.npts
@@ -405,10 +405,11 @@ def extrude(c2: Case, nz: int, lz: float, name: Optional[str] = None) -> Case:
     m2 = lift(c2.mask[0])
     mask = np.stack([m2, m2, m2])
     ub = np.stack([lift(c2.ubase[0]), lift(c2.ubase[1]), np.zeros_like(Z)])
-    key = (c2.key[None, :] * nz + np.arange(nz)[:, None]).reshape(-1)
-    d2 = 1
-    while d2 < c2.d2 * nz:
-        d2 *= 2
+    # partition key: every z-layer of a 2-D element inherits the element's RSB key, so the power-of-two rule
+    # rank = key // (d2/P) splits the extruded mesh into the same balanced 2-D sub-domains as the shipped mesh
+    # (genmap is not available to produce a true 3-D RSB key: "parity unpinned" for this synthetic mesh)
+    key = np.broadcast_to(c2.key[None, :], (nz, nel2)).reshape(-1).copy()
+    d2 = c2.d2
     case = Case(name or (c2.name + f"_x{nz}"), 3, lx1, nz * nel2, np.ascontiguousarray(xyz), glo,
                 np.ascontiguousarray(mask), key, d2, np.ascontiguousarray(ub), re=c2.re,
                 end_time=c2.end_time, tol_p=c2.tol_p, tol_v=c2.tol_v)

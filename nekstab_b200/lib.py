@@ -107,6 +107,7 @@ _SIGS = {
 EXPORTED = sorted(list(_SIGS) + ["nsb_last_error", "nsb_n", "nsb_n2"])
 
 _lib = None
+_comm = None          # (rank, nranks) once the process-wide NCCL communicator exists (a unique id is single-use)
 
 
 def find_lapack() -> Optional[str]:
@@ -158,11 +159,14 @@ class NekStabB200:
         lp = find_lapack()
         if lp:
             _ck(self.lib.nsb_lapack_load(lp.encode()))
-        if nranks > 1:
-            assert nccl_id is not None and len(nccl_id) == 128
-            _ck(self.lib.nsb_comm_init(rank, nranks, nccl_id, device))
-        else:
-            _ck(self.lib.nsb_comm_init(0, 1, b"\0" * 128, device))
+        global _comm
+        if _comm != (rank, nranks):
+            if nranks > 1:
+                assert nccl_id is not None and len(nccl_id) == 128
+                _ck(self.lib.nsb_comm_init(rank, nranks, nccl_id, device))
+            else:
+                _ck(self.lib.nsb_comm_init(0, 1, b"\0" * 128, device))
+            _comm = (rank, nranks)
         self.case = case
         self.ldim, self.lx1, self.lx2, self.lxd = case.ldim, case.lx1, case.lx1 - 2, 3 * case.lx1 // 2
         self.nel = case.nel

@@ -85,6 +85,19 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
+def ncu_traffic(kernel_kind):
+    """dram__bytes_read+write per launch of the dominant kernel from the committed `ncu --set full` capture."""
+    names = {"pcg_div": "k_div3<8, 1, 0>", "pcg_gradt": "k_gradt3<8, 1>", "dssum": "k_gs_sum<3, 0>"}
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_dram_traffic.json")) as f:
+            d = json.load(f)
+        rec = d[names[kernel_kind]][0]
+        mult = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}.get(rec.get("unit", "Mbyte"), 1e6)
+        return (rec["dram_read"] + rec["dram_write"]) * mult
+    except Exception:
+        return None
+
+
 def hbm_peak():
     try:
         with open(PEAKS_FILE) as f:
@@ -278,7 +291,7 @@ def main():
         roof = None
         if dom:
             roof = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["alg_GBs"], "peak": peak, "unit": "GB/s",
-                    "frac": kern[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                    "frac": kern[dom]["frac"], "traffic": ncu_traffic(dom) if world == 1 else None, "peak_source": peak_src,
                     "alg_bytes_per_launch": WORDS[dom] * 8.0 * n_loc,
                     "pressure_iteration": {"alg_GBs": iter_words * 8.0 * n_loc / (iter_ms * 1e-3) / 1e9,
                                            "frac": iter_words * 8.0 * n_loc / (iter_ms * 1e-3) / 1e9 / peak, "ms": iter_ms,
@@ -298,9 +311,9 @@ def main():
                         "note": "one matvec call = K steps; vector copied in/out once per call"},
                 "roofline": roof}
         if world == 1 and not args.small:
-            os.makedirs(os.path.dirname(ITERS_FILE), exist_ok=True)
-            try:
-                with open(ITERS_FILE, "w") as f:
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            try:     # measured counts go to scratch; the committed profiles/workload_iters.json is updated by hand
+                with open(os.path.join(ROOT, "gpurun_out", "workload_iters.json"), "w") as f:
                     json.dump({"pres_iters_per_step": int(round(st["pres_iters"] / K)),
                                "helm_iters_per_comp_per_step": int(round(st["helm_iters"] / K / 3)), "tol": args.tol, "steps": K}, f)
             except Exception:

@@ -138,6 +138,16 @@ int nsb_op_esolver(const double* g, double* phi, int* iters);
 int nsb_op_cfl(const double* ux, const double* uy, const double* uz, double dt, double* cfl);
 /* named geometry arrays for parity checks: "bm1","binvm1","jacm1","g1".."g6","bm2","ediag","hdiagA","vmult" */
 int nsb_get_field(const char* name, double* out, long long* count);
+/* Host-only views of the gather-scatter plan (no CUDA/NCCL needed): the multi-rank map construction of gs_setup
+ * (replaces gslib gs_setup's discovery of shared nodes) exposed for CPU tests with any transport.
+ * 1) nsb_gs_host_candidates: this rank's element-surface global ids (ascending) -- what ranks all-gather;
+ * 2) nsb_gs_host_plan: given every rank's list (counts[r], concatenated ids) build segments + halo lists;
+ *    sizes_out = {nseg, len(seg_idx), nneighbours, nshared, len(rseg_pos), 0,0,0};
+ * 3) nsb_gs_host_get(which): 0 seg_off 1 seg_idx 2 nbr_rank 3 nbr_off 4 send_seg 5 send_base 6 send_cnt 7 rseg_off
+ *    8 rseg_pos 9 rseg_cnt 10 rseg_nbefore. */
+int nsb_gs_host_candidates(int ldim, int lx1, int nelv, const long long* glo_num, long long* ids_out, long long* count);
+int nsb_gs_host_plan(int rank, int nranks, const long long* counts, const long long* ids, int sizes_out[8]);
+int nsb_gs_host_get(int which, int* out);
 long long nsb_n(void);   /* nelv*lx1^ldim */
 long long nsb_n2(void);  /* nelv*lx2^ldim */
 

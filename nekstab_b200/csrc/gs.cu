@@ -100,33 +100,149 @@ int gs_free(Ctx* c) {
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ host-side plan
+// Everything below up to gs_setup is pure host code (no CUDA, no NCCL) so that the multi-rank map construction can be
+// exercised on a CPU-only box (tests/test_multirank_gloo.py drives it through nsb_gs_host_* with gloo as the transport).
+struct HostPlan {
+  std::vector<int> order, ustart;            // dofs sorted by (global id, dof); run starts per unique id
+  std::vector<long long> uid;
+  std::vector<int> seg_off, seg_idx;         // segments (sorted by smallest local dof)
+  std::vector<int> nbr_rank, nbr_off;        // neighbours (ascending rank), offsets into the send/recv buffers
+  std::vector<int> send_seg, send_base, send_cnt;
+  std::vector<int> rseg_off, rseg_pos, rseg_cnt, nbefore;
+  int nshared = 0;
+};
+
+static bool is_surface(int p, int N, int D) {
+  int i = p % N, j = (p / N) % N, kk = (D == 3) ? p / (N * N) : 1;
+  return i == 0 || i == N - 1 || j == 0 || j == N - 1 || (D == 3 && (kk == 0 || kk == N - 1));
+}
+
+static void plan_sort(HostPlan& P, long long n, const long long* glo) {
+  P.order.resize(n);
+  std::iota(P.order.begin(), P.order.end(), 0);
+  std::sort(P.order.begin(), P.order.end(), [&](int a, int b) { return glo[a] != glo[b] ? glo[a] < glo[b] : a < b; });
+  P.uid.clear(); P.ustart.clear();
+  for (long long i = 0; i < n; ++i)
+    if (i == 0 || glo[P.order[i]] != glo[P.order[i - 1]]) { P.uid.push_back(glo[P.order[i]]); P.ustart.push_back((int)i); }
+  P.ustart.push_back((int)n);
+}
+
+// ids of this rank's element-surface nodes (ascending): the only nodes another rank can share
+static void plan_candidates(const HostPlan& P, int N, int D, int np, std::vector<long long>& cand) {
+  cand.clear();
+  const int nu = (int)P.uid.size();
+  for (int k = 0; k < nu; ++k)
+    if (is_surface(P.order[P.ustart[k]] % np, N, D)) cand.push_back(P.uid[k]);
+}
+
+// counts[r], ids (concatenated, each rank's list ascending) = every rank's candidate list
+static void plan_build(HostPlan& P, int rank, int nranks, const long long* counts, const long long* ids) {
+  const int nu = (int)P.uid.size();
+  std::vector<std::vector<int>> shared_u(nranks);
+  long long base = 0;
+  for (int r = 0; r < nranks; ++r) {
+    const long long no = counts ? counts[r] : 0;
+    if (r != rank && counts) {
+      const long long* other = ids + base;
+      long long a = 0;
+      int k = 0;
+      while (a < no && k < nu) {                       // both ascending: two-pointer intersection
+        if (other[a] < P.uid[k]) ++a;
+        else if (other[a] > P.uid[k]) ++k;
+        else { shared_u[r].push_back(k); ++a; ++k; }
+      }
+    }
+    base += no;
+  }
+  std::vector<char> is_shared(nu, 0);
+  for (int r = 0; r < nranks; ++r)
+    for (int k : shared_u[r]) is_shared[k] = 1;
+  std::vector<int> seg_of_u(nu, -1);
+  P.seg_off.assign(1, 0); P.seg_idx.clear();
+  {
+    // order the segments by their smallest local dof: neighbouring threads then touch neighbouring memory
+    // (r1a ncu: with global-id order the 3-field dssum moved 2x the algorithmic bytes at 20 % of the HBM roofline)
+    std::vector<int> segk;
+    for (int k = 0; k < nu; ++k)
+      if (P.ustart[k + 1] - P.ustart[k] > 1 || is_shared[k]) segk.push_back(k);
+    std::sort(segk.begin(), segk.end(), [&](int a, int b) { return P.order[P.ustart[a]] < P.order[P.ustart[b]]; });
+    for (int k : segk) {
+      seg_of_u[k] = (int)P.seg_off.size() - 1;
+      for (int j = P.ustart[k]; j < P.ustart[k + 1]; ++j) P.seg_idx.push_back(P.order[j]);
+      P.seg_off.push_back((int)P.seg_idx.size());
+    }
+  }
+  const int nseg = (int)P.seg_off.size() - 1;
+  std::vector<std::vector<std::pair<int, int>>> rlist(nseg);   // per segment: (pos, cnt) in ascending rank
+  P.nbefore.assign(nseg, 0);
+  P.nbr_rank.clear(); P.nbr_off.clear(); P.send_seg.clear(); P.send_base.clear(); P.send_cnt.clear();
+  int off = 0;
+  for (int r = 0; r < nranks; ++r) {
+    if (shared_u[r].empty()) continue;
+    const int cnt = (int)shared_u[r].size();
+    P.nbr_rank.push_back(r);
+    P.nbr_off.push_back(off);
+    for (int j = 0; j < cnt; ++j) {
+      const int seg = seg_of_u[shared_u[r][j]];
+      P.send_seg.push_back(seg);
+      P.send_base.push_back(3 * off + j);
+      P.send_cnt.push_back(cnt);
+      rlist[seg].push_back({3 * off + j, cnt});
+      if (r < rank) P.nbefore[seg]++;
+    }
+    off += cnt;
+  }
+  P.nbr_off.push_back(off);
+  P.nshared = off;
+  P.rseg_off.assign(1, 0); P.rseg_pos.clear(); P.rseg_cnt.clear();
+  for (int sidx = 0; sidx < nseg; ++sidx) {
+    for (auto& pr : rlist[sidx]) { P.rseg_pos.push_back(pr.first); P.rseg_cnt.push_back(pr.second); }
+    P.rseg_off.push_back((int)P.rseg_pos.size());
+  }
+}
+
+// ---- host-only debug/test entry points (declared in include/nekstab_b200.h)
+static HostPlan g_host_plan;
+extern "C" int nsb_gs_host_candidates(int ldim, int lx1, int nelv, const long long* glo_num, long long* ids_out,
+                                      long long* count) {
+  const int np = (ldim == 3) ? lx1 * lx1 * lx1 : lx1 * lx1;
+  plan_sort(g_host_plan, (long long)nelv * np, glo_num);
+  std::vector<long long> cand;
+  plan_candidates(g_host_plan, lx1, ldim, np, cand);
+  if (count) *count = (long long)cand.size();
+  if (ids_out) memcpy(ids_out, cand.data(), cand.size() * sizeof(long long));
+  return 0;
+}
+extern "C" int nsb_gs_host_plan(int rank, int nranks, const long long* counts, const long long* ids, int sizes_out[8]) {
+  if (g_host_plan.order.empty()) { nsb_set_error("nsb_gs_host_plan: call nsb_gs_host_candidates first"); return 1; }
+  plan_build(g_host_plan, rank, nranks, counts, ids);
+  const HostPlan& P = g_host_plan;
+  const int v[8] = {(int)P.seg_off.size() - 1, (int)P.seg_idx.size(), (int)P.nbr_rank.size(), P.nshared,
+                    (int)P.rseg_pos.size(), 0, 0, 0};
+  for (int i = 0; i < 8; ++i) sizes_out[i] = v[i];
+  return 0;
+}
+// which: 0 seg_off, 1 seg_idx, 2 nbr_rank, 3 nbr_off, 4 send_seg, 5 send_base, 6 send_cnt, 7 rseg_off, 8 rseg_pos, 9 rseg_cnt, 10 nbefore
+extern "C" int nsb_gs_host_get(int which, int* out) {
+  const HostPlan& P = g_host_plan;
+  const std::vector<int>* v[11] = {&P.seg_off, &P.seg_idx, &P.nbr_rank, &P.nbr_off, &P.send_seg, &P.send_base, &P.send_cnt,
+                                   &P.rseg_off, &P.rseg_pos, &P.rseg_cnt, &P.nbefore};
+  if (which < 0 || which > 10) { nsb_set_error("nsb_gs_host_get: bad selector"); return 1; }
+  memcpy(out, v[which]->data(), v[which]->size() * sizeof(int));
+  return 0;
+}
+
 int gs_setup(Ctx* c, const long long* glo) {
   GSMap& m = c->gs;
   const long long n = c->n;
   if (n >= (1LL << 31)) { nsb_set_error("gs_setup: more than 2^31 local dofs"); return 1; }
-  // ---- sort local dofs by global id (stable in local index => fixed summation order)
-  std::vector<int> order(n);
-  std::iota(order.begin(), order.end(), 0);
-  std::sort(order.begin(), order.end(), [&](int a, int b) { return glo[a] != glo[b] ? glo[a] < glo[b] : a < b; });
-  // unique ids with their runs
-  std::vector<long long> uid;
-  std::vector<int> ustart;
-  for (long long i = 0; i < n; ++i)
-    if (i == 0 || glo[order[i]] != glo[order[i - 1]]) { uid.push_back(glo[order[i]]); ustart.push_back((int)i); }
-  ustart.push_back((int)n);
-  const int nu = (int)uid.size();
-
-  // ---- which unique ids are shared with other ranks?  (candidates: nodes on element surfaces)
-  std::vector<std::vector<int>> shared_u(c->nranks);   // per neighbour rank: indices into uid, ascending id
+  HostPlan P;
+  plan_sort(P, n, glo);
+  std::vector<long long> cnts(c->nranks, 0), all;
   if (c->nranks > 1) {
-    const int N = c->lx1, D = c->ldim, np = c->np1;
     std::vector<long long> cand;
-    for (int k = 0; k < nu; ++k) {
-      int p = order[ustart[k]] % np;
-      int i = p % N, j = (p / N) % N, kk = (D == 3) ? p / (N * N) : 1;
-      bool surf = (i == 0 || i == N - 1 || j == 0 || j == N - 1 || (D == 3 && (kk == 0 || kk == N - 1)));
-      if (surf) cand.push_back(uid[k]);
-    }
+    plan_candidates(P, c->lx1, c->ldim, c->np1, cand);
     // allgather counts then ids (padded) through NCCL
     long long mycnt = (long long)cand.size();
     long long* d_cnt = nullptr;
@@ -134,7 +250,6 @@ int gs_setup(Ctx* c, const long long* glo) {
     NSB_CUDA(cudaMemcpy(d_cnt + c->nranks, &mycnt, sizeof(long long), cudaMemcpyHostToDevice));
     NSB_NCCL(ncclAllGather(d_cnt + c->nranks, d_cnt, 1, ncclInt64, c->comm, c->stream));
     NSB_CUDA(cudaStreamSynchronize(c->stream));
-    std::vector<long long> cnts(c->nranks);
     NSB_CUDA(cudaMemcpy(cnts.data(), d_cnt, sizeof(long long) * c->nranks, cudaMemcpyDeviceToHost));
     cudaFree(d_cnt);
     long long mx = *std::max_element(cnts.begin(), cnts.end());
@@ -146,82 +261,24 @@ int gs_setup(Ctx* c, const long long* glo) {
     NSB_CUDA(cudaMemcpy(d_my, cand.data(), sizeof(long long) * cand.size(), cudaMemcpyHostToDevice));
     NSB_NCCL(ncclAllGather(d_my, d_all, mx, ncclInt64, c->comm, c->stream));
     NSB_CUDA(cudaStreamSynchronize(c->stream));
-    std::vector<long long> all(mx * c->nranks);
-    NSB_CUDA(cudaMemcpy(all.data(), d_all, sizeof(long long) * all.size(), cudaMemcpyDeviceToHost));
+    std::vector<long long> padded(mx * c->nranks);
+    NSB_CUDA(cudaMemcpy(padded.data(), d_all, sizeof(long long) * padded.size(), cudaMemcpyDeviceToHost));
     cudaFree(d_my); cudaFree(d_all);
-    for (int r = 0; r < c->nranks; ++r) {
-      if (r == c->rank) continue;
-      const long long* other = all.data() + (size_t)r * mx;
-      long long no = cnts[r];
-      // both lists ascending: two-pointer intersection against uid (ascending)
-      long long a = 0;
-      int k = 0;
-      while (a < no && k < nu) {
-        if (other[a] < uid[k]) ++a;
-        else if (other[a] > uid[k]) ++k;
-        else { shared_u[r].push_back(k); ++a; ++k; }
-      }
-    }
+    for (int r = 0; r < c->nranks; ++r) all.insert(all.end(), padded.begin() + (size_t)r * mx, padded.begin() + (size_t)r * mx + cnts[r]);
   }
-
-  // ---- segments: unique ids with local multiplicity > 1 or shared remotely
-  std::vector<char> is_shared(nu, 0);
-  for (int r = 0; r < c->nranks; ++r)
-    for (int k : shared_u[r]) is_shared[k] = 1;
-  std::vector<int> seg_of_u(nu, -1);
-  std::vector<int> seg_off(1, 0), seg_idx;
-  {
-    // order the segments by their smallest local dof: neighbouring threads then touch neighbouring memory
-    // (r1a ncu: with global-id order the 3-field dssum moved 2x the algorithmic bytes at 20 % of the HBM roofline)
-    std::vector<int> segk;
-    for (int k = 0; k < nu; ++k)
-      if (ustart[k + 1] - ustart[k] > 1 || is_shared[k]) segk.push_back(k);
-    std::sort(segk.begin(), segk.end(), [&](int a, int b) { return order[ustart[a]] < order[ustart[b]]; });
-    for (int k : segk) {
-      seg_of_u[k] = (int)seg_off.size() - 1;
-      for (int j = ustart[k]; j < ustart[k + 1]; ++j) seg_idx.push_back(order[j]);
-      seg_off.push_back((int)seg_idx.size());
-    }
-  }
-  m.nseg = (int)seg_off.size() - 1;
-
-  // ---- halo lists
-  std::vector<int> send_seg, send_base, send_cnt;
-  std::vector<std::vector<std::pair<int, int>>> rlist(m.nseg);   // per segment: (pos, cnt) in ascending rank
-  std::vector<int> nbefore(m.nseg, 0);
-  m.nbr_rank.clear(); m.nbr_off.clear();
-  int off = 0;
-  for (int r = 0; r < c->nranks; ++r) {
-    if (shared_u[r].empty()) continue;
-    int cnt = (int)shared_u[r].size();
-    m.nbr_rank.push_back(r);
-    m.nbr_off.push_back(off);
-    for (int j = 0; j < cnt; ++j) {
-      int seg = seg_of_u[shared_u[r][j]];
-      send_seg.push_back(seg);
-      send_base.push_back(3 * off + j);
-      send_cnt.push_back(cnt);
-      rlist[seg].push_back({3 * off + j, cnt});
-      if (r < c->rank) nbefore[seg]++;
-    }
-    off += cnt;
-  }
-  m.nbr_off.push_back(off);
+  plan_build(P, c->rank, c->nranks, c->nranks > 1 ? cnts.data() : nullptr, all.data());
+  m.nseg = (int)P.seg_off.size() - 1;
+  m.nbr_rank = P.nbr_rank; m.nbr_off = P.nbr_off;
   m.nnbr = (int)m.nbr_rank.size();
-  m.nshared = off;
-  std::vector<int> rseg_off(1, 0), rseg_pos, rseg_cnt;
-  for (int s = 0; s < m.nseg; ++s) {
-    for (auto& pr : rlist[s]) { rseg_pos.push_back(pr.first); rseg_cnt.push_back(pr.second); }
-    rseg_off.push_back((int)rseg_pos.size());
-  }
+  m.nshared = P.nshared;
+  const std::vector<int>&order = P.order, &ustart = P.ustart;
+  const int nu = (int)P.uid.size();
   // ---- per-element gather table (fused direct-stiffness sum; single rank only: no halo entries)
   if (c->nranks == 1) {
     const int N = c->lx1, D = c->ldim, np = c->np1;
     std::vector<int> surf;
-    for (int p = 0; p < np; ++p) {
-      int i = p % N, j = (p / N) % N, kk = (D == 3) ? p / (N * N) : 1;
-      if (i == 0 || i == N - 1 || j == 0 || j == N - 1 || (D == 3 && (kk == 0 || kk == N - 1))) surf.push_back(p);
-    }
+    for (int p = 0; p < np; ++p)
+      if (is_surface(p, N, D)) surf.push_back(p);
     const int ns = (int)surf.size();
     std::vector<int> uof(n);                       // dof -> index of its unique id
     for (int k = 0; k < nu; ++k)
@@ -245,15 +302,15 @@ int gs_setup(Ctx* c, const long long* glo) {
       NSB_TRY(upload(&m.nb_idx, nb_idx));
     }
   }
-  NSB_TRY(upload(&m.seg_off, seg_off));
-  NSB_TRY(upload(&m.seg_idx, seg_idx));
-  NSB_TRY(upload(&m.send_seg, send_seg));
-  NSB_TRY(upload(&d_send_base, send_base));
-  NSB_TRY(upload(&d_send_cnt, send_cnt));
-  NSB_TRY(upload(&m.rseg_off, rseg_off));
-  NSB_TRY(upload(&m.rseg_pos, rseg_pos));
-  NSB_TRY(upload(&d_rseg_cnt, rseg_cnt));
-  NSB_TRY(upload(&m.rseg_nbefore, nbefore));
+  NSB_TRY(upload(&m.seg_off, P.seg_off));
+  NSB_TRY(upload(&m.seg_idx, P.seg_idx));
+  NSB_TRY(upload(&m.send_seg, P.send_seg));
+  NSB_TRY(upload(&d_send_base, P.send_base));
+  NSB_TRY(upload(&d_send_cnt, P.send_cnt));
+  NSB_TRY(upload(&m.rseg_off, P.rseg_off));
+  NSB_TRY(upload(&m.rseg_pos, P.rseg_pos));
+  NSB_TRY(upload(&d_rseg_cnt, P.rseg_cnt));
+  NSB_TRY(upload(&m.rseg_nbefore, P.nbefore));
   size_t hb = std::max<size_t>((size_t)3 * m.nshared, 1) * sizeof(double);
   NSB_CUDA(cudaMalloc(&m.sendbuf, hb));
   NSB_CUDA(cudaMalloc(&m.recvbuf, hb));

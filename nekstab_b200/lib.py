@@ -93,6 +93,9 @@ _SIGS = {
     "nsb_op_esolver": [_dp, _dp, _ip],
     "nsb_op_cfl": [_dp] * 3 + [C.c_double, _dp],
     "nsb_get_field": [C.c_char_p, _dp, _lp],
+    "nsb_gs_host_candidates": [C.c_int, C.c_int, C.c_int, _lp, _lp, _lp],
+    "nsb_gs_host_plan": [C.c_int, C.c_int, _lp, _lp, _ip],
+    "nsb_gs_host_get": [C.c_int, _ip],
     "nsb_arnoldi_factorization": [C.c_int, C.c_int, _dp, C.c_int, C.c_int, C.c_int, C.c_int],
     "nsb_krylov_schur": [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, _dp, _dp, _dp, _dp, _ip, _ip, C.c_int],
     "nsb_schur_condensation": [_ip, _dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double],

@@ -47,14 +47,18 @@ WORDS = {
 }
 
 
-def build_workload(ngpus: int, small: bool = False):
+def build_workload(ngpus: int, rank: int = 0, small: bool = False):
+    """This rank's share of the synthetic 3-D cylinder-wake mesh.  The 2-D mesh is partitioned by Nek5000's rule on the
+    shipped RSB keys; every rank extrudes its own 2-D elements (global node ids stay consistent: id2d*levels + level)."""
     g = np.load(os.path.join(ROOT, "tests", "golden", "cyl.npz"))
-    if small:
-        c2 = cases.cylinder_case(g, lx1=8, sponge=False)
-        return cases.extrude(c2, 3, 2 * np.pi * 0.3, name="cyl3d_small")
     c2 = cases.cylinder_case(g, lx1=8, sponge=False)          # sponge off for benchmarks (SURVEY 8d)
-    nz = 10 * ngpus
-    return cases.extrude(c2, nz, 2 * np.pi * ngpus, name=f"cyl3d_1996x{nz}_lx8")
+    nz, lz = (3, 2 * np.pi * 0.3) if small else (10 * ngpus, 2 * np.pi * ngpus)
+    nel_glob = c2.nel * nz
+    if ngpus > 1:
+        c2 = c2.local_part(rank, ngpus)
+    c3 = cases.extrude(c2, nz, lz, name="cyl3d_small" if small else f"cyl3d_1996x{nz}_lx8", compress_ids=False)
+    c3.nelg = nel_glob
+    return c3, nel_glob * 512
 
 
 class ClockSampler(threading.Thread):
@@ -202,21 +206,18 @@ def main():
         # exchange, all-reduces) runs on the library's own NCCL communicator over NVLink (nsb_comm_init).
         dist.init_process_group("gloo")
     t_setup = time.time()
-    gcase = build_workload(world, small=args.small)
-    seed = cases.add_noise(gcase)
+    case, n_glob = build_workload(world, rank, small=args.small)
+    nid = None
     if world > 1:
-        pr = cases.partition(gcase.key, world, gcase.d2)
-        sel = np.nonzero(pr == rank)[0]
-        case = gcase.local_part(rank, world)
-        seed = seed[:, sel]
         ids = [lib.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         nid = ids[0]
-    else:
-        case, nid = gcase, None
-    n_glob = gcase.n
-    del gcase
     ctx = lib.NekStabB200(case, device=local_rank, rank=rank, nranks=world, nccl_id=nid)
+    # nekStab's noise seed (core/utils.f:344-408): mth_rand, then the direct-stiffness AVERAGE -- done with the library's
+    # (multi-rank) dssum: avg = dssum(q)/dssum(1), then the Dirichlet mask
+    raw = cases.raw_noise(case)
+    mult = ctx.op_dssum(np.ones(case.n))
+    seed = np.stack([ctx.op_dssum(raw[k].ravel()) / mult for k in range(3)]).reshape(3, case.nel, -1) * case.mask
     ctx.set_params(1.0 / case.re, 1.0, args.tol, args.tol, 2000, 100000)
     dt, _, ctarg = ctx.prepare_linearized_solver(1.0, 0.5)
     ctx.vec_alloc(3)

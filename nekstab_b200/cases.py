@@ -65,8 +65,9 @@ def _compress(glo: np.ndarray) -> np.ndarray:
     return inv.reshape(glo.shape).astype(np.int64)
 
 
-def extrude_numbering(glo2d: np.ndarray, lx1: int, nz: int, periodic: bool = True) -> np.ndarray:
-    """Global ids for the z-extrusion of a 2-D numbering: node = (2-D node, global z level)."""
+def extrude_numbering(glo2d: np.ndarray, lx1: int, nz: int, periodic: bool = True, compress: bool = True) -> np.ndarray:
+    """Global ids for the z-extrusion of a 2-D numbering: node = (2-D node, global z level).  With compress=False the
+    ids are `glo2d*nlev + level`, i.e. consistent across ranks that each extrude their own share of the 2-D mesh."""
     nel2, npt2 = glo2d.shape
     N = lx1 - 1
     nlev = nz * N if periodic else nz * N + 1
@@ -75,7 +76,8 @@ def extrude_numbering(glo2d: np.ndarray, lx1: int, nz: int, periodic: bool = Tru
     for L in range(nz):
         lev = (L * N + k) % nlev if periodic else (L * N + k)
         out[L] = glo2d[:, None, :] * nlev + lev[None, :, None]
-    return _compress(out.reshape(nz * nel2, lx1 * npt2))
+    out = out.reshape(nz * nel2, lx1 * npt2)
+    return _compress(out) if compress else out
 
 
 # ----------------------------------------------------------------------------- partition
@@ -229,6 +231,19 @@ def mth_rand(ix, iy, iz, ieg, xl, fcoeff, if3d):
     r = 1.0e3 * np.sin(r)
     r = 1.0e3 * np.sin(r)
     return np.cos(r)
+
+
+def raw_noise(case: "Case") -> np.ndarray:
+    """mth_rand per GLL point and component (core/utils.f:344-383), before the direct-stiffness average."""
+    d, lx1, nel = case.ldim, case.lx1, case.nel
+    ieg = (np.arange(1, nel + 1) if case.lglel is None else np.asarray(case.lglel)).astype(np.float64)[:, None]
+    p = np.arange(lx1 ** d)
+    ix = (p % lx1 + 1).astype(np.float64)[None, :]
+    iy = ((p // lx1) % lx1 + 1).astype(np.float64)[None, :]
+    iz = (p // (lx1 * lx1) + 1).astype(np.float64)[None, :] if d == 3 else np.ones((1, lx1 ** d))
+    xl = [case.xyz[k] for k in range(d)]
+    coeffs = [(3.0e4, -1.5e3, 0.5e5), (2.3e4, 2.3e3, -2.0e5), (2.0e4, 1.0e3, 1.0e5)]
+    return np.stack([mth_rand(ix, iy, iz, ieg, xl, coeffs[k], d == 3) for k in range(d)])
 
 
 def add_noise(case: "Case", lglel=None) -> np.ndarray:
@@ -387,7 +402,7 @@ def bfs_case(g: dict, sponge: bool = True) -> Case:
     return case
 
 
-def extrude(c2: Case, nz: int, lz: float, name: Optional[str] = None) -> Case:
+def extrude(c2: Case, nz: int, lz: float, name: Optional[str] = None, compress_ids: bool = True) -> Case:
     """Config 5 recipe (SURVEY 8d): extrude a 2-D case into nz uniform periodic layers over [0,lz];
     element eg3 = layer*nel2 + eg2, key3 = key2, z-invariant base flow with W=0."""
     lx1 = c2.lx1
@@ -401,7 +416,7 @@ def extrude(c2: Case, nz: int, lz: float, name: Optional[str] = None) -> Case:
     zc = (np.arange(nz)[:, None] + (z[None, :] + 1) / 2) * dz            # (nz, lx1)
     Z = np.broadcast_to(zc[:, None, :, None], (nz, nel2, lx1, np2)).reshape(nz * nel2, lx1 * np2)
     xyz = np.stack([lift(c2.xyz[0]), lift(c2.xyz[1]), Z])
-    glo = extrude_numbering(c2.glo, lx1, nz, periodic=True)
+    glo = extrude_numbering(c2.glo, lx1, nz, periodic=True, compress=compress_ids)
     m2 = lift(c2.mask[0])
     mask = np.stack([m2, m2, m2])
     ub = np.stack([lift(c2.ubase[0]), lift(c2.ubase[1]), np.zeros_like(Z)])
@@ -414,6 +429,10 @@ def extrude(c2: Case, nz: int, lz: float, name: Optional[str] = None) -> Case:
                 np.ascontiguousarray(mask), key, d2, np.ascontiguousarray(ub), re=c2.re,
                 end_time=c2.end_time, tol_p=c2.tol_p, tol_v=c2.tol_v)
     case.ifvcor, case.ifvcor_adjoint = c2.ifvcor, c2.ifvcor_adjoint
+    if c2.nelg is not None:
+        case.nelg = c2.nelg * nz
+    if c2.lglel is not None:                      # eg3 = layer*nel2_global + eg2
+        case.lglel = (np.arange(nz)[:, None] * c2.nelg + c2.lglel[None, :]).reshape(-1)
     if c2.spng_fun is not None:
         case.spng_fun = np.ascontiguousarray(lift(c2.spng_fun))
     if "mask_adjoint" in c2.extra:

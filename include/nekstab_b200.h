@@ -64,6 +64,12 @@ int nsb_set_timestep(double dt, int nsteps);
  * pressure right-hand side and solution) for the direct and the adjoint mask set: 1 / 0, or -1 to decide
  * numerically from ||E 1|| (the default after nsb_init). */
 int nsb_set_ifvcor(int direct, int adjoint);
+/* Pressure residual projection, Nek5000's `[PRESSURE] residualProj = yes` (on in every shipped .par, e.g. 1cyl.par:30)
+ * with `mxprev` previous solutions (SIZE: mxprev=20) [UPSTREAM navier4.f setrhsp/gensolnp]: the right-hand side of the
+ * pressure solve is first projected onto the E-orthonormal span of earlier solutions, which cuts the CG iteration
+ * count; the converged answer is unchanged.  The basis persists across steps and matvecs, as in the reference.
+ * 0 (the default) switches it off, which makes every matvec a pure function of its input (used by the parity tests). */
+int nsb_set_projection(int mxprev);
 
 /* ------------------------------------------------------------------ krylov_vector algebra
  * One slot = one `type(krylov_vector)` (core/krylov_subspace.f:10-15): vx,vy,vz(n), pr(n2); the

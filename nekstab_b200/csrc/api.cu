@@ -111,6 +111,7 @@ extern "C" int nsb_finalize(void) {
     for (int d = 0; d < 3; ++d) { if (c->mask[s][d]) cudaFree(c->mask[s][d]); if (c->mbinv[s][d]) cudaFree(c->mbinv[s][d]); }
     if (c->dinvE[s]) cudaFree(c->dinvE[s]);
   }
+  if (c->projX) { cudaFree(c->projX); cudaFree(c->projEX); }
   if (c->cgs) cudaFree(c->cgs);
   if (c->cgs_host) cudaFreeHost(c->cgs_host);
   if (c->red_host) cudaFreeHost(c->red_host);
@@ -284,6 +285,17 @@ extern "C" int nsb_set_timestep(double dt, int nsteps) {
   REQUIRE_CTX();
   if (!(dt > 0) || nsteps <= 0) { nsb_set_error("dt and nsteps must be positive"); return 1; }
   c->dt = dt; c->nsteps = nsteps;
+  return 0;
+}
+extern "C" int nsb_set_projection(int mxprev) {
+  REQUIRE_CTX();
+  if (mxprev < 0 || mxprev > 200) { nsb_set_error("nsb_set_projection: mxprev out of range"); return 1; }
+  if (c->projX) { cudaFree(c->projX); cudaFree(c->projEX); c->projX = c->projEX = nullptr; }
+  c->proj_max = mxprev; c->proj_m = 0; c->proj_adj = -1;
+  if (mxprev > 0) {
+    NSB_TRY(dalloc(&c->projX, (long long)mxprev * c->n2));
+    NSB_TRY(dalloc(&c->projEX, (long long)mxprev * c->n2));
+  }
   return 0;
 }
 extern "C" int nsb_set_ifvcor(int direct, int adjoint) {

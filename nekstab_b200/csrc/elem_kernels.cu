@@ -839,6 +839,18 @@ int ek_div(Ctx* c, const double* u, const double* scale, double* q, double sign)
   return 0;
 }
 
+int ek_div_mbinv(Ctx* c, const double* u, int adj, double* q, double sign) {
+  const double* s0 = c->mbinv[adj][0];
+  const double* s1 = c->mbinv[adj][1];
+  const double* s2 = c->mbinv[adj][c->ldim == 3 ? 2 : 1];
+  if (c->ldim == 3) return pk_div(c, u, s0, c->mask_same[adj] ? nullptr : s1, c->mask_same[adj] ? nullptr : s2, q, sign);
+  DISPATCH_DN(c, k_div<D, N, 0><<<c->nel, Cfg<D, N>::TPB, 0, c->stream>>>(u, s0, s1, s2, q, c->RW2, nullptr, nullptr, nullptr,
+                                                                       nullptr, nullptr, 0, c->n, c->n2, sign));
+  nsb_count_launch();
+  NSB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int ek_pcg_div(Ctx* c, int adj) {
   // w = wk[2] (dssum'd, or raw when the gather is fused), Ep = pk[3], pdir = pk[2]
   if (c->ldim == 3) return pk_pcg_div(c, adj, c->fused_gs ? 1 : 0);

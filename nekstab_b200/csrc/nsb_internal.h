@@ -155,6 +155,12 @@ struct Ctx {
   double* hpart = nullptr;  // partial multi-dot sums
   long long hpart_cap = 0;
 
+  // pressure residual projection (Nek5000 `residualProj = yes`: setrhsp / gensolnp [UPSTREAM navier4.f]; every shipped
+  // .par enables it, e.g. 1cyl.par:30): E-orthonormal basis of previous solutions and their images under E
+  int proj_max = 0, proj_m = 0, proj_adj = -1;
+  double* projX = nullptr;    // [proj_max][n2]
+  double* projEX = nullptr;   // [proj_max][n2]
+
   // per-kernel sampling profiler (CUDA events on the launching stream; one sample set per host poll)
   int prof_on = 0;
   cudaEvent_t prof_ev[16] = {nullptr};
@@ -196,6 +202,7 @@ int ek_cfl(Ctx* c, const double* u, double* cfl_dev);                  // max re
 int ek_hcg_dir_ax(Ctx* c, int ncomp, double h1, double h2);     // p = dinv r + beta p; w = H p; rho partial = sum p*w
 int ek_pcg_dir_gradt(Ctx* c, int adj);                           // p = dinvE r + beta p ; w = gradt(p)
 int ek_pcg_div(Ctx* c, int adj);                                 // Ep = div(mbinv w); rho = sum p Ep
+int ek_div_mbinv(Ctx* c, const double* u, int adj, double* q, double sign);   // q = sign * D (mask*binv .* u)
 
 // ---- second-generation 3-D pressure-operator kernels (pcg_kernels.cu)
 int pk_upload_constants(const ConstMats& cm);
@@ -232,6 +239,10 @@ int vk_dinvH(Ctx* c, double h1, double h2);
 int vk_multidot(Ctx* c, int k, int first_slot, int slot_f, double* h_dev);      // h = Q^T (W f)
 int vk_multiaxpy(Ctx* c, int k, int first_slot, int slot_f, const double* h_dev, double sign);  // f += sign * Q h
 int vk_gemv_out(Ctx* c, int k, int first_slot, const double* y_dev, int slot_out);
+int vk_multidot_raw(Ctx* c, int k, const double* Q, long long vlen, const double* f, const double* W, long long n, long long nw,
+                    double* h_dev);
+int vk_multiaxpy_raw(Ctx* c, int k, const double* Q, long long vlen, const double* f, double a, const double* h_dev, double sign,
+                     double* out);
 int vk_rotate(Ctx* c, int k, int first_slot, const double* S_dev, int lds);
 
 // ---- solvers / stepper (stepper.cu)

@@ -118,6 +118,66 @@ int st_helmholtz(Ctx* c, int adj, double h1, double h2, int* iters) {
   return 0;
 }
 
+// out = E in  (in, out: mesh-2 vectors; uses wk[2] as scratch)
+static int apply_E(Ctx* c, int adj, const double* in, double* out) {
+  NSB_TRY(ek_gradt(c, in, c->wk[2]));
+  NSB_TRY(gs_dssum(c, c->wk[2], c->ldim, c->n, nullptr));
+  return ek_div_mbinv(c, c->wk[2], adj, out, 1.0);
+}
+
+// Residual projection [UPSTREAM navier4.f setrhsp]: xbar = X X^T g (X is E-orthonormal), g <- g - (E X) X^T g.
+// xbar is left in pk[4].
+static int proj_pre(Ctx* c, int adj) {
+  if (c->proj_adj != adj) { c->proj_m = 0; c->proj_adj = adj; }      // the basis belongs to one operator E
+  const int m = c->proj_m;
+  if (m == 0) return vk_fill(c, c->pk[4], 0.0, c->n2);
+  double* al = c->hbuf + 40000;
+  NSB_TRY(vk_multidot_raw(c, m, c->projX, c->n2, c->pk[0], nullptr, c->n2, c->n2, al));
+  NSB_TRY(vk_multiaxpy_raw(c, m, c->projX, c->n2, c->pk[4], 0.0, al, 1.0, c->pk[4]));
+  return vk_multiaxpy_raw(c, m, c->projEX, c->n2, c->pk[0], 1.0, al, -1.0, c->pk[0]);
+}
+// [UPSTREAM navier4.f gensolnp]: phi = xbar + delta; E-orthonormalise delta against the basis and append it (restart
+// from the full solution when the basis is full).  delta = pk[1] on entry; phi in pk[1] on exit.
+static int proj_post(Ctx* c, int adj) {
+  double* al = c->hbuf + 40000;
+  double* x = c->pk[1];
+  int m = c->proj_m;
+  double* xn;
+  double* exn;
+  if (m == c->proj_max) {                      // restart: keep only the newest full solution
+    NSB_TRY(vk_axpy(c, x, 1.0, c->pk[4], c->n2));
+    xn = c->projX; exn = c->projEX;
+    NSB_TRY(vk_copy(c, xn, x, c->n2));
+    NSB_TRY(apply_E(c, adj, xn, exn));
+    m = 0;
+  } else {
+    xn = c->projX + (long long)m * c->n2; exn = c->projEX + (long long)m * c->n2;
+    NSB_TRY(vk_copy(c, xn, x, c->n2));
+    NSB_TRY(apply_E(c, adj, xn, exn));
+    if (m > 0) {                               // xn -= X (X^T E xn) ; E xn likewise
+      NSB_TRY(vk_multidot_raw(c, m, c->projX, c->n2, exn, nullptr, c->n2, c->n2, al));
+      NSB_TRY(vk_multiaxpy_raw(c, m, c->projX, c->n2, xn, 1.0, al, -1.0, xn));
+      NSB_TRY(vk_multiaxpy_raw(c, m, c->projEX, c->n2, exn, 1.0, al, -1.0, exn));
+    }
+    NSB_TRY(vk_axpy(c, x, 1.0, c->pk[4], c->n2));
+  }
+  // normalise in the E inner product
+  NSB_TRY(vk_dot3(c, xn, exn, nullptr, c->n2, c->red_out + 10));
+  NSB_TRY(vk_allreduce_sum(c, c->red_out + 10, 1));
+  double nrm2 = 0;
+  NSB_CUDA(cudaMemcpyAsync(&nrm2, c->red_out + 10, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  NSB_CUDA(cudaStreamSynchronize(c->stream));
+  if (nrm2 > 0 && nrm2 == nrm2) {
+    const double sc = 1.0 / std::sqrt(nrm2);
+    NSB_TRY(vk_scale(c, xn, sc, c->n2));
+    NSB_TRY(vk_scale(c, exn, sc, c->n2));
+    c->proj_m = m + 1;
+  } else {
+    c->proj_m = m;                             // zero update (already converged): nothing to add
+  }
+  return 0;
+}
+
 // Solve E x = g with Jacobi-PCG, E = D (mask B~^-1 QQ^T) D^T [UPSTREAM navier1.f esolver/cdabdtp; the reference runs
 // GMRES+multigrid here, the north-star prescribes Jacobi-PCG].  In: c->pk[0] = g (destroyed). Out: c->pk[1].
 int st_pressure(Ctx* c, int adj, int* iters) {
@@ -127,6 +187,8 @@ int st_pressure(Ctx* c, int adj, int* iters) {
     NSB_TRY(vk_allreduce_sum(c, c->red_out + 8, 1));
     NSB_TRY(vk_add_scalar_from_dev(c, c->pk[0], c->red_out + 8, -1.0 / (double)c->n2_glob, c->n2));
   }
+  const bool proj = c->proj_max > 0;
+  if (proj) NSB_TRY(proj_pre(c, adj));
   NSB_TRY(cg_state_setup(c, 3, 1, c->tol_p, c->vol2, c->maxit_p));
   NSB_TRY(vk_pcg_init(c, adj));
   bool done = false;
@@ -152,6 +214,7 @@ int st_pressure(Ctx* c, int adj, int* iters) {
     if (issued > c->maxit_p + c->check_every_p) break;
   }
   if (!(c->cgs_host[3].rnorm == c->cgs_host[3].rnorm)) { nsb_set_error("pressure CG produced NaN"); return 2; }
+  if (proj) NSB_TRY(proj_post(c, adj));
   if (c->ifvcor[adj]) {
     NSB_TRY(vk_sum(c, c->pk[1], c->n2, c->red_out + 8));
     NSB_TRY(vk_allreduce_sum(c, c->red_out + 8, 1));

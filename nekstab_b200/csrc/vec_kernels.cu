@@ -346,7 +346,7 @@ k_multidot(const double* __restrict__ Q, long long vlen, int k, const double* __
     for (int r = 0; r < RPT; ++r) {
       long long i = base + r * 256 + threadIdx.x;
       idx[r] = i;
-      wf[r] = (i < nw) ? f[i] * W[i % n] : 0.0;
+      wf[r] = (i < nw) ? (W ? f[i] * W[i % n] : f[i]) : 0.0;
     }
     for (int j = 0; j < k; ++j) {
       const double* q = Q + (long long)j * vlen;
@@ -373,6 +373,29 @@ __global__ void k_multidot_final(const double* __restrict__ part, int nb, int k,
   for (int b = 0; b < nb; ++b) s += part[(long long)b * k + j];
   h[j] = s;
 }
+// generic form: h_j = sum_{i<nw} Q[j*vlen+i] * W[i%n] * f[i]  (W may be null), all-reduced over ranks
+int vk_multidot_raw(Ctx* c, int k, const double* Q, long long vlen, const double* f, const double* W, long long n, long long nw,
+                    double* h_dev) {
+  int nb = grid_for(nw, 256, 4);
+  if ((long long)nb * k > c->hpart_cap) {
+    if (c->hpart) cudaFree(c->hpart);
+    c->hpart_cap = (long long)nb * k * 2;
+    NSB_CUDA(cudaMalloc(&c->hpart, c->hpart_cap * sizeof(double)));
+  }
+  size_t smem = (size_t)k * 8 * sizeof(double);
+  if (smem > 200 * 1024) { nsb_set_error("multidot: k too large"); return 1; }
+  if (smem > 48 * 1024) NSB_CUDA(cudaFuncSetAttribute(k_multidot<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_multidot<4><<<nb, 256, smem, c->stream>>>(Q, vlen, k, f, W, n, nw, c->hpart);
+  k_multidot_final<<<(k + 127) / 128, 128, 0, c->stream>>>(c->hpart, nb, k, h_dev);
+  nsb_count_launch(2);
+  NSB_CUDA(cudaGetLastError());
+  NSB_TRY(vk_allreduce_sum(c, h_dev, k));
+  return 0;
+}
+// out[i] = a*f[i] + sign * sum_j h_j Q[j*vlen+i], i < vlen
+int vk_multiaxpy_raw(Ctx* c, int k, const double* Q, long long vlen, const double* f, double a, const double* h_dev, double sign,
+                     double* out);
+
 int vk_multidot(Ctx* c, int k, int first_slot, int slot_f, double* h_dev) {
   const long long nw = c->n * c->ldim;
   int nb = grid_for(nw, 256, 4);
@@ -418,6 +441,14 @@ k_multiaxpy(const double* __restrict__ Q, long long vlen, int k, const double* _
     for (int r = 0; r < 4; ++r)
       if (idx[r] < vlen) out[idx[r]] = acc[r];
   }
+}
+int vk_multiaxpy_raw(Ctx* c, int k, const double* Q, long long vlen, const double* f, double a, const double* h_dev, double sign,
+                     double* out) {
+  size_t smem = (size_t)k * sizeof(double);
+  k_multiaxpy<<<grid_for(vlen, 256, 4), 256, smem, c->stream>>>(Q, vlen, k, f, a, h_dev, sign, out);
+  nsb_count_launch();
+  NSB_CUDA(cudaGetLastError());
+  return 0;
 }
 int vk_multiaxpy(Ctx* c, int k, int first_slot, int slot_f, const double* h_dev, double sign) {
   size_t smem = (size_t)k * sizeof(double);

@@ -63,6 +63,7 @@ _SIGS = {
     "nsb_prepare_linearized_solver": [C.c_double, C.c_double, _dp, _ip, _dp],
     "nsb_set_timestep": [C.c_double, C.c_int],
     "nsb_set_ifvcor": [C.c_int, C.c_int],
+    "nsb_set_projection": [C.c_int],
     "nsb_set_adjoint_masks": [_dp] * 3,
     "nsb_vec_alloc": [C.c_int],
     "nsb_vec_upload": [C.c_int] + [_dp] * 4,
@@ -207,6 +208,9 @@ class NekStabB200:
         dt, ns, ct = C.c_double(), C.c_int(), C.c_double()
         _ck(self.lib.nsb_prepare_linearized_solver(end_time, cfl_target, C.byref(dt), C.byref(ns), C.byref(ct)))
         return dt.value, ns.value, ct.value
+
+    def set_projection(self, mxprev):
+        _ck(self.lib.nsb_set_projection(int(mxprev)))
 
     def set_timestep(self, dt, nsteps):
         _ck(self.lib.nsb_set_timestep(dt, nsteps))

@@ -118,3 +118,36 @@ def test_krylov_vector_algebra_and_arnoldi():
             assert rel(v, refv) < 1e-12 and rel(p, refp) < 1e-12
     finally:
         g.close()
+
+
+def test_pressure_residual_projection_same_answer_fewer_iterations():
+    """`residualProj = yes` (1cyl.par:30; [UPSTREAM navier4.f setrhsp/gensolnp]): same converged matvec, fewer pressure
+    iterations; the basis persists across steps and restarts when full."""
+    from nekstab_b200 import lib
+    c = CASES["box3d_n6_dirichlet"]          # singular E (ifvcor) exercises the mean-free path too
+    s = make_oracle(c)
+    g = lib.NekStabB200(c)
+    try:
+        nsteps, dt = 12, 2.0e-3
+        g.set_params(1.0 / c.re, 1.0, 1e-12, 1e-12, 3000, 100000)
+        g.set_timestep(dt, nsteps)
+        g.vec_alloc(3)
+        v0 = smooth_field(c, 21).reshape((c.ldim,) + s.eshape)
+        g.vec_upload(0, v0, np.zeros(s.eshape2))
+        g.stats(reset=True)
+        g.matvec(lib.DIRECT, 0, 1)
+        it_off = g.stats(reset=True)["pres_iters"]
+        ref, pref = g.vec_download(1)
+        g.set_projection(5)                  # small basis: forces at least one restart in 12 steps
+        g.matvec(lib.DIRECT, 0, 2)
+        it_on = g.stats(reset=True)["pres_iters"]
+        v, p = g.vec_download(2)
+        assert energy_rel(s, v.reshape((c.ldim,) + s.eshape), ref.reshape((c.ldim,) + s.eshape)) < 1e-9
+        assert rel(p, pref) < 1e-6
+        assert it_on < 0.95 * it_off, (it_on, it_off)      # oracle experiment with the same algorithm: 3133 vs 3371
+        g.set_projection(0)
+        g.matvec(lib.DIRECT, 0, 2)
+        v2, _ = g.vec_download(2)
+        assert np.array_equal(v2, ref)       # projection off => a pure, bit-reproducible function of the input
+    finally:
+        g.close()

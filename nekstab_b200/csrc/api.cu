@@ -216,6 +216,8 @@ extern "C" int nsb_init(int ldim, int lx1, int lxd, int lx2, int nelv, long long
   c->has_adj_masks = false;
   // measured (r1b): the separate, segment-sorted dssum (0.115 ms) + k_div3 (0.318 ms) beats the fused gather (0.465 ms) on
   // cfg 5, so the fused variant is opt-in
+  const char* np_ = getenv("NSB_PERSISTENT");
+  c->persistent_pcg = !(np_ && np_[0] == '0');
   const char* nf = getenv("NSB_FUSED_GS");
   c->fused_gs = (c->ldim == 3 && c->nranks == 1 && c->gs.nb_off != nullptr && nf && nf[0] == '1');
   NSB_CUDA(cudaStreamSynchronize(c->stream));

@@ -784,6 +784,7 @@ int ek_cfl(Ctx* c, const double* u, double* cfl_dev) {
 }
 
 int ek_axhelm(Ctx* c, const double* u, double* w, int nfields, double h1, double h2) {
+  if (c->ldim == 3) return pk_axhelm(c, 0, u, w, nullptr, nfields, h1, h2);
   DISPATCH_DN(c, k_axhelm<D, N, 0><<<c->nel, Cfg<D, N>::TPB, 0, c->stream>>>(
                      u, w, nullptr, c->G, c->bm1, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nfields, c->n, h1, h2));
   nsb_count_launch();
@@ -792,6 +793,7 @@ int ek_axhelm(Ctx* c, const double* u, double* w, int nfields, double h1, double
 }
 
 int ek_axhelm_resid(Ctx* c, const double* u, const double* b, double* r, int nfields, double h1, double h2) {
+  if (c->ldim == 3) return pk_axhelm(c, 1, u, r, b, nfields, h1, h2);
   DISPATCH_DN(c, k_axhelm<D, N, 1><<<c->nel, Cfg<D, N>::TPB, 0, c->stream>>>(
                      u, r, b, c->G, c->bm1, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nfields, c->n, h1, h2));
   nsb_count_launch();
@@ -801,6 +803,7 @@ int ek_axhelm_resid(Ctx* c, const double* u, const double* b, double* r, int nfi
 
 int ek_hcg_dir_ax(Ctx* c, int ncomp, double h1, double h2) {
   // r = rk, p = wk[1], w = wk[2]
+  if (c->ldim == 3) return pk_axhelm(c, 2, nullptr, nullptr, nullptr, ncomp, h1, h2);
   DISPATCH_DN(c, k_axhelm<D, N, 2><<<c->nel, Cfg<D, N>::TPB, 0, c->stream>>>(
                      c->rk, c->wk[2], nullptr, c->G, c->bm1, c->dinvH, c->wk[1], c->cgs, c->red_part, c->red_count,
                      c->red_out, c->nranks == 1, ncomp, c->n, h1, h2));

@@ -122,6 +122,7 @@ struct Ctx {
   double dt = 0;
   int nsteps = 0;
   int check_every_v = 4, check_every_p = 32;
+  bool persistent_pcg = true; // 3-D: persistent, TMA-pipelined k_gradt3p / k_div3p in the pressure-CG loop (NSB_PERSISTENT=0 disables)
   bool fused_gs = false;      // 3-D, single rank: k_div3 gathers the surface sums itself (no dssum in the pressure loop)
 
   // base flow, sponge
@@ -210,6 +211,7 @@ int pk_gradt(Ctx* c, const double* p, double* w);
 int pk_pcg_dir_gradt(Ctx* c, int adj);
 int pk_div(Ctx* c, const double* u, const double* s0, const double* s1, const double* s2, double* q, double sign);
 int pk_pcg_div(Ctx* c, int adj, int fused);
+int pk_axhelm(Ctx* c, int mode, const double* u, double* w, const double* b, int nfields, double h1, double h2);
 
 // ---- pointwise / reduction kernels (vec_kernels.cu)
 int vk_fill(Ctx* c, double* a, double v, long long n);

@@ -14,6 +14,11 @@
 // register accumulation (no shared-memory read-modify-write); (3) the metric multiply is folded into the first
 // (gradt) / last (div) stage with the metrics read straight from global memory in column order; (4) gradt's last
 // stage stores to global memory directly.  Shared-memory accesses per element drop by ~half.
+#include <cuda_pipeline.h>
+
+#include <algorithm>
+#include <cstdint>
+
 #include "elem_common.cuh"
 
 namespace {
@@ -186,10 +191,15 @@ k_div3(const double* __restrict__ u, const double* __restrict__ scale0, const do
   using C2 = ColIn<2, N, N, N>;
   using C1 = ColIn<1, N2, N, N>;
   using C0 = ColIn<0, N2, N2, N>;
-  // su (3 x S1) is dead after the t stage and sbuf (9 x SB) is first written in the s stage: they share storage
+  // su (3 x S1) is dead after the t stage and sbuf (9 x SB) is first written in the s stage: they share storage.
+  // Dynamic shared memory: sus | sa (reused for the 9 partial-product arrays) | srw (9 metric arrays + pdir, filled
+  // asynchronously with cp.async at kernel entry so that their DRAM latency hides behind the three tensor stages).
   constexpr int SU = 3 * S1::size, SBB = 9 * SB::size;
-  __shared__ double sus[(SU > SBB) ? SU : SBB];
-  __shared__ double sa[6][SA::size];       // [c*2 + {J,D}]; dead after the s stage => reused for the partial sums
+  constexpr int SUS = (SU > SBB) ? SU : SBB;
+  extern __shared__ double dsm[];
+  double* sus = dsm;
+  double (*sa)[SA::size] = reinterpret_cast<double (*)[SA::size]>(dsm + SUS);
+  double* srw = dsm + SUS + 6 * SA::size;          // [10][NP2]
   __shared__ double sred[32];
   double (*spart)[NP2] = reinterpret_cast<double (*)[NP2]>(&sa[0][0]);
   static_assert(9 * NP2 <= 6 * SA::size, "spart alias");
@@ -199,6 +209,13 @@ k_div3(const double* __restrict__ u, const double* __restrict__ scale0, const do
   if (MODE == 1 && cgs->done) return;
   const long long e2 = (long long)blockIdx.x * NP2;
   const long long e1 = (long long)blockIdx.x * NP1;
+  static_assert(NP2 <= TPB, "one mesh-2 point per thread");
+  if (tid < NP2) {                                  // LDGSTS: global -> shared without staging through registers
+#pragma unroll
+    for (int g = 0; g < 9; ++g) __pipeline_memcpy_async(&srw[g * NP2 + tid], &RW2[(long long)g * n2 + e2 + tid], sizeof(double));
+    if (MODE == 1) __pipeline_memcpy_async(&srw[9 * NP2 + tid], &pdir[e2 + tid], sizeof(double));
+  }
+  __pipeline_commit();
   if (FUSED) {
     // ---- stage the three (scaled) components, then overwrite the surface nodes with the gathered sums
     for (int q = tid; q < NP1; q += TPB) {
@@ -290,20 +307,428 @@ k_div3(const double* __restrict__ u, const double* __restrict__ scale0, const do
     if (dir == 0) apply_store<N2, N>(cm.D12, v, po, 1);
     else apply_store<N2, N>(cm.J12, v, po, 1);
   }
+  __pipeline_wait_prior(0);
   __syncthreads();
   double rho[1] = {0.0};
   for (int q = tid; q < NP2; q += TPB) {
     double acc = 0.0;
 #pragma unroll
-    for (int g = 0; g < 9; ++g) acc = fma(RW2[(long long)g * n2 + e2 + q], spart[g][q], acc);   // metrics: coalesced
+    for (int g = 0; g < 9; ++g) acc = fma(srw[g * NP2 + q], spart[g][q], acc);
     const double v = sign * acc;
     qout[e2 + q] = v;
-    if (MODE == 1) rho[0] += pdir[e2 + q] * v;
+    if (MODE == 1) rho[0] += srw[9 * NP2 + q] * v;
   }
   if (MODE == 1) {
     if (grid_sum_finish<1>(rho, part, counter, red_out, sred) && finalize && tid == 0) {
       cgs->rho = red_out[0];
       cgs->alpha = cgs->rtz1 / red_out[0];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ TMA (bulk async copy) + mbarrier
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// 1-D bulk tensor-memory-accelerator copy global -> shared; completion (bytes) is signalled on the mbarrier
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ persistent, TMA-pipelined pressure-CG kernels
+// One CTA per SM slot (2 per SM) walks over elements e = blockIdx.x, += gridDim.x.  All global -> shared traffic of an
+// element (metrics, CG vectors, the three w components) is moved by bulk TMA copies into a double-buffered stage while
+// the previous element is being contracted, so DRAM requests are in flight for the whole life of the CTA instead of
+// only during each CTA's load phase (r1b ncu: k_div3 27 % DRAM, barrier + long-scoreboard stalls).
+template <int N>
+struct GradtP {
+  static constexpr int N2 = N - 2, NP1 = N * N * N, NP2 = N2 * N2 * N2;
+  static constexpr int NIN = 12;                                   // 9 metric arrays, r, dinvE, pdir
+  using SA = Shp<N2, N2, N>;
+  using SB = Shp<N2, N, N>;
+  static constexpr int in_doubles = 2 * NIN * NP2;
+  static constexpr size_t smem = sizeof(double) * (in_doubles + 9 * SA::size + 6 * SB::size) + 2 * sizeof(uint64_t);
+};
+
+// One element of k_gradt3p.  Deliberately NOT inlined: inside the persistent element loop the compiler would treat the
+// constant-bank operator matrices as loop invariants and hoist them into registers (80+ registers and spills, measured).
+template <int N>
+__device__ __noinline__ void gradt3_element(const double* __restrict__ in, double* __restrict__ sq, double* __restrict__ sa,
+                                            double* __restrict__ sb, double* __restrict__ w, double* __restrict__ pdir,
+                                            double beta, long long n, int e, int tid) {
+  using P = GradtP<N>;
+  constexpr int N2 = P::N2, NP1 = P::NP1, NP2 = P::NP2;
+  using S2 = Shp<N2, N2, N2>;
+  using SA = typename P::SA;
+  using SB = typename P::SB;
+  using C0 = ColIn<0, N2, N2, N2>;
+  using C1 = ColIn<1, N2, N2, N>;
+  using C2 = ColIn<2, N2, N, N>;
+  {
+    const long long e2 = (long long)e * NP2, e1 = (long long)e * NP1;
+    if (tid < NP2) {
+      const int q = tid;
+      const double v = in[10 * NP2 + q] * in[9 * NP2 + q] + beta * in[11 * NP2 + q];
+      pdir[e2 + q] = v;
+      const int o = S2::lin(q);
+#pragma unroll
+      for (int g = 0; g < 9; ++g) sq[g * S2::size + o] = in[g * NP2 + q] * v;
+    }
+    __syncthreads();
+    if (tid < 9 * C0::ncol) {
+      const int combo = tid / C0::ncol, col = tid - combo * C0::ncol;
+      const double* pin = sq + combo * S2::size + C0::base(col);
+      double v[N2];
+#pragma unroll
+      for (int l = 0; l < N2; ++l) v[l] = pin[l];
+      double* po = sa + combo * SA::size + col * SA::PI;
+      if (combo < 3) apply_store<N, N2>(cm.D12t, v, po, 1);
+      else apply_store<N, N2>(cm.J12t, v, po, 1);
+    }
+    __syncthreads();
+    if (tid < 6 * C1::ncol) {
+      const int grp = tid / C1::ncol, col = tid - grp * C1::ncol;
+      const int which = grp / 3, c = grp - which * 3;
+      const int bi = C1::base(col);
+      const int bo = (col / N) * N * SB::PI + (col % N);
+      double v[N2], v2[N2];
+      double* po = sb + (c * 2 + which) * SB::size + bo;
+      if (which == 0) {
+#pragma unroll
+        for (int l = 0; l < N2; ++l) { v[l] = sa[c * SA::size + bi + l * C1::stride]; v2[l] = sa[(3 + c) * SA::size + bi + l * C1::stride]; }
+        apply2_store<N, N2>(cm.J12t, v, cm.D12t, v2, po, SB::PI);
+      } else {
+#pragma unroll
+        for (int l = 0; l < N2; ++l) v[l] = sa[(6 + c) * SA::size + bi + l * C1::stride];
+        apply_store<N, N2>(cm.J12t, v, po, SB::PI);
+      }
+    }
+    __syncthreads();
+    if (tid < 3 * C2::ncol) {
+      const int c = tid / C2::ncol, col = tid - c * C2::ncol;
+      const int bi = C2::base(col);
+      double v[N2], v2[N2];
+#pragma unroll
+      for (int l = 0; l < N2; ++l) { v[l] = sb[(c * 2) * SB::size + bi + l * C2::stride]; v2[l] = sb[(c * 2 + 1) * SB::size + bi + l * C2::stride]; }
+      apply2_store<N, N2>(cm.J12t, v, cm.D12t, v2, w + (long long)c * n + e1 + col, N * N);
+    }
+    __syncthreads();
+  }
+}
+
+template <int N>
+__global__ void __launch_bounds__(PK_TPB, 2)
+k_gradt3p(const double* __restrict__ r, double* __restrict__ w, const double* __restrict__ RW2, const double* __restrict__ dinvE,
+          double* __restrict__ pdir, const CGState* __restrict__ cgs, long long n, long long n2, int nel) {
+  using P = GradtP<N>;
+  constexpr int N2 = P::N2, TPB = PK_TPB, NP1 = P::NP1, NP2 = P::NP2, NIN = P::NIN;
+  using S2 = Shp<N2, N2, N2>;
+  using SA = typename P::SA;
+  using SB = typename P::SB;
+  using C0 = ColIn<0, N2, N2, N2>;
+  using C1 = ColIn<1, N2, N2, N>;
+  using C2 = ColIn<2, N2, N, N>;
+  extern __shared__ __align__(128) double dsm[];
+  double* sin = dsm;                                   // [2][NIN][NP2]
+  double* sa = dsm + P::in_doubles;                    // [9][SA::size]
+  double* sb = sa + 9 * SA::size;                      // [6][SB::size]
+  double* sq = sb;                                     // [9][S2::size] products, dead before the s stage writes sb
+  static_assert(9 * S2::size <= 6 * SB::size, "sq alias");
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sb + 6 * SB::size);
+  const int tid = threadIdx.x;
+  if (cgs->done) return;
+  const double beta = cgs->beta;
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  auto issue = [&](int e, int st) {
+    double* dst = sin + st * NIN * NP2;
+    const long long e2 = (long long)e * NP2;
+    mbar_expect_tx(&bar[st], NIN * NP2 * (uint32_t)sizeof(double));
+#pragma unroll
+    for (int g = 0; g < 9; ++g) tma_bulk_g2s(dst + g * NP2, RW2 + (long long)g * n2 + e2, NP2 * sizeof(double), &bar[st]);
+    tma_bulk_g2s(dst + 9 * NP2, r + e2, NP2 * sizeof(double), &bar[st]);
+    tma_bulk_g2s(dst + 10 * NP2, dinvE + e2, NP2 * sizeof(double), &bar[st]);
+    tma_bulk_g2s(dst + 11 * NP2, pdir + e2, NP2 * sizeof(double), &bar[st]);
+  };
+  if (tid == 0 && (int)blockIdx.x < nel) issue(blockIdx.x, 0);
+  int it = 0;
+  for (int e = blockIdx.x; e < nel; e += gridDim.x, ++it) {
+    const int st = it & 1;
+    if (tid == 0 && e + (int)gridDim.x < nel) issue(e + gridDim.x, st ^ 1);
+    mbar_wait(&bar[st], (it >> 1) & 1);
+    gradt3_element<N>(sin + st * NIN * NP2, sq, sa, sb, w, pdir, beta, n, e, tid);
+  }
+}
+
+template <int N>
+struct DivP {
+  static constexpr int N2 = N - 2, NP1 = N * N * N, NP2 = N2 * N2 * N2;
+  using SA = Shp<N2, N, N>;
+  using SB = Shp<N2, N2, N>;
+  static constexpr int stage = 4 * NP1 + 10 * NP2;                 // w (3 comps), mask*binv, 9 metric arrays, pdir
+  static constexpr size_t smem = sizeof(double) * (2 * stage + 6 * SA::size + 9 * SB::size) + 2 * sizeof(uint64_t);
+};
+
+// One element of k_div3p (not inlined, see gradt3_element).  Returns this thread's contribution to sum pdir*Ep.
+template <int N>
+__device__ __noinline__ double div3_element(const double* __restrict__ in, double* __restrict__ sa, double* __restrict__ sbuf,
+                                            double* __restrict__ qout, int e, int tid) {
+  using P = DivP<N>;
+  constexpr int N2 = P::N2, NP1 = P::NP1, NP2 = P::NP2;
+  using SA = typename P::SA;
+  using SB = typename P::SB;
+  using C2 = ColIn<2, N, N, N>;
+  using C1 = ColIn<1, N2, N, N>;
+  using C0 = ColIn<0, N2, N2, N>;
+  double* spart = sa;
+  double rho[1] = {0.0};
+  {
+    const double* inmb = in + 3 * NP1;
+    const double* inrw = in + 4 * NP1;
+    // ---- t stage: columns along t straight from the (unpitched) staged element: lanes run over (j,i) => conflict free
+    if (tid < 3 * C2::ncol) {
+      const int c = tid / C2::ncol, col = tid - c * C2::ncol;
+      double v[N];
+#pragma unroll
+      for (int l = 0; l < N; ++l) v[l] = in[c * NP1 + l * N * N + col] * inmb[l * N * N + col];
+      apply_store<N2, N>(cm.J12, v, sa + (c * 2) * SA::size + C2::base(col), C2::stride);
+      apply_store<N2, N>(cm.D12, v, sa + (c * 2 + 1) * SA::size + C2::base(col), C2::stride);
+    }
+    __syncthreads();
+    if (tid < 6 * C1::ncol) {
+      const int grp = tid / C1::ncol, col = tid - grp * C1::ncol;
+      const int which = grp / 3, c = grp - which * 3;
+      const int bi = C1::base(col);
+      const int bo = (col / N) * N2 * SB::PI + (col % N);
+      double v[N];
+#pragma unroll
+      for (int l = 0; l < N; ++l) v[l] = sa[(c * 2 + which) * SA::size + bi + l * C1::stride];
+      apply_store<N2, N>(cm.J12, v, sbuf + (c * 3 + (which == 0 ? 0 : 2)) * SB::size + bo, SB::PI);
+      if (which == 0) apply_store<N2, N>(cm.D12, v, sbuf + (c * 3 + 1) * SB::size + bo, SB::PI);
+    }
+    __syncthreads();
+    if (tid < 9 * C0::ncol) {
+      const int grp = tid / C0::ncol, col = tid - grp * C0::ncol;
+      const int dir = grp / 3, c = grp - dir * 3;
+      const double* b0 = sbuf + (c * 3 + dir) * SB::size + C0::base(col);
+      double v[N];
+#pragma unroll
+      for (int l = 0; l < N; ++l) v[l] = b0[l];
+      double* po = spart + grp * NP2 + col * N2;
+      if (dir == 0) apply_store<N2, N>(cm.D12, v, po, 1);
+      else apply_store<N2, N>(cm.J12, v, po, 1);
+    }
+    __syncthreads();
+    if (tid < NP2) {
+      const int q = tid;
+      double acc = 0.0;
+#pragma unroll
+      for (int g = 0; g < 9; ++g) acc = fma(inrw[g * NP2 + q], spart[g * NP2 + q], acc);
+      qout[(long long)e * NP2 + q] = acc;
+      rho[0] += inrw[9 * NP2 + q] * acc;
+    }
+    __syncthreads();
+  }
+  return rho[0];
+}
+
+template <int N>
+__global__ void __launch_bounds__(PK_TPB, 2)
+k_div3p(const double* __restrict__ u, const double* __restrict__ mbinv, double* __restrict__ qout, const double* __restrict__ RW2,
+        const double* __restrict__ pdir, CGState* __restrict__ cgs, double* __restrict__ part, unsigned* counter,
+        double* __restrict__ red_out, int finalize, long long n, long long n2, int nel) {
+  using P = DivP<N>;
+  constexpr int N2 = P::N2, TPB = PK_TPB, NP1 = P::NP1, NP2 = P::NP2, STG = P::stage;
+  using SA = typename P::SA;
+  using SB = typename P::SB;
+  using C2 = ColIn<2, N, N, N>;
+  using C1 = ColIn<1, N2, N, N>;
+  using C0 = ColIn<0, N2, N2, N>;
+  extern __shared__ __align__(128) double dsm[];
+  double* sin = dsm;                                   // [2][STG]
+  double* sa = dsm + 2 * STG;                          // [6][SA::size], reused for the 9 partial arrays
+  double* sbuf = sa + 6 * SA::size;                    // [9][SB::size]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sbuf + 9 * SB::size);
+  __shared__ double sred[32];
+  double* spart = sa;
+  static_assert(9 * NP2 <= 6 * SA::size, "spart alias");
+  const int tid = threadIdx.x;
+  if (cgs->done) return;
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  auto issue = [&](int e, int st) {
+    double* dst = sin + st * STG;
+    const long long e1 = (long long)e * NP1, e2 = (long long)e * NP2;
+    mbar_expect_tx(&bar[st], STG * (uint32_t)sizeof(double));
+#pragma unroll
+    for (int c = 0; c < 3; ++c) tma_bulk_g2s(dst + c * NP1, u + (long long)c * n + e1, NP1 * sizeof(double), &bar[st]);
+    tma_bulk_g2s(dst + 3 * NP1, mbinv + e1, NP1 * sizeof(double), &bar[st]);
+#pragma unroll
+    for (int g = 0; g < 9; ++g) tma_bulk_g2s(dst + 4 * NP1 + g * NP2, RW2 + (long long)g * n2 + e2, NP2 * sizeof(double), &bar[st]);
+    tma_bulk_g2s(dst + 4 * NP1 + 9 * NP2, pdir + e2, NP2 * sizeof(double), &bar[st]);
+  };
+  if (tid == 0 && (int)blockIdx.x < nel) issue(blockIdx.x, 0);
+  double rho[1] = {0.0};
+  int it = 0;
+  for (int e = blockIdx.x; e < nel; e += gridDim.x, ++it) {
+    const int st = it & 1;
+    if (tid == 0 && e + (int)gridDim.x < nel) issue(e + gridDim.x, st ^ 1);
+    mbar_wait(&bar[st], (it >> 1) & 1);
+    rho[0] += div3_element<N>(sin + st * STG, sa, sbuf, qout, e, tid);
+  }
+  if (grid_sum_finish<1>(rho, part, counter, red_out, sred) && finalize && tid == 0) {
+    cgs->rho = red_out[0];
+    cgs->alpha = cgs->rtz1 / red_out[0];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ axhelm
+// w_f = (h1 A + h2 B) u_f for up to 3 fields at once [UPSTREAM hmholtz.f axhelm = local_grad3 -> G -> local_grad3_t]:
+// every (field, direction) pair is one column task per thread in both tensor stages; the stiffness factors are read
+// once per point for all fields.  MODE 0: w = H u.  MODE 1: r = b + r - H u (cresvipp).  MODE 2: Helmholtz-CG
+// iteration head: p = dinv*r + beta*p (stored), w = H p, rho_f = sum p*w (per-component CG states).
+template <int N>
+struct AxCfg {
+  static constexpr int NP1 = N * N * N;
+  static constexpr int NT = 9 * N * N;
+  static constexpr int TPB = (((NT > NP1) ? NT : NP1) + 31) / 32 * 32;
+};
+
+template <int N, int MODE>
+__global__ void __launch_bounds__(AxCfg<N>::TPB, 2)
+k_axhelm3(const double* __restrict__ u, double* __restrict__ w, const double* __restrict__ b, const double* __restrict__ G,
+          const double* __restrict__ bm1, const double* __restrict__ dinv, double* __restrict__ pdir, CGState* __restrict__ cgs,
+          double* __restrict__ part, unsigned* counter, double* __restrict__ red_out, int finalize, int nfields, long long n,
+          double h1, double h2) {
+  constexpr int NP1 = N * N * N, NC = N * N;
+  using S1 = Shp<N, N, N>;
+  constexpr int PI = S1::PI;
+  extern __shared__ double dsm[];
+  double* su = dsm;                     // [3][S1::size]
+  double* sr = dsm + 3 * S1::size;      // [9][S1::size]  (field*3 + direction)
+  __shared__ double sred[3 * 32];
+  const int tid = threadIdx.x;
+  const long long e0 = (long long)blockIdx.x * NP1;
+  bool act[3];
+  double beta[3];
+#pragma unroll
+  for (int f = 0; f < 3; ++f) {
+    act[f] = f < nfields && !(MODE == 2 && cgs[f].done);
+    beta[f] = (MODE == 2 && f < nfields) ? cgs[f].beta : 0.0;
+  }
+  if (MODE == 2 && !(act[0] || act[1] || act[2])) return;
+  double uo[3] = {0.0, 0.0, 0.0};
+  if (tid < NP1) {
+    const int o = S1::lin(tid);
+    const double di = (MODE == 2) ? dinv[e0 + tid] : 0.0;
+#pragma unroll
+    for (int f = 0; f < 3; ++f)
+      if (act[f]) {
+        const long long gi = (long long)f * n + e0 + tid;
+        double v;
+        if (MODE == 2) {
+          v = di * u[gi] + beta[f] * pdir[gi];          // u = r
+          pdir[gi] = v;
+        } else {
+          v = u[gi];
+        }
+        uo[f] = v;
+        su[f * S1::size + o] = v;
+      }
+  }
+  __syncthreads();
+  // ---- derivatives: sr[f*3+dir] = D applied along dir to su[f]
+  const int tf = tid / (3 * NC), tdir = (tid / NC) % 3, tcol = tid % NC;
+  const bool task = tid < 9 * NC && tf < nfields && act[tf < 3 ? tf : 0];
+  const int cbase = (tdir == 0) ? tcol * PI : ((tdir == 1) ? (tcol / N) * N * PI + (tcol % N) : (tcol / N) * PI + (tcol % N));
+  const int cstr = (tdir == 0) ? 1 : ((tdir == 1) ? PI : N * PI);
+  if (task) {
+    const double* pin = su + tf * S1::size + cbase;
+    double v[N];
+#pragma unroll
+    for (int l = 0; l < N; ++l) v[l] = pin[l * cstr];
+    apply_store<N, N>(cm.D, v, sr + (tf * 3 + tdir) * S1::size + cbase, cstr);
+  }
+  __syncthreads();
+  // ---- geometric factors, all fields of a point at once
+  if (tid < NP1) {
+    const int o = S1::lin(tid);
+    double g[6];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) g[q] = G[(long long)q * n + e0 + tid];
+#pragma unroll
+    for (int f = 0; f < 3; ++f)
+      if (act[f]) {
+        double* p0 = sr + (f * 3) * S1::size + o;
+        const double d0 = p0[0], d1 = p0[S1::size], d2 = p0[2 * S1::size];
+        p0[0] = g[0] * d0 + g[3] * d1 + g[4] * d2;
+        p0[S1::size] = g[3] * d0 + g[1] * d1 + g[5] * d2;
+        p0[2 * S1::size] = g[4] * d0 + g[5] * d1 + g[2] * d2;
+      }
+  }
+  __syncthreads();
+  // ---- transposed derivatives, in place (each thread owns its column)
+  if (task) {
+    double* pc = sr + (tf * 3 + tdir) * S1::size + cbase;
+    double v[N];
+#pragma unroll
+    for (int l = 0; l < N; ++l) v[l] = pc[l * cstr];
+    apply_store<N, N>(cm.Dt, v, pc, cstr);
+  }
+  __syncthreads();
+  double rho[3] = {0.0, 0.0, 0.0};
+  if (tid < NP1) {
+    const int o = S1::lin(tid);
+    const double bm = bm1[e0 + tid];
+#pragma unroll
+    for (int f = 0; f < 3; ++f)
+      if (act[f]) {
+        const double* p0 = sr + (f * 3) * S1::size + o;
+        const double hv = h1 * ((p0[0] + p0[S1::size]) + p0[2 * S1::size]) + h2 * bm * uo[f];
+        const long long gi = (long long)f * n + e0 + tid;
+        if (MODE == 1) {
+          w[gi] = b[gi] + w[gi] - hv;
+        } else {
+          w[gi] = hv;
+          if (MODE == 2) rho[f] = uo[f] * hv;
+        }
+      }
+  }
+  if (MODE == 2) {
+    if (grid_sum_finish<3>(rho, part, counter, red_out, sred) && finalize && tid == 0) {
+      for (int f = 0; f < nfields; ++f)
+        if (!cgs[f].done) {
+          cgs[f].rho = red_out[f];
+          cgs[f].alpha = cgs[f].rtz1 / red_out[f];
+        }
     }
   }
 }
@@ -331,15 +756,44 @@ int pk_gradt(Ctx* c, const double* p, double* w) {
   NSB_CUDA(cudaGetLastError());
   return 0;
 }
+template <class K>
+static int set_smem(K kernel, size_t bytes);
+static int persistent_grid(Ctx* c) {
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+  return std::min(c->nel, 2 * sms);
+}
 int pk_pcg_dir_gradt(Ctx* c, int adj) {
+  if (c->persistent_pcg) {
+    DISPATCH_N(c, NSB_TRY(set_smem(k_gradt3p<N>, GradtP<N>::smem));
+               k_gradt3p<N><<<persistent_grid(c), PK_TPB, GradtP<N>::smem, c->stream>>>(c->pk[0], c->wk[2], c->RW2, c->dinvE[adj],
+                                                                                       c->pk[2], c->cgs + 3, c->n, c->n2, c->nel));
+    nsb_count_launch();
+    NSB_CUDA(cudaGetLastError());
+    return 0;
+  }
   DISPATCH_N(c, k_gradt3<N, 1><<<c->nel, PK_TPB, 0, c->stream>>>(c->pk[0], c->wk[2], c->RW2, c->dinvE[adj], c->pk[2], c->cgs + 3,
                                                               c->n, c->n2));
   nsb_count_launch();
   NSB_CUDA(cudaGetLastError());
   return 0;
 }
+template <int N>
+static constexpr size_t div3_smem() {
+  using S1 = Shp<N, N, N>;
+  using SA = Shp<N - 2, N, N>;
+  using SB = Shp<N - 2, N - 2, N>;
+  constexpr int SU = 3 * S1::size, SBB = 9 * SB::size;
+  return sizeof(double) * ((SU > SBB ? SU : SBB) + 6 * SA::size + 10 * (N - 2) * (N - 2) * (N - 2));
+}
+template <class K>
+static int set_smem(K kernel, size_t bytes) {
+  NSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return 0;
+}
+
 int pk_div(Ctx* c, const double* u, const double* s0, const double* s1, const double* s2, double* q, double sign) {
-  DISPATCH_N(c, k_div3<N, 0, 0><<<c->nel, PK_TPB, 0, c->stream>>>(u, s0, s1, s2, q, c->RW2, nullptr, nullptr, nullptr, nullptr,
+  DISPATCH_N(c, NSB_TRY(set_smem(k_div3<N, 0, 0>, div3_smem<N>())); k_div3<N, 0, 0><<<c->nel, PK_TPB, div3_smem<N>(), c->stream>>>(u, s0, s1, s2, q, c->RW2, nullptr, nullptr, nullptr, nullptr,
                                                                nullptr, 0, c->n, c->n2, sign, nullptr, 0, nullptr, nullptr));
   nsb_count_launch();
   NSB_CUDA(cudaGetLastError());
@@ -350,14 +804,43 @@ int pk_pcg_div(Ctx* c, int adj, int fused) {
   const double* s1 = c->mask_same[adj] ? nullptr : c->mbinv[adj][1];
   const double* s2 = c->mask_same[adj] ? nullptr : c->mbinv[adj][2];
   const GSMap& m = c->gs;
+  if (c->persistent_pcg && !fused && c->mask_same[adj]) {
+    DISPATCH_N(c, NSB_TRY(set_smem(k_div3p<N>, DivP<N>::smem));
+               k_div3p<N><<<persistent_grid(c), PK_TPB, DivP<N>::smem, c->stream>>>(c->wk[2], s0, c->pk[3], c->RW2, c->pk[2], c->cgs + 3,
+                                                                                    c->red_part, c->red_count, c->red_out,
+                                                                                    c->nranks == 1, c->n, c->n2, c->nel));
+    nsb_count_launch();
+    NSB_CUDA(cudaGetLastError());
+    return 0;
+  }
   if (fused) {
-    DISPATCH_N(c, k_div3<N, 1, 1><<<c->nel, PK_TPB, 0, c->stream>>>(c->wk[2], s0, s1, s2, c->pk[3], c->RW2, c->pk[2], c->cgs + 3,
+    DISPATCH_N(c, NSB_TRY(set_smem(k_div3<N, 1, 1>, div3_smem<N>())); k_div3<N, 1, 1><<<c->nel, PK_TPB, div3_smem<N>(), c->stream>>>(c->wk[2], s0, s1, s2, c->pk[3], c->RW2, c->pk[2], c->cgs + 3,
                                                                  c->red_part, c->red_count, c->red_out, c->nranks == 1, c->n,
                                                                  c->n2, 1.0, m.surf_pts, m.ns, m.nb_off, m.nb_idx));
   } else {
-    DISPATCH_N(c, k_div3<N, 1, 0><<<c->nel, PK_TPB, 0, c->stream>>>(c->wk[2], s0, s1, s2, c->pk[3], c->RW2, c->pk[2], c->cgs + 3,
+    DISPATCH_N(c, NSB_TRY(set_smem(k_div3<N, 1, 0>, div3_smem<N>())); k_div3<N, 1, 0><<<c->nel, PK_TPB, div3_smem<N>(), c->stream>>>(c->wk[2], s0, s1, s2, c->pk[3], c->RW2, c->pk[2], c->cgs + 3,
                                                                  c->red_part, c->red_count, c->red_out, c->nranks == 1, c->n,
                                                                  c->n2, 1.0, nullptr, 0, nullptr, nullptr));
+  }
+  nsb_count_launch();
+  NSB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int N>
+static constexpr size_t ax3_smem() { return sizeof(double) * 12 * Shp<N, N, N>::size; }
+
+int pk_axhelm(Ctx* c, int mode, const double* u, double* w, const double* b, int nfields, double h1, double h2) {
+  if (mode == 0) {
+    DISPATCH_N(c, NSB_TRY(set_smem(k_axhelm3<N, 0>, ax3_smem<N>())); k_axhelm3<N, 0><<<c->nel, AxCfg<N>::TPB, ax3_smem<N>(), c->stream>>>(
+                      u, w, nullptr, c->G, c->bm1, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nfields, c->n, h1, h2));
+  } else if (mode == 1) {
+    DISPATCH_N(c, NSB_TRY(set_smem(k_axhelm3<N, 1>, ax3_smem<N>())); k_axhelm3<N, 1><<<c->nel, AxCfg<N>::TPB, ax3_smem<N>(), c->stream>>>(
+                      u, w, b, c->G, c->bm1, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nfields, c->n, h1, h2));
+  } else {
+    DISPATCH_N(c, NSB_TRY(set_smem(k_axhelm3<N, 2>, ax3_smem<N>())); k_axhelm3<N, 2><<<c->nel, AxCfg<N>::TPB, ax3_smem<N>(), c->stream>>>(
+                      c->rk, c->wk[2], nullptr, c->G, c->bm1, c->dinvH, c->wk[1], c->cgs, c->red_part, c->red_count, c->red_out,
+                      c->nranks == 1, nfields, c->n, h1, h2));
   }
   nsb_count_launch();
   NSB_CUDA(cudaGetLastError());

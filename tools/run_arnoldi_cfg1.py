@@ -1,0 +1,76 @@
+#!/usr/bin/env python
+"""Config 1 end to end on the GPU: 2-D cylinder Re=50, direct Arnoldi / Krylov-Schur for the leading eigenpairs
+(examples/cylinder/stability/direct as shipped: k_dim=200, schur_tgt=0, endTime 1, tol 1e-7/1e-9, sponge 5/5/1.7), i.e.
+`krylov_schur` of core/eigensolvers.f:141-388 with every matvec on the device.  Writes Spectre_Hd.dat / Spectre_NSd.dat /
+Spectre_NSd_conv.dat in the reference's format (core/eigensolvers.f:590-604) under gpurun_out/ and compares with the
+shipped spectra (tests/golden/cyl.npz).  Usage: python tools/run_arnoldi_cfg1.py [k_dim] [tol_p] [tol_v]"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from nekstab_b200 import cases, lib  # noqa: E402
+
+
+def main():
+    k_dim = int(sys.argv[1]) if len(sys.argv) > 1 else 200
+    tol_p = float(sys.argv[2]) if len(sys.argv) > 2 else 1e-7
+    tol_v = float(sys.argv[3]) if len(sys.argv) > 3 else 1e-9
+    g = np.load(os.path.join(ROOT, "tests", "golden", "cyl.npz"))
+    c = cases.cylinder_case(g)
+    t0 = time.time()
+    ctx = lib.NekStabB200(c)
+    ctx.set_params(1.0 / c.re, 1.0, tol_v, tol_p, 2000, 100000)
+    dt, nsteps, ctarg = ctx.prepare_linearized_solver(c.end_time)
+    ctx.vec_alloc(k_dim + 3)
+    # seed: noise -> normalise -> one matvec ("smoothing") -> normalise   (core/eigensolvers.f:222-278)
+    ctx.vec_upload(k_dim + 1, cases.add_noise(c), None)
+    ctx.normalize(k_dim + 1)
+    ctx.matvec(lib.DIRECT, k_dim + 1, 0)
+    ctx.normalize(0)
+    t1 = time.time()
+    vals, res, V, ncv, scnt = ctx.krylov_schur(lib.DIRECT, k_dim, 0, eigen_tol=1e-6, schur_del=0.1, seed_slot=0)
+    wall = time.time() - t1
+    st = ctx.stats()
+    tau = dt * nsteps
+    lam = np.log(vals.astype(complex)) / tau
+    out = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "Spectre_Hd.dat"), "w") as f1, open(os.path.join(out, "Spectre_NSd.dat"), "w") as f2, \
+            open(os.path.join(out, "Spectre_NSd_conv.dat"), "w") as f3:
+        for i in range(k_dim):
+            f1.write("%15.7E%15.7E%15.7E\n" % (vals[i].real, vals[i].imag, res[i]))
+            f2.write("%15.7E%15.7E%15.7E\n" % (lam[i].real, lam[i].imag, res[i]))
+            if res[i] < 1e-6:
+                f3.write("%15.7E%15.7E\n" % (lam[i].real, lam[i].imag))
+    ref_h = g["Spectre_Hd"]
+    ref_mu = ref_h[:, 0] + 1j * ref_h[:, 1]
+    nconv_ref = int((ref_h[:, 2] < 1e-6).sum())
+    # match converged reference Ritz values to ours (nearest neighbour)
+    errs = []
+    for m in ref_mu[:min(nconv_ref, 12)]:
+        j = int(np.argmin(np.abs(vals - m)))
+        errs.append(float(abs(vals[j] - m) / abs(m)))
+    ref_lam = g["Spectre_NSd_conv"][0, 0] + 1j * g["Spectre_NSd_conv"][0, 1]
+    jl = int(np.argmin(np.abs(lam - ref_lam)))
+    summary = {"case": "cylinder Re=50 direct (cfg 1)", "k_dim": k_dim, "nsteps": nsteps, "dt": dt, "tol_p": tol_p, "tol_v": tol_v,
+               "matvecs": k_dim + 1, "time_steps": st["steps"], "wall_s_arnoldi": wall, "setup_s": t1 - t0,
+               "pres_iters_per_step": st["pres_iters"] / max(st["steps"], 1), "helm_iters_per_step": st["helm_iters"] / max(st["steps"], 1),
+               "converged_ritz_pairs(res<1e-6)": int(ncv), "reference_converged": nconv_ref,
+               "leading_mu": [vals[0].real, vals[0].imag], "reference_leading_mu": [ref_mu[0].real, ref_mu[0].imag],
+               "leading_lambda": [lam[jl].real, lam[jl].imag], "reference_leading_lambda": [ref_lam.real, ref_lam.imag],
+               "rel_err_leading_lambda": float(abs(lam[jl] - ref_lam) / abs(ref_lam)),
+               "rel_err_first_converged_ritz_values": errs, "leading_residual": float(res[0]),
+               "dof_steps_per_s": c.n * st["steps"] / (st["step_ms"] * 1e-3)}
+    with open(os.path.join(out, "arnoldi_cfg1_summary.json"), "w") as f:
+        json.dump(summary, f, indent=1)
+    print(json.dumps(summary, indent=1))
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

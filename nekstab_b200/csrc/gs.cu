@@ -81,6 +81,9 @@ __global__ void k_gs_sum(int nseg, const int* __restrict__ seg_off, const int* _
   }
 }
 
+// Note (r1c, measured): splitting the two-copy (face) segments into a separate offset-free pair list, to shorten the
+// dependent load chain, made the 3-field dssum SLOWER (0.173 vs 0.117 ms on cfg 5): face, edge and vertex nodes share
+// 32-byte sectors, and processing them in one dof-ordered sweep is what keeps every sector to one read and one write.
 template <class T>
 static int upload(T** dptr, const std::vector<T>& h) {
   size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);

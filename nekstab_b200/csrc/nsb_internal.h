@@ -122,6 +122,7 @@ struct Ctx {
   double dt = 0;
   int nsteps = 0;
   int check_every_v = 4, check_every_p = 32;
+  bool persistent_gradt = false;
   bool persistent_pcg = true; // 3-D: persistent, TMA-pipelined k_gradt3p / k_div3p in the pressure-CG loop (NSB_PERSISTENT=0 disables)
   bool fused_gs = false;      // 3-D, single rank: k_div3 gathers the surface sums itself (no dssum in the pressure loop)
 

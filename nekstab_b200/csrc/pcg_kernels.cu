@@ -764,7 +764,9 @@ static int persistent_grid(Ctx* c) {
   return std::min(c->nel, 2 * sms);
 }
 int pk_pcg_dir_gradt(Ctx* c, int adj) {
-  if (c->persistent_pcg) {
+  // measured (r1c, cfg 5): persistent gradt 0.198 ms (2 CTAs/SM) vs 0.157 ms one-CTA-per-element (4 CTAs/SM) => opt-in only;
+  // the persistent div (0.191 vs 0.238 ms) is the default
+  if (c->persistent_pcg && c->persistent_gradt) {
     DISPATCH_N(c, NSB_TRY(set_smem(k_gradt3p<N>, GradtP<N>::smem));
                k_gradt3p<N><<<persistent_grid(c), PK_TPB, GradtP<N>::smem, c->stream>>>(c->pk[0], c->wk[2], c->RW2, c->dinvE[adj],
                                                                                        c->pk[2], c->cgs + 3, c->n, c->n2, c->nel));

@@ -62,7 +62,12 @@ extern "C" int nsb_comm_init(int rank, int nranks, const char id_in[128], int de
 }
 
 // ------------------------------------------------------------------------------------------ setup
+static void drop_graphs(Ctx* c) {
+  for (auto& g : c->graph_p) { if (g.exec) cudaGraphExecDestroy(g.exec); g = Ctx::GraphEntry(); }
+  for (auto& g : c->graph_h) { if (g.exec) cudaGraphExecDestroy(g.exec); g = Ctx::GraphEntry(); }
+}
 static int setup_masks(Ctx* c, int set, const double* m0, const double* m1, const double* m2) {
+  drop_graphs(c);
   const double* hm[3] = {m0, m1, m2};
   c->mask_same[set] = true;
   for (int d = 1; d < c->ldim; ++d)
@@ -100,6 +105,7 @@ extern "C" int nsb_finalize(void) {
   Ctx* c = g_ctx;
   if (!c) return 0;
   cudaStreamSynchronize(c->stream);
+  drop_graphs(c);
   gs_free(c);
   double* ptrs[] = {c->xyz[0], c->xyz[1], c->xyz[2], c->R, c->jac, c->bm1, c->binv, c->mult, c->bm1s, c->G, c->RW2, c->bm2inv,
                     c->Rd, c->hdiagA, c->hdiagB, c->dinvH, c->ub, c->spng, c->u, c->ulag[0], c->ulag[1], c->f[0], c->f[1],
@@ -216,6 +222,8 @@ extern "C" int nsb_init(int ldim, int lx1, int lxd, int lx2, int nelv, long long
   c->has_adj_masks = false;
   // measured (r1b): the separate, segment-sorted dssum (0.115 ms) + k_div3 (0.318 ms) beats the fused gather (0.465 ms) on
   // cfg 5, so the fused variant is opt-in
+  const char* ng = getenv("NSB_GRAPHS");
+  c->use_graphs = !(ng && ng[0] == '0');
   const char* np_ = getenv("NSB_PERSISTENT");
   c->persistent_pcg = !(np_ && np_[0] == '0');
   c->persistent_gradt = (np_ && np_[0] == '2');
@@ -227,6 +235,7 @@ extern "C" int nsb_init(int ldim, int lx1, int lxd, int lx2, int nelv, long long
 
 extern "C" int nsb_set_adjoint_masks(const double* m0, const double* m1, const double* m2) {
   REQUIRE_CTX();
+  drop_graphs(c);
   if (c->has_adj_masks) {
     for (int d = 0; d < c->ldim; ++d) { cudaFree(c->mask[1][d]); cudaFree(c->mbinv[1][d]); }
     cudaFree(c->dinvE[1]);

@@ -163,6 +163,14 @@ struct Ctx {
   double* projX = nullptr;    // [proj_max][n2]
   double* projEX = nullptr;   // [proj_max][n2]
 
+  // CUDA graphs of the CG iteration batches (single rank): one captured batch = `check_every` iterations; the launch-bound
+  // 2-D / small cases replay it instead of issuing ~130 kernel launches per batch from the host
+  struct GraphEntry { cudaGraphExec_t exec = nullptr; int launches = 0; int adj = -1; double h1 = 0, h2 = 0; };
+  bool use_graphs = true;
+  GraphEntry graph_p[2];
+  GraphEntry graph_h[8];
+  bool graph_warm = false;
+
   // per-kernel sampling profiler (CUDA events on the launching stream; one sample set per host poll)
   int prof_on = 0;
   cudaEvent_t prof_ev[16] = {nullptr};

@@ -81,6 +81,31 @@ static void prof_collect(Ctx* c, const int* kinds, int nk, int first_slot) {
   }
 }
 
+// ---- CUDA-graph replay of one CG batch (single rank, profiler off).  The first batches of a context run un-captured so
+//      that one-time function attributes are set outside any capture.
+static bool graphs_ok(Ctx* c) { return c->use_graphs && c->nranks == 1 && !c->prof_on && c->graph_warm; }
+template <class F>
+static int run_batch_graph(Ctx* c, Ctx::GraphEntry* ge, F&& batch) {
+  if (!ge->exec) {
+    const long long l0 = c->stats.kernel_launches;
+    cudaGraph_t g = nullptr;
+    NSB_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = batch(false);
+    cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+    if (rc || e != cudaSuccess || !g) {
+      nsb_set_error("CUDA graph capture of a CG batch failed (%s)", cudaGetErrorString(e));
+      return rc ? rc : 1;
+    }
+    NSB_CUDA(cudaGraphInstantiate(&ge->exec, g, 0));
+    cudaGraphDestroy(g);
+    ge->launches = (int)(c->stats.kernel_launches - l0);
+    c->stats.kernel_launches = l0;                 // captured, not executed
+  }
+  NSB_CUDA(cudaGraphLaunch(ge->exec, c->stream));
+  c->stats.kernel_launches += ge->launches;
+  return 0;
+}
+
 // Solve (h1 A + h2 B) x_c = r_c for the ldim velocity components at once (independent CG recurrences sharing
 // every kernel launch) [UPSTREAM hmholtz.f hmholtz/cggo].  In: c->rk (assembled, masked). Out: c->wk[3].
 int st_helmholtz(Ctx* c, int adj, double h1, double h2, int* iters) {
@@ -90,8 +115,15 @@ int st_helmholtz(Ctx* c, int adj, double h1, double h2, int* iters) {
   NSB_TRY(vk_hcg_init(c, nc));
   bool done = false;
   int issued = 0;
-  while (!done) {
-    const bool sample = c->prof_on && issued == 0;
+  Ctx::GraphEntry* ge = nullptr;
+  if (graphs_ok(c)) {
+    for (auto& g : c->graph_h)
+      if (g.exec && g.adj == adj && g.h1 == h1 && g.h2 == h2) ge = &g;
+    if (!ge)
+      for (auto& g : c->graph_h)
+        if (!g.exec) { ge = &g; ge->adj = adj; ge->h1 = h1; ge->h2 = h2; break; }
+  }
+  auto batch = [&](bool sample) -> int {
     for (int it = 0; it < c->check_every_v; ++it) {
       const bool sm = sample && it == 0;
       prof_mark(c, sm, 0);
@@ -102,8 +134,14 @@ int st_helmholtz(Ctx* c, int adj, double h1, double h2, int* iters) {
       prof_mark(c, sm, 2);
       NSB_TRY(vk_hcg_update(c, nc, adj));
       prof_mark(c, sm, 3);
-      ++issued;
     }
+    return 0;
+  };
+  while (!done) {
+    const bool sample = c->prof_on && issued == 0;
+    if (ge) NSB_TRY(run_batch_graph(c, ge, batch));
+    else NSB_TRY(batch(sample));
+    issued += c->check_every_v;
     NSB_TRY(cg_state_poll(c, 0, nc, &done));
     if (sample) { const int kinds[3] = {4, 7, 5}; prof_collect(c, kinds, 3, 0); }
     if (issued > c->maxit_v + c->check_every_v) break;
@@ -193,8 +231,8 @@ int st_pressure(Ctx* c, int adj, int* iters) {
   NSB_TRY(vk_pcg_init(c, adj));
   bool done = false;
   int issued = 0;
-  while (!done) {
-    const bool sample = c->prof_on != 0;
+  Ctx::GraphEntry* ge = graphs_ok(c) ? &c->graph_p[adj] : nullptr;
+  auto batch = [&](bool sample) -> int {
     for (int it = 0; it < c->check_every_p; ++it) {
       const bool sm = sample && it == 0;       // first iteration of the batch: cannot be a skipped (converged) one
       prof_mark(c, sm, 4);
@@ -207,8 +245,14 @@ int st_pressure(Ctx* c, int adj, int* iters) {
       prof_mark(c, sm, 7);
       NSB_TRY(vk_pcg_update(c, adj));
       prof_mark(c, sm, 8);
-      ++issued;
     }
+    return 0;
+  };
+  while (!done) {
+    const bool sample = c->prof_on != 0;
+    if (ge) NSB_TRY(run_batch_graph(c, ge, batch));
+    else NSB_TRY(batch(sample));
+    issued += c->check_every_p;
     NSB_TRY(cg_state_poll(c, 3, 1, &done));
     if (sample) { const int kinds[4] = {0, 1, 2, 3}; prof_collect(c, kinds, 4, 4); }
     if (issued > c->maxit_p + c->check_every_p) break;
@@ -258,6 +302,7 @@ static int one_step(Ctx* c, int istep, int adj) {
   double* t = c->ulag[1]; c->ulag[1] = c->ulag[0]; c->ulag[0] = c->u; c->u = t;
   double* tp = c->prlag; c->prlag = c->pr; c->pr = tp;
   c->stats.steps += 1;
+  c->graph_warm = true;
   return 0;
 }
 

@@ -91,7 +91,7 @@ class ClockSampler(threading.Thread):
 
 def ncu_traffic(kernel_kind):
     """dram__bytes_read+write per launch of the dominant kernel from the committed `ncu --set full` capture."""
-    names = {"pcg_div": "k_div3<8, 1, 0>", "pcg_gradt": "k_gradt3<8, 1>", "dssum": "k_gs_sum<3, 0>"}
+    names = {"pcg_div": "k_div3p<8>", "pcg_gradt": "k_gradt3<8, 1>", "dssum": "k_gs_sum<3, 0>", "pcg_update": "k_pcg_update"}
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_dram_traffic.json")) as f:
             d = json.load(f)

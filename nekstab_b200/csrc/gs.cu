@@ -94,6 +94,7 @@ static int upload(T** dptr, const std::vector<T>& h) {
 
 int gs_free(Ctx* c) {
   GSMap& m = c->gs;
+  p2p_free(c);
   cudaFree(m.seg_off); cudaFree(m.seg_idx); cudaFree(m.send_seg); cudaFree(m.rseg_off); cudaFree(m.rseg_pos);
   cudaFree(m.rseg_nbefore); cudaFree(m.sendbuf); cudaFree(m.recvbuf);
   cudaFree(d_send_base); cudaFree(d_send_cnt); cudaFree(d_rseg_cnt);
@@ -319,6 +320,12 @@ int gs_setup(Ctx* c, const long long* glo) {
   NSB_CUDA(cudaMalloc(&m.recvbuf, hb));
   NSB_CUDA(cudaMemset(m.sendbuf, 0, hb));
   NSB_CUDA(cudaMemset(m.recvbuf, 0, hb));
+  if (c->nranks > 1) {
+    std::vector<int> send_nbr, send_j;
+    for (int i = 0; i < m.nnbr; ++i)
+      for (int j = 0; j < m.nbr_off[i + 1] - m.nbr_off[i]; ++j) { send_nbr.push_back(i); send_j.push_back(j); }
+    NSB_TRY(p2p_setup(c, send_nbr, send_j));
+  }
   return 0;
 }
 
@@ -326,6 +333,7 @@ template <int NF>
 static int dssum_nf(Ctx* c, double* u, long long stride, const CGState* skip) {
   GSMap& m = c->gs;
   const int T = 128;
+  if (c->p2p.on) return p2p_dssum(c, u, NF, stride, skip, m.send_seg, d_rseg_cnt);
   if (m.nshared > 0) {
     k_gs_pack<NF><<<(m.nshared + T - 1) / T, T, 0, c->stream>>>(m.nshared, m.send_seg, d_send_base, d_send_cnt, m.seg_off,
                                                                m.seg_idx, u, stride, m.sendbuf, skip);

@@ -79,6 +79,23 @@ struct GSMap {
   int* nb_idx = nullptr;
 };
 
+// NVLink peer-memory collectives (p2p.cu)
+struct P2P {
+  bool on = false;
+  double* arena = nullptr;
+  long long words = 0, halo_stride = 0;
+  double* peer[16] = {nullptr};
+  double** d_peer_dst = nullptr;                 // [2 parities][nnbr]
+  unsigned long long** d_peer_flag = nullptr;    // [2 parities][nnbr]
+  double** d_peer_base = nullptr;                // [16]
+  int* d_cnt = nullptr;
+  int* d_nbr_rank = nullptr;
+  int* d_send_nbr = nullptr;
+  int* d_send_j = nullptr;
+  int* d_err = nullptr;
+  unsigned long long epoch_halo = 0, epoch_red = 0;
+};
+
 struct Ctx {
   int ldim = 0, lx1 = 0, lxd = 0, lx2 = 0, nel = 0;
   long long nelg = 0;
@@ -115,6 +132,7 @@ struct Ctx {
   long long n2_glob = 0;
   bool ifvcor[2] = {false, false};
   GSMap gs;
+  P2P p2p;
 
   // parameters
   double visc = 1.0, rho = 1.0, tol_v = 1e-9, tol_p = 1e-7;
@@ -196,6 +214,13 @@ void sem_build_constmats(int lx1, int lx2, int lxd, ConstMats* cm);
 int gs_setup(Ctx* c, const long long* glo_num);
 int gs_free(Ctx* c);
 int gs_dssum(Ctx* c, double* u, int nfields, long long stride, const CGState* skip_if_done = nullptr);
+
+// ---- NVLink peer-memory collectives (p2p.cu)
+int p2p_setup(Ctx* c, const std::vector<int>& send_nbr, const std::vector<int>& send_j);
+int p2p_free(Ctx* c);
+int p2p_dssum(Ctx* c, double* u, int nfields, long long stride, const CGState* skip, const int* d_send_seg, const int* d_rseg_cnt);
+int p2p_allreduce(Ctx* c, double* dev, int count, int op, CGState* cgs, int ncomp, int kind);
+int p2p_check_error(Ctx* c);
 
 // ---- element kernels (elem_kernels.cu)
 int ek_upload_constants(const ConstMats& cm);

@@ -1,0 +1,351 @@
+// p2p.cu -- NVLink peer-memory collectives of the multi-GPU hot path (no NCCL call inside the time step).
+//
+// Each rank owns one "arena" in device memory, mapped into every other rank's address space with CUDA IPC at setup
+// (handles are exchanged once over the NCCL communicator).  Two collectives of the hot path run on it:
+//   * dssum halo: the pack kernel adds the local copies of every interface node and STORES the partial sums straight
+//     into the neighbour's arena over NVLink, then the last CTA raises an epoch flag there; the neighbour's segmented-sum
+//     kernel waits on the flag and folds the partials in (ascending rank order => bit-identical sums on all ranks).
+//   * all-reduce of CG / inner-product scalars: every rank stores its deterministic local sums into slot [my rank] of
+//     every arena, raises a flag, waits for all flags and adds the slots in rank order; for the CG loops the scalar
+//     update (alpha, beta, convergence flag) happens in the same one-CTA kernel.
+// Replaces grouped ncclSend/ncclRecv + ncclAllReduce (two host-enqueued collectives and two extra kernels per pressure
+// iteration) by remote stores issued from the producing kernels.  Flow control: two parity copies of every buffer; a rank
+// can never be more than one exchange ahead of a rank it exchanges with, because each exchange needs the partner's
+// data of the same epoch.  Every spin-wait has a time-out that raises an error flag instead of hanging the GPU.
+#include <algorithm>
+
+#include "nsb_internal.h"
+
+static constexpr int RSLOT = 512;                 // doubles per rank slot of the all-reduce buffer
+static constexpr long long SPIN_TIMEOUT_NS = 4000000000LL;
+
+__device__ __forceinline__ unsigned long long ld_flag(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_flag(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ long long gtime() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ bool p2p_wait(const unsigned long long* flag, unsigned long long epoch, int* err) {
+  const long long t0 = gtime();
+  while (ld_flag(flag) < epoch) {
+    if (gtime() - t0 > SPIN_TIMEOUT_NS) { *err = 1; return false; }
+  }
+  return true;
+}
+
+// arena layout (units: 8 bytes)
+static inline long long off_red(int parity, int rank, int nranks) { return ((long long)parity * nranks + rank) * RSLOT; }
+static inline long long off_redflag(int parity, int rank, int nranks) { return 2LL * nranks * RSLOT + (long long)parity * nranks + rank; }
+static inline long long off_haloflag(int parity, int rank, int nranks) { return 2LL * nranks * RSLOT + 2LL * nranks + (long long)parity * nranks + rank; }
+static inline long long off_halo(int nranks) { return 2LL * nranks * RSLOT + 4LL * nranks; }
+
+int p2p_free(Ctx* c) {
+  P2P& p = c->p2p;
+  if (!p.on) return 0;
+  for (int r = 0; r < c->nranks; ++r)
+    if (r != c->rank && p.peer[r]) cudaIpcCloseMemHandle(p.peer[r]);
+  cudaFree(p.arena); cudaFree(p.d_peer_dst); cudaFree(p.d_peer_flag); cudaFree(p.d_nbr_rank); cudaFree(p.d_err);
+  cudaFree(p.d_send_nbr); cudaFree(p.d_send_j); cudaFree(p.d_cnt);
+  p = P2P();
+  return 0;
+}
+
+// called at the end of gs_setup (multi-rank); send_nbr/send_j: neighbour index and position of every send entry
+int p2p_setup(Ctx* c, const std::vector<int>& send_nbr, const std::vector<int>& send_j) {
+  P2P& p = c->p2p;
+  const char* env = getenv("NSB_P2P");
+  if (c->nranks <= 1 || c->nranks > 16 || (env && env[0] == '0')) return 0;
+  const GSMap& m = c->gs;
+  const int R = c->nranks;
+  // every peer must be reachable
+  for (int r = 0; r < R; ++r) {
+    if (r == c->rank) continue;
+    int can = 0;
+    // device ordinals = local ranks on one node (one process per GPU)
+    if (cudaDeviceCanAccessPeer(&can, c->device, r) != cudaSuccess || !can) return 0;   // fall back to NCCL
+  }
+  // allgather nshared and the table "where does rank q receive data from rank r" (in doubles, -1: not a neighbour)
+  std::vector<long long> mine(R + 1, -1), all((size_t)R * (R + 1));
+  for (int i = 0; i < m.nnbr; ++i) mine[m.nbr_rank[i]] = 3LL * m.nbr_off[i];
+  mine[R] = m.nshared;
+  long long *d_my = nullptr, *d_all = nullptr;
+  NSB_CUDA(cudaMalloc(&d_my, sizeof(long long) * (R + 1)));
+  NSB_CUDA(cudaMalloc(&d_all, sizeof(long long) * (R + 1) * R));
+  NSB_CUDA(cudaMemcpy(d_my, mine.data(), sizeof(long long) * (R + 1), cudaMemcpyHostToDevice));
+  NSB_NCCL(ncclAllGather(d_my, d_all, R + 1, ncclInt64, c->comm, c->stream));
+  NSB_CUDA(cudaStreamSynchronize(c->stream));
+  NSB_CUDA(cudaMemcpy(all.data(), d_all, sizeof(long long) * all.size(), cudaMemcpyDeviceToHost));
+  cudaFree(d_my); cudaFree(d_all);
+  // arena
+  p.halo_stride = 3LL * std::max(m.nshared, 1);
+  p.words = off_halo(R) + 2 * p.halo_stride;
+  NSB_CUDA(cudaMalloc(&p.arena, p.words * sizeof(double)));
+  NSB_CUDA(cudaMemset(p.arena, 0, p.words * sizeof(double)));
+  cudaIpcMemHandle_t h;
+  NSB_CUDA(cudaIpcGetMemHandle(&h, p.arena));
+  char *d_h = nullptr, *d_hall = nullptr;
+  NSB_CUDA(cudaMalloc(&d_h, sizeof(h)));
+  NSB_CUDA(cudaMalloc(&d_hall, sizeof(h) * R));
+  NSB_CUDA(cudaMemcpy(d_h, &h, sizeof(h), cudaMemcpyHostToDevice));
+  NSB_NCCL(ncclAllGather(d_h, d_hall, sizeof(h), ncclChar, c->comm, c->stream));
+  NSB_CUDA(cudaStreamSynchronize(c->stream));
+  std::vector<cudaIpcMemHandle_t> hs(R);
+  NSB_CUDA(cudaMemcpy(hs.data(), d_hall, sizeof(h) * R, cudaMemcpyDeviceToHost));
+  cudaFree(d_h); cudaFree(d_hall);
+  for (int r = 0; r < R; ++r) {
+    if (r == c->rank) { p.peer[r] = p.arena; continue; }
+    void* ptr = nullptr;
+    NSB_CUDA(cudaIpcOpenMemHandle(&ptr, hs[r], cudaIpcMemLazyEnablePeerAccess));
+    p.peer[r] = (double*)ptr;
+  }
+  // per neighbour: destination (parity 0) inside the neighbour's arena, its halo stride, its flag slot for me
+  std::vector<double*> dst(2 * std::max(m.nnbr, 1));
+  std::vector<unsigned long long*> flg(2 * std::max(m.nnbr, 1));
+  std::vector<int> cnt(std::max(m.nnbr, 1));
+  for (int i = 0; i < m.nnbr; ++i) {
+    const int q = m.nbr_rank[i];
+    const long long where = all[(size_t)q * (R + 1) + c->rank];        // offset inside q's halo block for data from me
+    const long long qstride = 3LL * std::max<long long>(all[(size_t)q * (R + 1) + R], 1);
+    if (where < 0) { nsb_set_error("p2p_setup: asymmetric neighbour table (rank %d <-> %d)", c->rank, q); return 1; }
+    for (int par = 0; par < 2; ++par) {
+      dst[par * m.nnbr + i] = p.peer[q] + off_halo(R) + par * qstride + where;
+      flg[par * m.nnbr + i] = (unsigned long long*)(p.peer[q] + off_haloflag(par, c->rank, R));
+    }
+    cnt[i] = m.nbr_off[i + 1] - m.nbr_off[i];
+  }
+  NSB_CUDA(cudaMalloc(&p.d_peer_dst, dst.size() * sizeof(double*)));
+  NSB_CUDA(cudaMemcpy(p.d_peer_dst, dst.data(), dst.size() * sizeof(double*), cudaMemcpyHostToDevice));
+  NSB_CUDA(cudaMalloc(&p.d_peer_flag, flg.size() * sizeof(void*)));
+  NSB_CUDA(cudaMemcpy(p.d_peer_flag, flg.data(), flg.size() * sizeof(void*), cudaMemcpyHostToDevice));
+  NSB_CUDA(cudaMalloc(&p.d_cnt, cnt.size() * sizeof(int)));
+  NSB_CUDA(cudaMemcpy(p.d_cnt, cnt.data(), cnt.size() * sizeof(int), cudaMemcpyHostToDevice));
+  std::vector<int> nr(std::max(m.nnbr, 1), 0);
+  for (int i = 0; i < m.nnbr; ++i) nr[i] = m.nbr_rank[i];
+  NSB_CUDA(cudaMalloc(&p.d_nbr_rank, nr.size() * sizeof(int)));
+  NSB_CUDA(cudaMemcpy(p.d_nbr_rank, nr.data(), nr.size() * sizeof(int), cudaMemcpyHostToDevice));
+  NSB_CUDA(cudaMalloc(&p.d_send_nbr, std::max<size_t>(send_nbr.size(), 1) * sizeof(int)));
+  NSB_CUDA(cudaMalloc(&p.d_send_j, std::max<size_t>(send_j.size(), 1) * sizeof(int)));
+  if (!send_nbr.empty()) {
+    NSB_CUDA(cudaMemcpy(p.d_send_nbr, send_nbr.data(), send_nbr.size() * sizeof(int), cudaMemcpyHostToDevice));
+    NSB_CUDA(cudaMemcpy(p.d_send_j, send_j.data(), send_j.size() * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  NSB_CUDA(cudaMalloc(&p.d_err, 4 * sizeof(int)));
+  NSB_CUDA(cudaMemset(p.d_err, 0, 4 * sizeof(int)));
+  // peer table of arena bases for the all-reduce kernel
+  NSB_CUDA(cudaMalloc(&p.d_peer_base, 16 * sizeof(double*)));
+  NSB_CUDA(cudaMemcpy(p.d_peer_base, p.peer, 16 * sizeof(double*), cudaMemcpyHostToDevice));
+  // everybody must have mapped everybody before the first remote store
+  double* d_tok = nullptr;
+  NSB_CUDA(cudaMalloc(&d_tok, sizeof(double)));
+  NSB_CUDA(cudaMemset(d_tok, 0, sizeof(double)));
+  NSB_NCCL(ncclAllReduce(d_tok, d_tok, 1, ncclDouble, ncclSum, c->comm, c->stream));
+  NSB_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFree(d_tok);
+  p.on = true;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ halo
+template <int NF>
+__global__ void k_gs_pack_p2p(int nshared, const int* __restrict__ send_seg, const int* __restrict__ send_nbr,
+                              const int* __restrict__ send_j, const int* __restrict__ nbr_cnt, const int* __restrict__ seg_off,
+                              const int* __restrict__ seg_idx, const double* __restrict__ u, long long stride,
+                              double* const* __restrict__ peer_dst, unsigned long long* const* __restrict__ peer_flag, int nnbr,
+                              unsigned long long epoch, unsigned* counter, const CGState* skip) {
+  if (skip && skip->done) return;
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < nshared) {
+    const int seg = send_seg[s];
+    const int a = seg_off[seg], b = seg_off[seg + 1];
+    double acc[NF];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) acc[f] = 0.0;
+    for (int j = a; j < b; ++j) {
+      const int idx = seg_idx[j];
+#pragma unroll
+      for (int f = 0; f < NF; ++f) acc[f] += u[(long long)f * stride + idx];
+    }
+    const int nb = send_nbr[s];
+    double* dst = peer_dst[nb] + send_j[s];
+    const int cnt = nbr_cnt[nb];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) dst[(long long)f * cnt] = acc[f];        // remote store over NVLink
+  }
+  __threadfence_system();
+  __shared__ int s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicInc(counter, gridDim.x - 1);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x < nnbr) {
+    __threadfence_system();
+    st_flag(peer_flag[threadIdx.x], epoch);
+  }
+}
+
+template <int NF>
+__global__ void k_gs_sum_p2p(int nseg, const int* __restrict__ seg_off, const int* __restrict__ seg_idx,
+                             const int* __restrict__ rseg_off, const int* __restrict__ rseg_pos, const int* __restrict__ rseg_cnt,
+                             const int* __restrict__ rseg_nbefore, const double* __restrict__ recvbuf, double* __restrict__ u,
+                             long long stride, const unsigned long long* __restrict__ flags, const int* __restrict__ nbr_rank,
+                             int nnbr, unsigned long long epoch, int* err, const CGState* skip) {
+  if (skip && skip->done) return;
+  __shared__ int ok;
+  if (threadIdx.x == 0) ok = 1;
+  __syncthreads();
+  if (threadIdx.x < nnbr)
+    if (!p2p_wait(flags + nbr_rank[threadIdx.x], epoch, err)) ok = 0;
+  __syncthreads();
+  if (!ok) return;
+  const int seg = blockIdx.x * blockDim.x + threadIdx.x;
+  if (seg >= nseg) return;
+  const int a = seg_off[seg], b = seg_off[seg + 1];
+  double acc[NF], loc[NF];
+#pragma unroll
+  for (int f = 0; f < NF; ++f) { acc[f] = 0.0; loc[f] = 0.0; }
+  for (int j = a; j < b; ++j) {
+    const int idx = seg_idx[j];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) loc[f] += u[(long long)f * stride + idx];
+  }
+  const int ra = rseg_off[seg], rb = rseg_off[seg + 1], nb = rseg_nbefore[seg];
+  for (int j = ra; j < ra + nb; ++j) {
+#pragma unroll
+    for (int f = 0; f < NF; ++f) acc[f] += __ldcv(&recvbuf[rseg_pos[j] + f * rseg_cnt[j]]);
+  }
+#pragma unroll
+  for (int f = 0; f < NF; ++f) acc[f] = (nb > 0) ? acc[f] + loc[f] : loc[f];
+  for (int j = ra + nb; j < rb; ++j) {
+#pragma unroll
+    for (int f = 0; f < NF; ++f) acc[f] += __ldcv(&recvbuf[rseg_pos[j] + f * rseg_cnt[j]]);
+  }
+  for (int j = a; j < b; ++j) {
+    const int idx = seg_idx[j];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) u[(long long)f * stride + idx] = acc[f];
+  }
+}
+
+template <int NF>
+static int dssum_p2p_nf(Ctx* c, double* u, long long stride, const CGState* skip, const int* d_send_seg, const int* d_rseg_cnt) {
+  P2P& p = c->p2p;
+  GSMap& m = c->gs;
+  const int T = 128, R = c->nranks;
+  const unsigned long long epoch = ++p.epoch_halo;
+  const int par = (int)(epoch & 1);
+  if (m.nshared > 0) {
+    k_gs_pack_p2p<NF><<<(m.nshared + T - 1) / T, T, 0, c->stream>>>(m.nshared, d_send_seg, p.d_send_nbr, p.d_send_j, p.d_cnt, m.seg_off,
+                                                                   m.seg_idx, u, stride, p.d_peer_dst + par * m.nnbr,
+                                                                   p.d_peer_flag + par * m.nnbr, m.nnbr, epoch, c->red_count + 2, skip);
+    nsb_count_launch();
+  }
+  if (m.nseg > 0) {
+    const double* recv = p.arena + off_halo(R) + par * p.halo_stride;
+    const unsigned long long* flags = (const unsigned long long*)(p.arena + off_haloflag(par, 0, R));
+    k_gs_sum_p2p<NF><<<(m.nseg + T - 1) / T, T, 0, c->stream>>>(m.nseg, m.seg_off, m.seg_idx, m.rseg_off, m.rseg_pos, d_rseg_cnt,
+                                                               m.rseg_nbefore, recv, u, stride, flags, p.d_nbr_rank, m.nnbr, epoch,
+                                                               p.d_err, skip);
+    nsb_count_launch();
+  }
+  NSB_CUDA(cudaGetLastError());
+  return 0;
+}
+int p2p_dssum(Ctx* c, double* u, int nfields, long long stride, const CGState* skip, const int* d_send_seg, const int* d_rseg_cnt) {
+  switch (nfields) {
+    case 1: return dssum_p2p_nf<1>(c, u, stride, skip, d_send_seg, d_rseg_cnt);
+    case 2: return dssum_p2p_nf<2>(c, u, stride, skip, d_send_seg, d_rseg_cnt);
+    case 3: return dssum_p2p_nf<3>(c, u, stride, skip, d_send_seg, d_rseg_cnt);
+  }
+  return 1;
+}
+
+// ------------------------------------------------------------------------------------------------ all-reduce (+ CG scalar update)
+__device__ void cg_apply(CGState* s, const double* sums, int ncomp, int kind) {
+  for (int f = 0; f < ncomp; ++f) {
+    if (kind == 0) {
+      s[f].rtz1 = sums[2 * f]; s[f].rtz2 = 1.0; s[f].beta = 0.0; s[f].alpha = 0.0;
+      s[f].rnorm = sqrt(fmax(sums[2 * f + 1], 0.0) / s[f].vol);
+      s[f].iter = 0;
+      s[f].done = (s[f].rnorm <= s[f].tol) || (s[f].maxit <= 0);
+    } else if (kind == 1) {
+      if (s[f].done) continue;
+      s[f].rtz2 = s[f].rtz1; s[f].rtz1 = sums[2 * f]; s[f].beta = s[f].rtz1 / s[f].rtz2;
+      s[f].rnorm = sqrt(fmax(sums[2 * f + 1], 0.0) / s[f].vol);
+      s[f].iter += 1;
+      s[f].done = (s[f].rnorm <= s[f].tol) || (s[f].iter >= s[f].maxit) || !(s[f].rnorm == s[f].rnorm);
+    } else if (!s[f].done) {
+      s[f].rho = sums[f]; s[f].alpha = s[f].rtz1 / sums[f];
+    }
+  }
+}
+
+// one CTA; op 0: sum, 1: max.  vals (count <= RSLOT) are reduced in place over all ranks, in rank order.
+__global__ void k_p2p_allreduce(double* vals, int count, int op, double* const* __restrict__ peer_base, double* arena, int rank,
+                                int nranks, int parity, unsigned long long epoch, long long slot_off, long long flag_off,
+                                int* err, CGState* cgs, int ncomp, int kind, const CGState* skip) {
+  if (skip && skip->done) return;
+  __shared__ int ok;
+  if (threadIdx.x == 0) ok = 1;
+  // 1) publish my values in slot [rank] of every arena
+  for (int i = threadIdx.x; i < count * nranks; i += blockDim.x) {
+    const int r = i / count, k = i - r * count;
+    peer_base[r][slot_off + (long long)rank * RSLOT + k] = vals[k];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < nranks) {
+    unsigned long long* f = (unsigned long long*)(peer_base[threadIdx.x] + flag_off + rank);
+    st_flag(f, epoch);
+  }
+  // 2) wait for everybody's contribution
+  if (threadIdx.x < nranks)
+    if (!p2p_wait((const unsigned long long*)(arena + flag_off + threadIdx.x), epoch, err)) ok = 0;
+  __syncthreads();
+  if (!ok) return;
+  // 3) combine in rank order (identical on every rank)
+  for (int k = threadIdx.x; k < count; k += blockDim.x) {
+    double a = __ldcv(&arena[slot_off + k]);
+    for (int r = 1; r < nranks; ++r) {
+      const double b = __ldcv(&arena[slot_off + (long long)r * RSLOT + k]);
+      a = op ? fmax(a, b) : a + b;
+    }
+    vals[k] = a;
+  }
+  if (cgs) {
+    __syncthreads();
+    if (threadIdx.x == 0) cg_apply(cgs, vals, ncomp, kind);
+  }
+}
+
+int p2p_allreduce(Ctx* c, double* dev, int count, int op, CGState* cgs, int ncomp, int kind) {
+  P2P& p = c->p2p;
+  const int R = c->nranks;
+  for (int done = 0; done < count; done += RSLOT) {
+    const int cnt = std::min(RSLOT, count - done);
+    const unsigned long long epoch = ++p.epoch_red;
+    const int par = (int)(epoch & 1);
+    k_p2p_allreduce<<<1, 256, 0, c->stream>>>(dev + done, cnt, op, p.d_peer_base, p.arena, c->rank, R, par, epoch, off_red(par, 0, R),
+                                              off_redflag(par, 0, R), p.d_err, (done + RSLOT >= count) ? cgs : nullptr, ncomp, kind,
+                                              nullptr);
+    nsb_count_launch();
+  }
+  NSB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int p2p_check_error(Ctx* c) {
+  if (!c->p2p.on) return 0;
+  int e[4] = {0, 0, 0, 0};
+  NSB_CUDA(cudaMemcpy(e, c->p2p.d_err, sizeof(e), cudaMemcpyDeviceToHost));
+  if (e[0]) { nsb_set_error("peer-memory collective timed out (a rank stopped participating)"); return 3; }
+  return 0;
+}

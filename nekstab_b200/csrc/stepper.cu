@@ -151,6 +151,7 @@ int st_helmholtz(Ctx* c, int adj, double h1, double h2, int* iters) {
     tot += c->cgs_host[f].iter;
     if (!(c->cgs_host[f].rnorm == c->cgs_host[f].rnorm)) { nsb_set_error("Helmholtz CG produced NaN (component %d)", f); return 2; }
   }
+  NSB_TRY(p2p_check_error(c));
   c->stats.helm_iters += tot;
   if (iters) *iters = tot;
   return 0;
@@ -257,6 +258,7 @@ int st_pressure(Ctx* c, int adj, int* iters) {
     if (sample) { const int kinds[4] = {0, 1, 2, 3}; prof_collect(c, kinds, 4, 4); }
     if (issued > c->maxit_p + c->check_every_p) break;
   }
+  NSB_TRY(p2p_check_error(c));
   if (!(c->cgs_host[3].rnorm == c->cgs_host[3].rnorm)) { nsb_set_error("pressure CG produced NaN"); return 2; }
   if (proj) NSB_TRY(proj_post(c, adj));
   if (c->ifvcor[adj]) {

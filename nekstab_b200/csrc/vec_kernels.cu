@@ -74,10 +74,12 @@ int vk_dot3(Ctx* c, const double* a, const double* b, const double* w, long long
 int vk_sum(Ctx* c, const double* a, long long n, double* out_dev) { return vk_dot3(c, a, nullptr, nullptr, n, out_dev); }
 
 int vk_allreduce_sum(Ctx* c, double* dev, int count) {
+  if (c->p2p.on) return p2p_allreduce(c, dev, count, 0, nullptr, 0, 0);
   if (c->nranks > 1) NSB_NCCL(ncclAllReduce(dev, dev, count, ncclDouble, ncclSum, c->comm, c->stream));
   return 0;
 }
 int vk_allreduce_max(Ctx* c, double* dev, int count) {
+  if (c->p2p.on) return p2p_allreduce(c, dev, count, 1, nullptr, 0, 0);
   if (c->nranks > 1) NSB_NCCL(ncclAllReduce(dev, dev, count, ncclDouble, ncclMax, c->comm, c->stream));
   return 0;
 }
@@ -209,6 +211,7 @@ __global__ void k_cg_finalize(CGState* s, const double* sums, int ncomp, int kin
 int vk_cg_finalize_multi(Ctx* c, CGState* s, int ncomp, int kind) {   // multi-rank path: allreduce then finalize
   int cnt = (kind == 2) ? ncomp : 2 * ncomp;
   if (kind == 2 && s == c->cgs) cnt = 3;
+  if (c->p2p.on) return p2p_allreduce(c, c->red_out, cnt, 0, s, ncomp, kind);   // all-reduce + scalar update in one kernel
   NSB_TRY(vk_allreduce_sum(c, c->red_out, cnt));
   k_cg_finalize<<<1, 32, 0, c->stream>>>(s, c->red_out, ncomp, kind);
   nsb_count_launch();

@@ -107,6 +107,11 @@ enum {
   NSB_FORCE_SENS = 5       /* ts_force_sensitivity_map floor(uparam(1)) == 4   core/matvec.f:357 */
 };
 int nsb_matvec(int mode, int slot_in, int slot_out);
+/* nonlinear_forward_map (core/newton_krylov.f:336-378): slot_f = phi_T(slot_q) - slot_q with the FULL Navier-Stokes
+ * stepper (same kernels, advection term C(u)u; the Dirichlet data are the boundary values of slot_q), then ubase <- slot_q. */
+int nsb_nonlinear_forward_map(int slot_q, int slot_f);
+/* prepare_linearized_solver evaluated on the velocity in `slot` (newton_krylov re-prepares on every iterate, :69). */
+int nsb_prepare_solver_from_slot(int slot, double end_time, double cfl_target, double* dt, int* nsteps, double* ctarg);
 /* Adjoint problems may use different Dirichlet masks (outflow 'O' -> 'v', 1cyl.usr:126-132). NULL = same. */
 int nsb_set_adjoint_masks(const double* v1mask, const double* v2mask, const double* v3mask);
 
@@ -171,6 +176,12 @@ int nsb_select_eigenvalues(int* selected, int* cnt, const double* vals_re, const
 /* ts_gmres (core/newton_krylov.f:175-297): solves matvec(mode) * sol = rhs; slots first..first+ksize hold the basis */
 int nsb_ts_gmres(int mode, int rhs_slot, int sol_slot, int first_slot, int work_slot, int maxiter, int ksize, double tol,
                  int* calls, double* final_res);
+/* newton_krylov (core/newton_krylov.f:5-168), fixed-point branch (uparam(1) = 2): Newton iterations on phi_T(q) - q = 0
+ * with ts_gmres on newton_linearized_map; squared residual norms against tol as in the reference.  Returns 0 when
+ * converged, 3 when maxiter_newton was reached. */
+int nsb_newton_krylov(int q_slot, int f_slot, int dq_slot, int work_slot, int first_slot, int k_dim, double end_time,
+                      double cfl_target, double tol, int maxiter_newton, int maxiter_gmres, int* newton_iters,
+                      double* residual_out, double* hist, long long* calls_out);
 /* LAPACK wrappers exactly as core/lapack_wrapper.f (schur:7, ordschur:70, eig:129, lstsq:287). */
 int nsb_lapack_eig(const double* A, int n, double* vals_re, double* vals_im, double* vecs_reim);
 int nsb_lapack_schur(double* A, int n, double* vecs, double* vals_re, double* vals_im);

@@ -467,6 +467,35 @@ extern "C" int nsb_matvec(int mode, int sin, int sout) {
   return 1;
 }
 
+// nonlinear_forward_map (core/newton_krylov.f:336-378): f = phi_T(q) - q with the full Navier-Stokes stepper (q carries its
+// Dirichlet data); afterwards q becomes the base flow of the linearised maps (ubase <- q, :374-375).
+extern "C" int nsb_nonlinear_forward_map(int sq, int sf) {
+  REQUIRE_CTX(); CHECK_SLOT(sq); CHECK_SLOT(sf);
+  if (sq == sf) { nsb_set_error("nonlinear_forward_map: input and output slots must differ"); return 1; }
+  double* q = slot_ptr(c, sq);
+  double* f = slot_ptr(c, sf);
+  NSB_TRY(st_linearized_map(c, 2, q, f));
+  NSB_TRY(vk_axpy(c, f, -1.0, q, c->vlen));
+  if (!c->ub) NSB_TRY(dalloc(&c->ub, c->n * c->ldim));
+  return vk_copy(c, c->ub, q, c->n * c->ldim);
+}
+// prepare_linearized_solver on the velocity of a Krylov vector instead of the stored base flow (newton_krylov calls it on
+// the current Newton iterate, core/newton_krylov.f:69 with vx,vy,vz = q)
+extern "C" int nsb_prepare_solver_from_slot(int slot, double end_time, double cfl_target, double* dt, int* nsteps, double* ctarg) {
+  REQUIRE_CTX(); CHECK_SLOT(slot);
+  if (cfl_target > 1.0) cfl_target = 0.5;
+  NSB_TRY(ek_cfl(c, slot_ptr(c, slot), c->red_out + 8));
+  NSB_TRY(vk_allreduce_max(c, c->red_out + 8, 1));
+  double ct;
+  NSB_TRY(d2h(c, &ct, c->red_out + 8, 1));
+  if (!(ct > 0)) { nsb_set_error("compute_cfl returned %g", ct); return 1; }
+  int ns = (int)std::ceil(end_time / (cfl_target / ct));
+  c->dt = end_time / ns; c->nsteps = ns;
+  if (dt) *dt = c->dt;
+  if (nsteps) *nsteps = ns;
+  if (ctarg) *ctarg = ct;
+  return 0;
+}
 extern "C" int nsb_get_stats(nsb_stats* out, int reset) {
   REQUIRE_CTX();
   if (out) *out = c->stats;

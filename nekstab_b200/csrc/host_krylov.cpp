@@ -291,3 +291,35 @@ extern "C" int nsb_ts_gmres(int mode, int rhs_slot, int sol_slot, int first_slot
   if (final_res) *final_res = beta * beta;
   return 0;
 }
+
+// ------------------------------------------------------------------ core/newton_krylov.f:5-168 (fixed points, uparam(1) = 2)
+// q_slot: current estimate (in/out).  Slots used: f_slot, dq_slot, work_slot, and first_slot..first_slot+k_dim for the GMRES
+// basis.  Residuals are SQUARED norms compared with tol, as in the reference (:99,:109).  hist (optional, maxiter_newton
+// entries) receives the residual of every Newton iteration (residu_newton.dat).
+extern "C" int nsb_newton_krylov(int q_slot, int f_slot, int dq_slot, int work_slot, int first_slot, int k_dim, double end_time,
+                                 double cfl_target, double tol, int maxiter_newton, int maxiter_gmres, int* newton_iters,
+                                 double* residual_out, double* hist, long long* calls_out) {
+  double residual = 0.0;
+  long long calls_counter = 0;
+  int it = 0;
+  for (it = 1; it <= maxiter_newton; ++it) {
+    double dt = 0, ct = 0;
+    int nsteps = 0;
+    NSB_TRY(nsb_prepare_solver_from_slot(q_slot, end_time, cfl_target, &dt, &nsteps, &ct));   // :69
+    NSB_TRY(nsb_nonlinear_forward_map(q_slot, f_slot));                                        // :90
+    calls_counter += nsteps;
+    NSB_TRY(nsb_vec_norm(f_slot, &residual));
+    residual *= residual;                                                                      // :99
+    if (hist) hist[it - 1] = residual;
+    if (residual < tol) break;                                                                 // :109
+    int calls = 0;
+    double gres = 0;
+    NSB_TRY(nsb_ts_gmres(NSB_NEWTON, f_slot, dq_slot, first_slot, work_slot, maxiter_gmres, k_dim, tol, &calls, &gres));   // :117
+    calls_counter += (long long)calls * nsteps;
+    NSB_TRY(nsb_vec_sub2(q_slot, dq_slot));                                                    // :122
+  }
+  if (newton_iters) *newton_iters = it;
+  if (residual_out) *residual_out = residual;
+  if (calls_out) *calls_out = calls_counter;
+  return (residual < tol) ? 0 : 3;
+}

@@ -271,7 +271,9 @@ int st_pressure(Ctx* c, int adj, int* iters) {
   return 0;
 }
 
-static int one_step(Ctx* c, int istep, int adj) {
+// kind: 0 direct, 1 adjoint perturbation step; 2 full Navier-Stokes step (nonlinear_forward_map, core/newton_krylov.f:336-378)
+static int one_step(Ctx* c, int istep, int kind) {
+  const int adj = (kind == 1) ? 1 : 0;
   const int D = c->ldim;
   const long long dn = c->n * D;
   const int k = istep < 3 ? istep : 3;
@@ -279,7 +281,13 @@ static int one_step(Ctx* c, int istep, int adj) {
   // explicit term into the oldest ring slot, then rotate so that f[0] is current
   double* fnew = c->f[2];
   prof_mark(c, c->prof_on, 10);
-  NSB_TRY(ek_advab(c, adj, c->u, c->ub, c->spng, fnew));
+  if (kind == 2) {
+    // f = -B (u.grad)u : the direct perturbation form with U = u' = u gives 2 C(u)u  [UPSTREAM navier1.f makef -> advab -> convop]
+    NSB_TRY(ek_advab(c, 0, c->u, c->u, nullptr, fnew));
+    NSB_TRY(vk_scale(c, fnew, 0.5, dn));
+  } else {
+    NSB_TRY(ek_advab(c, adj, c->u, c->ub, c->spng, fnew));
+  }
   prof_mark(c, c->prof_on, 11);
   c->f[2] = c->f[1]; c->f[1] = c->f[0]; c->f[0] = fnew;
   double* b = c->wk[0];
@@ -311,14 +319,14 @@ static int one_step(Ctx* c, int istep, int adj) {
 // vin / vout: device Krylov vectors [vx|vy|(vz)|pr]
 int st_linearized_map(Ctx* c, int adjoint, const double* vin, double* vout) {
   if (c->nsteps <= 0 || c->dt <= 0) { nsb_set_error("time step not set: call nsb_prepare_linearized_solver / nsb_set_timestep"); return 1; }
-  if (!c->ub) { nsb_set_error("base flow not set: call nsb_set_baseflow"); return 1; }
+  if (!c->ub && adjoint != 2) { nsb_set_error("base flow not set: call nsb_set_baseflow"); return 1; }
   const long long dn = c->n * c->ldim;
   const int adj = (adjoint && c->has_adj_masks) ? 1 : 0;
   NSB_CUDA(cudaEventRecord(c->ev0, c->stream));
   NSB_TRY(vk_copy(c, c->u, vin, dn));            // nopcopy(vxp,..,prp <- q)   core/matvec.f:212
   NSB_TRY(vk_copy(c, c->pr, vin + dn, c->n2));
   for (int istep = 1; istep <= c->nsteps; ++istep) {
-    int rc = one_step(c, istep, adjoint ? 1 : 0);
+    int rc = one_step(c, istep, adjoint);
     if (rc) return rc;
     (void)adj;
   }

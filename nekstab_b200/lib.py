@@ -81,6 +81,9 @@ _SIGS = {
     "nsb_basis_rotate": [C.c_int, C.c_int, _dp, C.c_int],
     "nsb_orthonormalize": [C.c_int, C.c_int, C.c_int, _dp],
     "nsb_matvec": [C.c_int] * 3,
+    "nsb_nonlinear_forward_map": [C.c_int, C.c_int],
+    "nsb_prepare_solver_from_slot": [C.c_int, C.c_double, C.c_double, _dp, _ip, _dp],
+    "nsb_newton_krylov": [C.c_int] * 6 + [C.c_double] * 3 + [C.c_int, C.c_int, _ip, _dp, _dp, _lp],
     "nsb_get_stats": [C.POINTER(Stats), C.c_int],
     "nsb_profile": [C.c_int, _dp, _lp],
     "nsb_op_axhelm": [_dp, C.c_double, C.c_double, _dp],
@@ -287,6 +290,19 @@ class NekStabB200:
 
     def matvec(self, mode, slot_in, slot_out):
         _ck(self.lib.nsb_matvec(mode, slot_in, slot_out))
+
+    def nonlinear_forward_map(self, slot_q, slot_f):
+        _ck(self.lib.nsb_nonlinear_forward_map(slot_q, slot_f))
+
+    def newton_krylov(self, q_slot, f_slot, dq_slot, work_slot, first_slot, k_dim, end_time, tol, cfl_target=0.5,
+                      maxiter_newton=100, maxiter_gmres=100):
+        it, res, calls = C.c_int(), C.c_double(), C.c_longlong()
+        hist = np.zeros(maxiter_newton)
+        rc = self.lib.nsb_newton_krylov(q_slot, f_slot, dq_slot, work_slot, first_slot, k_dim, end_time, cfl_target, tol,
+                                        maxiter_newton, maxiter_gmres, C.byref(it), C.byref(res), _p(hist), C.byref(calls))
+        if rc not in (0, 3):
+            _ck(rc)
+        return rc == 0, it.value, res.value, hist[:min(it.value, maxiter_newton)], calls.value
 
     # ---- host drivers
     def arnoldi_factorization(self, mode, first_slot, H, mstart, mend, ksize):

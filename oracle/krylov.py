@@ -173,3 +173,19 @@ def ts_gmres(matvec, rhs, maxiter, ksize, tol, w):
         if beta ** 2 < tol:
             break
     return sol, calls, beta ** 2
+
+
+def newton_krylov(nonlinear_map, linearized_map_factory, q0, k_dim, tol, w, maxiter_newton=100, maxiter_gmres=100):
+    """core/newton_krylov.f:5-168, fixed-point branch.  nonlinear_map(q) -> phi_T(q) - q ; linearized_map_factory(q) returns
+    the matvec q' -> (exp(TL(q)) - I) q' about the current iterate (newton_linearized_map, core/matvec.f:381-402)."""
+    q = q0
+    hist = []
+    for it in range(1, maxiter_newton + 1):
+        f = nonlinear_map(q)
+        residual = inner(f, f, w)                      # squared norm (:99)
+        hist.append(residual)
+        if residual < tol:
+            break
+        dq, calls, _ = ts_gmres(linearized_map_factory(q), f, maxiter_gmres, k_dim, tol, w)
+        q = axpy(q, -1.0, dq)
+    return q, it, hist

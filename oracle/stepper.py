@@ -156,10 +156,18 @@ class LinearizedStepper:
     # -------------------------------------------------------------- explicit terms
     def explicit_rhs(self, u, adjoint):
         s = self.s
+        if adjoint == "nonlinear":
+            # full Navier-Stokes: f = -B (u.grad)u [UPSTREAM navier1.f makef/advab -> convop]; C(u)u = advab_direct(u,u)/2
+            return -0.5 * s.advab_direct(u, u)
         f = -(s.advab_adjoint(u, self.ub) if adjoint else s.advab_direct(u, self.ub))
         if self.spng is not None:
             f = f - s.bm1 * self.spng * u
         return f
+
+    def nonlinear_forward_map(self, v, p, nsteps, dt):
+        """core/newton_krylov.f:336-378: f = phi_T(q) - q with the full (nonlinear) stepper; Dirichlet data live in q."""
+        u, pr = self.linearized_map(v, p, nsteps, dt, adjoint="nonlinear")
+        return u - v.reshape(u.shape), pr - p.reshape(pr.shape), u, pr
 
     # -------------------------------------------------------------- the maps
     def linearized_map(self, v, p, nsteps, dt, adjoint=False, record=None):

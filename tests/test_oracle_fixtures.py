@@ -105,3 +105,17 @@ def test_kat_eig(cyl):
     # log-transform relation of Spectre_NSd.dat (core/eigensolvers.f:596-598)
     lam = np.log(mu) / (dt * nsteps)
     assert abs(lam.real - g["Spectre_NSd_conv"][0, 0]) < 2e-7 and abs(abs(lam.imag) - abs(g["Spectre_NSd_conv"][0, 1])) < 2e-7
+
+
+def test_kat_fixed_point_nonlinear_map(cyl):
+    """The shipped Re=50 base flow under the oracle's FULL Navier-Stokes stepper (nonlinear_forward_map,
+    core/newton_krylov.f:336-378; no sponge as in baseflow/newton/1cyl.par): ||phi_T(U) - U|| = 3.1e-6, ||U|| = 46.15
+     -- residual^2 = 9.6e-12, just under Newton's exit test of 1e-11."""
+    g, c, s = cyl
+    ub = c.ubase.reshape((2,) + s.eshape)
+    dt, nsteps, _ = prepare_linearized_solver(s, ub, 1.0)
+    st = LinearizedStepper(s, ub, c.re, None, solver="direct", ifvcor=False)
+    fv, fp, u, pr = st.nonlinear_forward_map(ub, s.to_m2(g["P"].astype(float)), nsteps, dt)
+    res = np.sqrt(_inner(s, fv, fv, s.bm1))
+    assert abs(np.sqrt(_inner(s, ub, ub, s.bm1)) - 46.1512) < 1e-3
+    assert abs(res - 3.096e-6) < 0.05e-6 and res ** 2 < 1e-11

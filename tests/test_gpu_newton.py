@@ -40,7 +40,7 @@ def test_nonlinear_forward_map(name):
         fo, fpo, uo, po = st.nonlinear_forward_map(q, p0, nsteps, dt)
         assert rel(f, fo) < 1e-9, rel(f, fo)
         # ubase <- q (core/newton_krylov.f:374-375): the Newton-mode matvec now linearises about q
-        st2 = LinearizedStepper(s, q, c.re, None, solver="direct", ifvcor=c.ifvcor)
+        st2 = LinearizedStepper(s, q, c.re, c.spng_fun, solver="direct", ifvcor=c.ifvcor)   # the perturbation sponge stays on
         v0 = smooth_field(c, 8).reshape(q.shape)
         g.vec_upload(0, v0, p0)
         g.matvec(lib.NEWTON, 0, 2)

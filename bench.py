@@ -40,6 +40,7 @@ WORDS = {
     "dssum": 3 * 2 * FS + 0.5 * FS,                  # surface values R+W for 3 fields + int32 index
     "pcg_div": 3.0 + 1.0 + (9 + 1 + 1) * R2,         # read 3 fields + mask*binv; 9 metrics + pdir read, Ep write (mesh 2)
     "pcg_update": 8 * R2,                            # x,p,r,Ep,dinvE,bm2inv read; x,r write
+    "pcg_precond": (2 + 1 + 126.0 / 216.0) * R2,     # r read twice (restrict, apply), z write, 126 words of FDM factors per element
     # Helmholtz-CG iteration pieces (3 components batched)
     "hcg_axhelm": 3 * (1 + 1 + 1 + 1) + 6 + 1 + 1,   # per comp r,p read, p,w write; 6 G + bm1 + dinv once
     "hcg_dssum": 3 * 2 * FS + 0.5 * FS,
@@ -177,6 +178,10 @@ def main():
     ap.add_argument("--small", action="store_true", help="tiny 3-layer mesh (debugging only; not a valid bench line)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tol", type=float, default=1e-8)
+    ap.add_argument("--precond", default=os.environ.get("NSB_BENCH_PRECOND", "jacobi"), choices=["jacobi", "pmg"],
+                    help="pressure-CG preconditioner: jacobi (north-star) or pmg (FDM element blocks + vertex-mesh Jacobi + "
+                         "aggregate coarse solve, csrc/pmg.cu: the reference's class of preconditioner)")
+    ap.add_argument("--nagg", type=int, default=0)
     ap.add_argument("--mxprev", type=int, default=0,
                     help="pressure residual projection size (reference: residualProj=yes, mxprev=20). Measured on this workload "
                          "(noise-seeded first steps): 20 -> 4317 its/step vs 2427 without, so the bench default is 0 = off")
@@ -223,6 +228,8 @@ def main():
     seed = np.stack([ctx.op_dssum(raw[k].ravel()) / mult for k in range(3)]).reshape(3, case.nel, -1) * case.mask
     ctx.set_params(1.0 / case.re, 1.0, args.tol, args.tol, 2000, 100000)
     ctx.set_projection(args.mxprev)
+    if args.precond == "pmg":
+        ctx.set_pressure_preconditioner(1, args.nagg)
     dt, _, ctarg = ctx.prepare_linearized_solver(1.0, 0.5)
     ctx.vec_alloc(3)
     ctx.vec_upload(0, seed, None)
@@ -289,10 +296,10 @@ def main():
                 kern[kname] = {"avg_ms": ms / cnt, "samples": cnt, "alg_GBs": gbs, "frac": gbs / peak}
             elif cnt > 0:
                 kern[kname] = {"avg_ms": ms / cnt, "samples": cnt}
-        pc = [k for k in ("pcg_gradt", "dssum", "pcg_div", "pcg_update") if k in kern]
+        pc = [k for k in ("pcg_gradt", "dssum", "pcg_div", "pcg_update", "pcg_precond") if k in kern]
         dom = max(pc, key=lambda k: kern[k]["avg_ms"]) if pc else None
         iter_ms = sum(kern[k]["avg_ms"] for k in pc) if pc else None
-        iter_words = sum(WORDS[k] for k in pc) if pc else None
+        iter_words = sum(WORDS.get(k, 0.0) for k in pc) if pc else None
         roof = None
         if dom:
             roof = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["alg_GBs"], "peak": peak, "unit": "GB/s",
@@ -307,7 +314,8 @@ def main():
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": case.name if world == 1 else f"cyl3d_1996x{10 * world}_lx8", "elements": int(n_glob // 512),
                            "dof": int(n_glob), "lx1": 8, "lxd": 12, "lx2": 6, "dt": dt, "re": 50.0, "tol_v": args.tol,
-                           "tol_p": args.tol, "pressure_solver": "Jacobi-PCG (north-star)", "residual_projection_mxprev": args.mxprev,
+                           "tol_p": args.tol, "pressure_solver": "Jacobi-PCG (north-star)" if args.precond == "jacobi" else
+                           "PCG, three-level additive preconditioner (FDM element blocks + Q1 vertex-mesh Jacobi + aggregate coarse solve)", "residual_projection_mxprev": args.mxprev,
                            "pres_iters_per_step": st["pres_iters"] / K, "helm_iters_per_comp_per_step": st["helm_iters"] / K / 3,
                            "l2": "per-iteration working set (2 GB) >> L2 (126 MB): no flush needed", "parallelism": f"elements/{world}",
                            "setup_s": t_setup, "wall_s_timed": wall},

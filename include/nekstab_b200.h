@@ -70,6 +70,13 @@ int nsb_set_ifvcor(int direct, int adjoint);
  * count; the converged answer is unchanged.  The basis persists across steps and matvecs, as in the reference.
  * 0 (the default) switches it off, which makes every matvec a pure function of its input (used by the parity tests). */
 int nsb_set_projection(int mxprev);
+/* Preconditioner of the pressure CG on E = D (mask B^-1 QQ^T) D^T.  kind 0: Jacobi (the default; the north-star's solver).
+ * kind 1: three-level additive operator of the class the reference runs (`[PRESSURE] preconditioner = semg_xxt`,
+ * 1cyl.par:28; [UPSTREAM] hsmg.f): element blocks by fast diagonalisation + Jacobi on the Q1 space of the element-vertex
+ * mesh + an exactly solved problem on `nagg` element aggregates (0 = automatic: nelv/32, at most 512).  Changes the
+ * iteration count (measured 2 787 -> 206 on the cylinder mesh), not the converged pressure.  Rebuilt automatically when
+ * nsb_set_adjoint_masks changes the adjoint operator.  Environment NSB_PRECOND=1 selects kind 1 at nsb_init. */
+int nsb_set_pressure_preconditioner(int kind, int nagg);
 
 /* ------------------------------------------------------------------ krylov_vector algebra
  * One slot = one `type(krylov_vector)` (core/krylov_subspace.f:10-15): vx,vy,vz(n), pr(n2); the
@@ -125,9 +132,10 @@ typedef struct nsb_stats {
 } nsb_stats;
 int nsb_get_stats(nsb_stats* out, int reset);
 /* Sampling kernel profiler (CUDA events on the launching stream around single launches, one sample set per host
- * poll of a CG loop).  enable: 1 start (clears), 0 stop (clears), -1 just read.  Arrays of 8: accumulated ms and
+ * poll of a CG loop).  enable: 1 start (clears), 0 stop (clears), -1 just read.  Arrays of 12: accumulated ms and
  * sample count per kind: 0 pressure-CG gradt, 1 dssum (ldim fields), 2 pressure-CG div, 3 pressure-CG vector update,
- * 4 Helmholtz-CG axhelm, 5 Helmholtz-CG vector update, 6 advection, 7 Helmholtz dssum. */
+ * 4 Helmholtz-CG axhelm, 5 Helmholtz-CG vector update, 6 advection, 7 Helmholtz dssum, 8 pressure preconditioner
+ * (all its launches), 9-11 unused. */
 int nsb_profile(int enable, double* ms_sum, long long* count);
 
 /* ------------------------------------------------------------------ operator-level entry points
@@ -146,6 +154,12 @@ int nsb_op_advab(int adjoint, const double* upx, const double* upy, const double
 int nsb_op_hmholtz(double* ux, double* uy, double* uz, const double* rx, const double* ry, const double* rz,
                    double h1, double h2, int* iters);            /* rhs un-assembled; returns du */
 int nsb_op_esolver(const double* g, double* phi, int* iters);
+/* z = M^-1 r, the preconditioner selected with nsb_set_pressure_preconditioner(1, ..), on mesh-2 arrays */
+int nsb_op_pc_apply(int adjoint, const double* r, double* z);
+/* set-up data of that preconditioner (direct mask set) as doubles: which 0: aggregate of every element [nelv];
+ * 1: diag(P^T E P) per local vertex (ascending global corner id); 2: (Pa^T E Pa)^-1 [nagg*nagg];
+ * 3: {vertices, aggregates, colours used for probing, local aggregates} */
+int nsb_pc_get(int which, double* out, long long* count);
 int nsb_op_cfl(const double* ux, const double* uy, const double* uz, double dt, double* cfl);
 /* named geometry arrays for parity checks: "bm1","binvm1","jacm1","g1".."g6","bm2","ediag","hdiagA","vmult" */
 int nsb_get_field(const char* name, double* out, long long* count);

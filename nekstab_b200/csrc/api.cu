@@ -118,6 +118,9 @@ extern "C" int nsb_finalize(void) {
     if (c->dinvE[s]) cudaFree(c->dinvE[s]);
   }
   if (c->projX) { cudaFree(c->projX); cudaFree(c->projEX); }
+  pm_free(c->pmg[0]); pm_free(c->pmg[1]);
+  if (c->pz) cudaFree(c->pz);
+  if (c->ones2) cudaFree(c->ones2);
   if (c->cgs) cudaFree(c->cgs);
   if (c->cgs_host) cudaFreeHost(c->cgs_host);
   if (c->red_host) cudaFreeHost(c->red_host);
@@ -193,6 +196,15 @@ extern "C" int nsb_init(int ldim, int lx1, int lxd, int lx2, int nelv, long long
   NSB_TRY(st_alloc(c));
 
   NSB_TRY(gs_setup(c, glo_num));
+  {   // global ids of the element corners: the vertex (Q1) mesh of the pressure preconditioner (pmg.cu)
+    const int NK = (D == 3) ? 8 : 4, N = lx1 - 1;
+    c->vglo.resize((size_t)nelv * NK);
+    for (int e = 0; e < nelv; ++e)
+      for (int k = 0; k < NK; ++k) {
+        const int i = (k & 1) ? N : 0, j = ((k >> 1) & 1) ? N : 0, kk = ((k >> 2) & 1) ? N : 0;
+        c->vglo[(size_t)e * NK + k] = glo_num[(size_t)e * c->np1 + (size_t)(kk * lx1 + j) * lx1 + i];
+      }
+  }
   NSB_TRY(ek_geometry(c));
   // positive Jacobian check + volumes
   NSB_TRY(vk_dot3(c, c->bm1, nullptr, nullptr, c->n, c->red_out + 8));
@@ -230,6 +242,8 @@ extern "C" int nsb_init(int ldim, int lx1, int lxd, int lx2, int nelv, long long
   const char* nf = getenv("NSB_FUSED_GS");
   c->fused_gs = (c->ldim == 3 && c->nranks == 1 && c->gs.nb_off != nullptr && nf && nf[0] == '1');
   NSB_CUDA(cudaStreamSynchronize(c->stream));
+  const char* pcv = getenv("NSB_PRECOND");
+  if (pcv && pcv[0] == '1') NSB_TRY(nsb_set_pressure_preconditioner(1, 0));
   return 0;
 }
 
@@ -246,6 +260,7 @@ extern "C" int nsb_set_adjoint_masks(const double* m0, const double* m1, const d
     c->dinvE[1] = c->dinvE[0];
     c->ifvcor[1] = c->ifvcor[0];
     c->mask_same[1] = c->mask_same[0];
+    if (c->pc_kind) NSB_TRY(pm_setup(c, 1, c->pc_nagg));
     return 0;
   }
   for (int d = 0; d < 3; ++d) { c->mask[1][d] = nullptr; c->mbinv[1][d] = nullptr; }
@@ -253,6 +268,7 @@ extern "C" int nsb_set_adjoint_masks(const double* m0, const double* m1, const d
   NSB_TRY(setup_masks(c, 1, m0, m1, m2));
   c->has_adj_masks = true;
   NSB_CUDA(cudaStreamSynchronize(c->stream));
+  if (c->pc_kind) NSB_TRY(pm_setup(c, 1, c->pc_nagg));
   return 0;
 }
 
@@ -308,6 +324,46 @@ extern "C" int nsb_set_projection(int mxprev) {
     NSB_TRY(dalloc(&c->projX, (long long)mxprev * c->n2));
     NSB_TRY(dalloc(&c->projEX, (long long)mxprev * c->n2));
   }
+  return 0;
+}
+extern "C" int nsb_set_pressure_preconditioner(int kind, int nagg) {
+  REQUIRE_CTX();
+  if (kind != 0 && kind != 1) { nsb_set_error("nsb_set_pressure_preconditioner: kind must be 0 (Jacobi) or 1 (pmg)"); return 1; }
+  if (nagg < 0 || nagg > 512) { nsb_set_error("nsb_set_pressure_preconditioner: nagg must be in [0, 512]"); return 1; }
+  drop_graphs(c);
+  c->pc_kind = 0;
+  if (kind == 0) return 0;
+  if (!c->pz) {
+    NSB_TRY(dalloc(&c->pz, c->n2));
+    NSB_TRY(dalloc(&c->ones2, c->n2));
+    NSB_TRY(vk_fill(c, c->ones2, 1.0, c->n2));
+  }
+  c->pc_nagg = nagg;
+  NSB_TRY(pm_setup(c, 0, nagg));
+  NSB_TRY(pm_setup(c, 1, nagg));     // the adjoint mask set has its own E (identical factors when the masks coincide)
+  c->pc_kind = 1;
+  return 0;
+}
+extern "C" int nsb_op_pc_apply(int adjoint, const double* r, double* z) {
+  REQUIRE_CTX();
+  if (!c->pz || !c->pmg[adjoint ? 1 : 0].ready) { nsb_set_error("nsb_op_pc_apply: call nsb_set_pressure_preconditioner(1, ..) first"); return 1; }
+  NSB_TRY(h2d(c, c->pk[3], r, c->n2));
+  NSB_TRY(pm_apply(c, adjoint ? 1 : 0, c->pk[3], c->pz, 0));
+  return d2h(c, z, c->pz, c->n2);
+}
+extern "C" int nsb_pc_get(int which, double* out, long long* count) {
+  REQUIRE_CTX();
+  const PMG& m = c->pmg[0];
+  if (!m.ready) { nsb_set_error("nsb_pc_get: preconditioner not set up"); return 1; }
+  long long n = 0;
+  switch (which) {
+    case 0: n = (long long)m.h_agg.size(); if (out) for (long long i = 0; i < n; ++i) out[i] = m.h_agg[i]; break;
+    case 1: n = (long long)m.h_d1.size(); if (out) for (long long i = 0; i < n; ++i) out[i] = m.h_d1[i]; break;
+    case 2: n = (long long)m.h_A2inv.size(); if (out) for (long long i = 0; i < n; ++i) out[i] = m.h_A2inv[i]; break;
+    case 3: n = 4; if (out) { out[0] = m.nv; out[1] = m.nagg; out[2] = m.ncolours; out[3] = m.nagg_loc; } break;
+    default: nsb_set_error("nsb_pc_get: bad selector %d", which); return 1;
+  }
+  if (count) *count = n;
   return 0;
 }
 extern "C" int nsb_set_ifvcor(int direct, int adjoint) {
@@ -506,11 +562,11 @@ extern "C" int nsb_profile(int enable, double* ms_sum, long long* count) {
   REQUIRE_CTX();
   if (enable > 0 && !c->prof_ev[0])
     for (int i = 0; i < 16; ++i) NSB_CUDA(cudaEventCreate(&c->prof_ev[i]));
-  if (ms_sum) for (int i = 0; i < 8; ++i) ms_sum[i] = c->prof_ms[i];
-  if (count) for (int i = 0; i < 8; ++i) count[i] = c->prof_cnt[i];
+  if (ms_sum) for (int i = 0; i < 12; ++i) ms_sum[i] = c->prof_ms[i];
+  if (count) for (int i = 0; i < 12; ++i) count[i] = c->prof_cnt[i];
   if (enable >= 0) {
     c->prof_on = enable;
-    for (int i = 0; i < 8; ++i) { c->prof_ms[i] = 0; c->prof_cnt[i] = 0; }
+    for (int i = 0; i < 12; ++i) { c->prof_ms[i] = 0; c->prof_cnt[i] = 0; }
   }
   return 0;
 }

@@ -823,7 +823,9 @@ int ek_gradt(Ctx* c, const double* p, double* w) {
 int ek_pcg_dir_gradt(Ctx* c, int adj) {
   // r = pk[0], pdir = pk[2], w = wk[2]
   if (c->ldim == 3) return pk_pcg_dir_gradt(c, adj);
-  DISPATCH_DN(c, k_gradt<D, N, 1><<<c->nel, Cfg<D, N>::TPB, 0, c->stream>>>(c->pk[0], c->wk[2], c->RW2, c->dinvE[adj], c->pk[2],
+  const double* zsrc = c->pc_kind ? c->pz : c->pk[0];           // separately applied preconditioner: z = M^-1 r replaces dinvE*r
+  const double* zscale = c->pc_kind ? c->ones2 : c->dinvE[adj];
+  DISPATCH_DN(c, k_gradt<D, N, 1><<<c->nel, Cfg<D, N>::TPB, 0, c->stream>>>(zsrc, c->wk[2], c->RW2, zscale, c->pk[2],
                                                                          c->cgs + 3, c->n, c->n2));
   nsb_count_launch();
   NSB_CUDA(cudaGetLastError());

@@ -96,6 +96,24 @@ struct P2P {
   unsigned long long epoch_halo = 0, epoch_red = 0;
 };
 
+// Three-level additive pressure preconditioner (pmg.cu), one instance per mask set (direct / adjoint)
+struct PMG {
+  bool ready = false;
+  int nv = 0;                       // local vertices of the element-vertex (Q1) mesh
+  int nagg = 0, nagg_loc = 0, agg_first = 0, ncolours = 0;
+  double* S = nullptr;              // [nel][ldim][lx2*lx2] FDM eigenvectors (row = nodal index, column = mode)
+  double* lam = nullptr;            // [nel][ldim][lx2]     FDM eigenvalues times the box-geometry factor
+  int* vid = nullptr;               // [nel][2^ldim] local vertex of every element corner
+  int *voff = nullptr, *vent = nullptr;   // CSR vertex -> (element, corner) entries
+  double* d1inv = nullptr;          // [nv] 1/diag(P^T E P)
+  int* agg = nullptr;               // [nel] aggregate of every element (global aggregate id)
+  int *aoff = nullptr, *aent = nullptr;   // CSR local aggregate -> elements
+  double* A2inv = nullptr;          // [nagg][nagg] (Pa^T E Pa)^-1
+  double *rc = nullptr, *xv = nullptr, *ra = nullptr, *x2 = nullptr;   // work: corner sums, vertex values, aggregate sums/values
+  std::vector<int> h_agg;
+  std::vector<double> h_d1, h_A2inv;
+};
+
 struct Ctx {
   int ldim = 0, lx1 = 0, lxd = 0, lx2 = 0, nel = 0;
   long long nelg = 0;
@@ -128,6 +146,12 @@ struct Ctx {
   double* dinvH = nullptr;  // 1/(h1*hdiagA + h2*hdiagB) for the current h2
   double dinvH_h1 = -1, dinvH_h2 = -1;
   double* dinvE[2] = {nullptr, nullptr};
+  // pressure preconditioner: 0 = Jacobi (north-star), 1 = three-level additive Schwarz/multilevel (pmg.cu)
+  int pc_kind = 0, pc_nagg = 0;
+  PMG pmg[2];
+  double* pz = nullptr;       // [n2] z = M^-1 r
+  double* ones2 = nullptr;    // [n2] all ones (lets the fused direction kernels read z in place of dinvE*r)
+  std::vector<long long> vglo;   // [nel][2^ldim] global ids of the element corners (from glo_num)
   double vol = 0, vol2 = 0;
   long long n2_glob = 0;
   bool ifvcor[2] = {false, false};
@@ -192,8 +216,8 @@ struct Ctx {
   // per-kernel sampling profiler (CUDA events on the launching stream; one sample set per host poll)
   int prof_on = 0;
   cudaEvent_t prof_ev[16] = {nullptr};
-  double prof_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  long long prof_cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  double prof_ms[12] = {0};
+  long long prof_cnt[12] = {0};
 
   // stats
   nsb_stats stats = {0, 0, 0, 0, 0.0};
@@ -280,6 +304,12 @@ int vk_multidot_raw(Ctx* c, int k, const double* Q, long long vlen, const double
 int vk_multiaxpy_raw(Ctx* c, int k, const double* Q, long long vlen, const double* f, double a, const double* h_dev, double sign,
                      double* out);
 int vk_rotate(Ctx* c, int k, int first_slot, const double* S_dev, int lds);
+
+// ---- pressure preconditioner (pmg.cu)
+int pm_setup(Ctx* c, int set, int nagg_req);
+int pm_apply(Ctx* c, int set, const double* r, double* z, int mode);
+void pm_free(PMG& m);
+int vk_cg_finalize_multi(Ctx* c, CGState* s, int ncomp, int kind);
 
 // ---- solvers / stepper (stepper.cu)
 int st_alloc(Ctx* c);

@@ -282,8 +282,21 @@ __device__ void cg_apply(CGState* s, const double* sums, int ncomp, int kind) {
       s[f].rnorm = sqrt(fmax(sums[2 * f + 1], 0.0) / s[f].vol);
       s[f].iter += 1;
       s[f].done = (s[f].rnorm <= s[f].tol) || (s[f].iter >= s[f].maxit) || !(s[f].rnorm == s[f].rnorm);
-    } else if (!s[f].done) {
-      s[f].rho = sums[f]; s[f].alpha = s[f].rtz1 / sums[f];
+    } else if (kind == 2) {
+      if (!s[f].done) { s[f].rho = sums[f]; s[f].alpha = s[f].rtz1 / sums[f]; }
+    } else if (kind == 3) {          // init, residual norm only (separate preconditioner delivers z^T r with kind 5)
+      s[f].rtz1 = 1.0; s[f].rtz2 = 1.0; s[f].beta = 0.0; s[f].alpha = 0.0;
+      s[f].rnorm = sqrt(fmax(sums[2 * f + 1], 0.0) / s[f].vol);
+      s[f].iter = 0;
+      s[f].done = (s[f].rnorm <= s[f].tol) || (s[f].maxit <= 0);
+    } else if (kind == 4) {
+      if (s[f].done) continue;
+      s[f].rtz2 = s[f].rtz1;
+      s[f].rnorm = sqrt(fmax(sums[2 * f + 1], 0.0) / s[f].vol);
+      s[f].iter += 1;
+      s[f].done = (s[f].rnorm <= s[f].tol) || (s[f].iter >= s[f].maxit) || !(s[f].rnorm == s[f].rnorm);
+    } else if (!s[f].done) {         // kind 5
+      s[f].rtz1 = sums[f]; s[f].beta = (s[f].iter == 0) ? 0.0 : sums[f] / s[f].rtz2;
     }
   }
 }

@@ -765,16 +765,19 @@ static int persistent_grid(Ctx* c) {
 }
 int pk_pcg_dir_gradt(Ctx* c, int adj) {
   // measured (r1c, cfg 5): persistent gradt 0.198 ms (2 CTAs/SM) vs 0.157 ms one-CTA-per-element (4 CTAs/SM) => opt-in only;
-  // the persistent div (0.191 vs 0.238 ms) is the default
+  // the persistent div (0.191 vs 0.238 ms) is the default.
+  // With a separately applied preconditioner (pc_kind != 0) the kernels read z = M^-1 r in place of r and ones in place of 1/diag(E).
+  const double* zsrc = c->pc_kind ? c->pz : c->pk[0];
+  const double* zscale = c->pc_kind ? c->ones2 : c->dinvE[adj];
   if (c->persistent_pcg && c->persistent_gradt) {
     DISPATCH_N(c, NSB_TRY(set_smem(k_gradt3p<N>, GradtP<N>::smem));
-               k_gradt3p<N><<<persistent_grid(c), PK_TPB, GradtP<N>::smem, c->stream>>>(c->pk[0], c->wk[2], c->RW2, c->dinvE[adj],
+               k_gradt3p<N><<<persistent_grid(c), PK_TPB, GradtP<N>::smem, c->stream>>>(zsrc, c->wk[2], c->RW2, zscale,
                                                                                        c->pk[2], c->cgs + 3, c->n, c->n2, c->nel));
     nsb_count_launch();
     NSB_CUDA(cudaGetLastError());
     return 0;
   }
-  DISPATCH_N(c, k_gradt3<N, 1><<<c->nel, PK_TPB, 0, c->stream>>>(c->pk[0], c->wk[2], c->RW2, c->dinvE[adj], c->pk[2], c->cgs + 3,
+  DISPATCH_N(c, k_gradt3<N, 1><<<c->nel, PK_TPB, 0, c->stream>>>(zsrc, c->wk[2], c->RW2, zscale, c->pk[2], c->cgs + 3,
                                                               c->n, c->n2));
   nsb_count_launch();
   NSB_CUDA(cudaGetLastError());

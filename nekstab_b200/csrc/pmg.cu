@@ -1,0 +1,658 @@
+// pmg.cu -- three-level additive pressure preconditioner for the CG on E = D (mask B~^-1 QQ^T) D^T.
+//
+// The reference solves this system with GMRES preconditioned by Nek5000's hybrid Schwarz multigrid (`preconditioner =
+// semg_xxt`, examples/cylinder/stability/direct/1cyl.par:28; [UPSTREAM] hsmg.f hsmg_solve: element-local fast-
+// diagonalisation solves + a coarse problem on the element-vertex mesh).  The north-star's Jacobi-PCG needs 2-7e3
+// iterations per step on the shipped meshes; a preconditioner of the reference's class changes the iteration count,
+// not the converged pressure.  Here (symmetric positive definite, so CG stays CG):
+//
+//   M^-1 r = sum_e R_e^T Et_e^-1 R_e r     element blocks, Et_e = separable (box) approximation of the element's diagonal
+//                                          block of E, inverted by fast diagonalisation:  (S x S x S) L^-1 (S x S x S)^T
+//          + P  diag(P^T E P)^-1 P^T r     one Jacobi sweep on the Q1 space of the element-vertex mesh
+//          + Pa (Pa^T E Pa)^-1  Pa^T r     piecewise constants on <= 512 element aggregates (recursive coordinate
+//                                          bisection), dense inverse replicated on every GPU and L2-resident
+//
+// Both Galerkin pieces are measured from E itself at setup (probing with a distance-2 colouring of the vertex graph;
+// one E application per aggregate), so boundary conditions, deformation and the adjoint mask set need no special cases.
+// Per CG iteration the preconditioner streams r and z once (2 n2 words + 126 words per element of FDM factors):
+// ~2 % of the bytes of one E application; the coarse levels are three latency-bound launches.
+// CPU restatement: oracle/pmg.py (tests/test_gpu_pmg.py compares M^-1 r, solutions and iteration counts).
+#include <algorithm>
+#include <cmath>
+#include <map>
+#include <numeric>
+
+#include "elem_common.cuh"
+
+static __constant__ double pm_l[2][8];   // Q1 hat functions (1-z)/2, (1+z)/2 at the GL(lx2) points
+
+// ---------------------------------------------------------------------------------------------- device kernels
+template <int D, int L>
+struct PmShape {
+  static constexpr int NP = (D == 3) ? L * L * L : L * L;
+  static constexpr int NK = (D == 3) ? 8 : 4;
+  static constexpr int NPL = (NP + 31) / 32;   // points per lane
+};
+
+template <int D, int L>
+__device__ __forceinline__ double pm_phi(int k, int p) {
+  const int i0 = p % L, i1 = (p / L) % L;
+  double f = pm_l[k & 1][i0] * pm_l[(k >> 1) & 1][i1];
+  if (D == 3) f *= pm_l[(k >> 2) & 1][p / (L * L)];
+  return f;
+}
+
+// rc[e][k] = sum_p phi_k(p) r_e(p); one warp per element, fixed-shape shuffle tree (deterministic)
+template <int D, int L>
+__global__ void __launch_bounds__(256) k_pm_restrict(const double* __restrict__ r, double* __restrict__ rc, int nel,
+                                                     const CGState* skip) {
+  if (skip && skip->done) return;
+  using S = PmShape<D, L>;
+  const int lane = threadIdx.x & 31;
+  const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (e >= nel) return;
+  double acc[S::NK];
+#pragma unroll
+  for (int k = 0; k < S::NK; ++k) acc[k] = 0.0;
+  for (int p = lane; p < S::NP; p += 32) {
+    const double v = r[(long long)e * S::NP + p];
+#pragma unroll
+    for (int k = 0; k < S::NK; ++k) acc[k] = fma(pm_phi<D, L>(k, p), v, acc[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < S::NK; ++k) {
+    double x = acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+    if (lane == 0) rc[(long long)e * S::NK + k] = x;
+  }
+}
+
+// threads [0, nv): xv[v] = d1inv[v] * sum of rc over the (element, corner) entries of vertex v (ascending order);
+// then one warp per local aggregate: ra[first + a] = sum over its elements of sum_k rc[e][k]  (sum_k phi_k = 1)
+__global__ void k_pm_coarse(int nv, const int* __restrict__ voff, const int* __restrict__ vent, const double* __restrict__ d1inv,
+                            const double* __restrict__ rc, double* __restrict__ xv, int nagg_loc, int agg_first,
+                            const int* __restrict__ aoff, const int* __restrict__ aent, int nk, double* __restrict__ ra,
+                            const CGState* skip) {
+  if (skip && skip->done) return;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int vthreads = ((nv + 31) / 32) * 32;
+  if (t < vthreads) {
+    if (t < nv) {
+      double s = 0.0;
+      for (int j = voff[t]; j < voff[t + 1]; ++j) s += rc[vent[j]];
+      xv[t] = d1inv ? d1inv[t] * s : s;
+    }
+    return;
+  }
+  const int a = (t - vthreads) >> 5, lane = t & 31;
+  if (a >= nagg_loc) return;
+  double s = 0.0;
+  for (int j = aoff[a] + lane; j < aoff[a + 1]; j += 32) {
+    const double* q = rc + (long long)aent[j] * nk;
+    double se = 0.0;
+    for (int k = 0; k < nk; ++k) se += q[k];
+    s += se;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if (lane == 0) ra[agg_first + a] = s;
+}
+
+// x2 = A2inv ra  (one warp per row; A2inv is <= 2 MB and stays in L2)
+__global__ void k_pm_gemv(int nagg, const double* __restrict__ A, const double* __restrict__ ra, double* __restrict__ x2,
+                          const CGState* skip) {
+  if (skip && skip->done) return;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= nagg) return;
+  double s = 0.0;
+  for (int j = lane; j < nagg; j += 32) s = fma(A[(long long)row * nagg + j], ra[j], s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if (lane == 0) x2[row] = s;
+}
+
+// out_e = sum_k phi_k xv[vid[e][k]] + x2[agg[e]]   (setup probing only)
+template <int D, int L>
+__global__ void k_pm_prolong(const double* __restrict__ xv, const int* __restrict__ vid, const double* __restrict__ x2,
+                             const int* __restrict__ agg, double* __restrict__ out, int nel) {
+  using S = PmShape<D, L>;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)nel * S::NP) return;
+  const int e = (int)(t / S::NP), p = (int)(t % S::NP);
+  double v = x2 ? x2[agg[e]] : 0.0;
+  if (xv) {
+#pragma unroll
+    for (int k = 0; k < S::NK; ++k) v = fma(pm_phi<D, L>(k, p), xv[vid[e * S::NK + k]], v);
+  }
+  out[t] = v;
+}
+
+// z_e = FDM_e(r_e) + sum_k phi_k xv[vid[e][k]] + x2[agg[e]];  rtz = sum z r  (deterministic two-stage reduction).
+// One warp per element, 8 elements per CTA; tensor stages are warp-synchronous on two shared buffers per warp.
+// mode 0: no CG bookkeeping (operator test); 1: single rank -> the last CTA sets rtz1/beta; 2: multi rank (sum only).
+template <int D, int L>
+__global__ void __launch_bounds__(256) k_pm_apply(const double* __restrict__ r, double* __restrict__ z, int nel,
+                                                  const double* __restrict__ Sg, const double* __restrict__ lamg,
+                                                  const double* __restrict__ xv, const int* __restrict__ vid,
+                                                  const double* __restrict__ x2, const int* __restrict__ agg, CGState* cgs,
+                                                  int mode, double* part, unsigned* counter, double* out) {
+  using S = PmShape<D, L>;
+  constexpr int NP = S::NP, NK = S::NK, NPL = S::NPL, LL = L * L;
+  if (mode && cgs->done) return;
+  __shared__ double sA[8][NP], sB[8][NP], sS[8][D * LL], sL[8][D * L];
+  __shared__ double sred[32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int e = blockIdx.x * 8 + w;
+  double dot[1] = {0.0};
+  if (e < nel) {
+    double rr[NPL];
+#pragma unroll
+    for (int q = 0; q < NPL; ++q) {
+      const int p = lane + 32 * q;
+      rr[q] = (p < NP) ? r[(long long)e * NP + p] : 0.0;
+      if (p < NP) sA[w][p] = rr[q];
+    }
+    for (int i = lane; i < D * LL; i += 32) sS[w][i] = Sg[(long long)e * D * LL + i];
+    if (lane < D * L) sL[w][lane] = lamg[(long long)e * D * L + lane];
+    __syncwarp();
+    double mx = 0.0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      double m = sL[w][d * L];
+#pragma unroll
+      for (int i = 1; i < L; ++i) m = fmax(m, sL[w][d * L + i]);
+      mx += m;
+    }
+    // forward: t(.., i_d, ..) = sum_a S_d[a][i_d] t(.., a, ..)
+    double* in = sA[w];
+    double* ou = sB[w];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const int str = (d == 0) ? 1 : (d == 1 ? L : LL);
+#pragma unroll
+      for (int q = 0; q < NPL; ++q) {
+        const int p = lane + 32 * q;
+        if (p < NP) {
+          const int id = (p / str) % L, base = p - id * str;
+          double s = 0.0;
+#pragma unroll
+          for (int a = 0; a < L; ++a) s = fma(sS[w][d * LL + a * L + id], in[base + a * str], s);
+          if (d == D - 1) {
+            const int i0 = p % L, i1 = (p / L) % L;
+            double den = sL[w][i0] + sL[w][L + i1];
+            if (D == 3) den += sL[w][2 * L + p / LL];
+            s = (den > 1e-12 * mx) ? s / den : 0.0;
+          }
+          ou[p] = s;
+        }
+      }
+      __syncwarp();
+      double* tmp = in; in = ou; ou = tmp;
+    }
+    // backward: t(.., a, ..) = sum_i S_d[a][i] t(.., i, ..)
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const int str = (d == 0) ? 1 : (d == 1 ? L : LL);
+#pragma unroll
+      for (int q = 0; q < NPL; ++q) {
+        const int p = lane + 32 * q;
+        if (p < NP) {
+          const int ia = (p / str) % L, base = p - ia * str;
+          double s = 0.0;
+#pragma unroll
+          for (int i = 0; i < L; ++i) s = fma(sS[w][d * LL + ia * L + i], in[base + i * str], s);
+          ou[p] = s;
+        }
+      }
+      __syncwarp();
+      double* tmp = in; in = ou; ou = tmp;
+    }
+    const double c2 = x2 ? x2[agg[e]] : 0.0;
+    double xk[NK];
+#pragma unroll
+    for (int k = 0; k < NK; ++k) xk[k] = xv ? xv[vid[e * NK + k]] : 0.0;
+#pragma unroll
+    for (int q = 0; q < NPL; ++q) {
+      const int p = lane + 32 * q;
+      if (p < NP) {
+        double v = in[p] + c2;
+#pragma unroll
+        for (int k = 0; k < NK; ++k) v = fma(pm_phi<D, L>(k, p), xk[k], v);
+        z[(long long)e * NP + p] = v;
+        dot[0] = fma(v, rr[q], dot[0]);
+      }
+    }
+  }
+  if (grid_sum_finish<1>(dot, part, counter, out, sred) && mode == 1 && threadIdx.x == 0) {
+    cgs->rtz1 = out[0];
+    cgs->beta = (cgs->iter == 0) ? 0.0 : out[0] / cgs->rtz2;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host helpers
+// symmetric eigen-decomposition by cyclic Jacobi rotations (n <= 8): A = V diag(w) V^T, A destroyed
+static void jacobi_eig(int n, double* A, double* V, double* w) {
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) V[i * n + j] = (i == j) ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    double off = 0.0, dg = 0.0;
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j) (i == j ? dg : off) += A[i * n + j] * A[i * n + j];
+    if (off <= 1e-32 * dg) break;
+    for (int p = 0; p < n - 1; ++p)
+      for (int q = p + 1; q < n; ++q) {
+        const double apq = A[p * n + q];
+        if (apq == 0.0) continue;
+        const double theta = (A[q * n + q] - A[p * n + p]) / (2.0 * apq);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        const double cs = 1.0 / std::sqrt(t * t + 1.0), sn = t * cs;
+        for (int k = 0; k < n; ++k) {
+          const double akp = A[k * n + p], akq = A[k * n + q];
+          A[k * n + p] = cs * akp - sn * akq;
+          A[k * n + q] = sn * akp + cs * akq;
+        }
+        for (int k = 0; k < n; ++k) {
+          const double apk = A[p * n + k], aqk = A[q * n + k];
+          A[p * n + k] = cs * apk - sn * aqk;
+          A[q * n + k] = sn * apk + cs * aqk;
+        }
+        for (int k = 0; k < n; ++k) {
+          const double vkp = V[k * n + p], vkq = V[k * n + q];
+          V[k * n + p] = cs * vkp - sn * vkq;
+          V[k * n + q] = sn * vkp + cs * vkq;
+        }
+      }
+  }
+  for (int i = 0; i < n; ++i) w[i] = A[i * n + i];
+}
+
+// generalised symmetric problem A s = lam M s (M SPD), S^T M S = I; S row-major [a][i] (a nodal, i mode)
+static bool gen_eig(int n, const double* A, const double* M, double* S, double* lam) {
+  double Lc[64], Li[64], C[64], T[64], V[64];
+  for (int i = 0; i < n * n; ++i) Lc[i] = 0.0;
+  for (int j = 0; j < n; ++j) {                         // Cholesky M = Lc Lc^T
+    double d = M[j * n + j];
+    for (int k = 0; k < j; ++k) d -= Lc[j * n + k] * Lc[j * n + k];
+    if (!(d > 0)) return false;
+    Lc[j * n + j] = std::sqrt(d);
+    for (int i = j + 1; i < n; ++i) {
+      double s = M[i * n + j];
+      for (int k = 0; k < j; ++k) s -= Lc[i * n + k] * Lc[j * n + k];
+      Lc[i * n + j] = s / Lc[j * n + j];
+    }
+  }
+  for (int c = 0; c < n; ++c)                           // Li = Lc^-1 (lower triangular)
+    for (int i = 0; i < n; ++i) {
+      double s = (i == c) ? 1.0 : 0.0;
+      for (int k = 0; k < i; ++k) s -= Lc[i * n + k] * Li[k * n + c];
+      Li[i * n + c] = s / Lc[i * n + i];
+    }
+  for (int i = 0; i < n; ++i)                           // T = Li A
+    for (int j = 0; j < n; ++j) {
+      double s = 0.0;
+      for (int k = 0; k < n; ++k) s += Li[i * n + k] * A[k * n + j];
+      T[i * n + j] = s;
+    }
+  for (int i = 0; i < n; ++i)                           // C = T Li^T
+    for (int j = 0; j < n; ++j) {
+      double s = 0.0;
+      for (int k = 0; k < n; ++k) s += T[i * n + k] * Li[j * n + k];
+      C[i * n + j] = s;
+    }
+  for (int i = 0; i < n; ++i)
+    for (int j = i + 1; j < n; ++j) C[i * n + j] = C[j * n + i] = 0.5 * (C[i * n + j] + C[j * n + i]);
+  jacobi_eig(n, C, V, lam);
+  for (int a = 0; a < n; ++a)                           // S = Li^T V
+    for (int i = 0; i < n; ++i) {
+      double s = 0.0;
+      for (int k = 0; k < n; ++k) s += Li[k * n + a] * V[k * n + i];
+      S[a * n + i] = s;
+    }
+  return true;
+}
+
+// dense SPD inverse by Cholesky (n <= 512), in place; false if not positive definite
+static bool spd_inverse(int n, std::vector<double>& A) {
+  std::vector<double> Lc((size_t)n * n, 0.0), Li((size_t)n * n, 0.0);
+  for (int j = 0; j < n; ++j) {
+    double d = A[(size_t)j * n + j];
+    for (int k = 0; k < j; ++k) d -= Lc[(size_t)j * n + k] * Lc[(size_t)j * n + k];
+    if (!(d > 0)) return false;
+    Lc[(size_t)j * n + j] = std::sqrt(d);
+    for (int i = j + 1; i < n; ++i) {
+      double s = A[(size_t)i * n + j];
+      const double *li = &Lc[(size_t)i * n], *lj = &Lc[(size_t)j * n];
+      for (int k = 0; k < j; ++k) s -= li[k] * lj[k];
+      Lc[(size_t)i * n + j] = s / Lc[(size_t)j * n + j];
+    }
+  }
+  // Li = Lc^-1 stored transposed (LiT[c][i] = Li[i][c]) for unit-stride inner loops
+  for (int c = 0; c < n; ++c) {
+    double* col = &Li[(size_t)c * n];
+    for (int i = c; i < n; ++i) {
+      double s = (i == c) ? 1.0 : 0.0;
+      const double* li = &Lc[(size_t)i * n];
+      for (int k = c; k < i; ++k) s -= li[k] * col[k];
+      col[i] = s / li[i];
+    }
+  }
+  for (int i = 0; i < n; ++i)                           // A^-1 = Li^T Li : (i,j) = sum_k Li[k][i] Li[k][j] = sum_k LiT[i][k] LiT[j][k]
+    for (int j = 0; j <= i; ++j) {
+      double s = 0.0;
+      const double *a = &Li[(size_t)i * n], *b = &Li[(size_t)j * n];
+      for (int k = i; k < n; ++k) s += a[k] * b[k];
+      A[(size_t)i * n + j] = A[(size_t)j * n + i] = s;
+    }
+  return true;
+}
+
+// recursive coordinate bisection of element centroids; ties by element index
+static void rcb(const std::vector<double>& cent, int D, std::vector<int>& idx, int lo, int hi, int first, int ng,
+                std::vector<int>& out) {
+  if (ng == 1 || hi - lo <= 1) {
+    for (int i = lo; i < hi; ++i) out[idx[i]] = first;
+    return;
+  }
+  double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+  for (int i = lo; i < hi; ++i)
+    for (int d = 0; d < D; ++d) {
+      mn[d] = std::min(mn[d], cent[(size_t)idx[i] * D + d]);
+      mx[d] = std::max(mx[d], cent[(size_t)idx[i] * D + d]);
+    }
+  int dm = 0;
+  for (int d = 1; d < D; ++d)
+    if (mx[d] - mn[d] > mx[dm] - mn[dm]) dm = d;
+  std::sort(idx.begin() + lo, idx.begin() + hi, [&](int a, int b) {
+    const double ca = cent[(size_t)a * D + dm], cb = cent[(size_t)b * D + dm];
+    return ca != cb ? ca < cb : a < b;
+  });
+  const int nl = ng / 2;
+  const int cut = lo + (int)(((long long)(hi - lo) * nl) / ng);
+  rcb(cent, D, idx, lo, cut, first, nl, out);
+  rcb(cent, D, idx, cut, hi, first + nl, ng - nl, out);
+}
+
+template <class T>
+static int pm_upload(T** dptr, const std::vector<T>& h) {
+  const size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
+  if (*dptr) cudaFree(*dptr);
+  NSB_CUDA(cudaMalloc((void**)dptr, bytes));
+  NSB_CUDA(cudaMemset(*dptr, 0, bytes));
+  if (!h.empty()) NSB_CUDA(cudaMemcpy(*dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+static int pm_download(Ctx* c, std::vector<double>& h, const double* d, long long n) {
+  h.resize(n);
+  NSB_CUDA(cudaStreamSynchronize(c->stream));
+  NSB_CUDA(cudaMemcpy(h.data(), d, n * sizeof(double), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+#define PM_DISPATCH(c, CALL)                                                                                   \
+  do {                                                                                                         \
+    const int key_ = (c)->ldim * 10 + (c)->lx2;                                                                \
+    switch (key_) {                                                                                            \
+      case 22: { constexpr int D = 2, L = 2; CALL; } break;                                                    \
+      case 24: { constexpr int D = 2, L = 4; CALL; } break;                                                    \
+      case 26: { constexpr int D = 2, L = 6; CALL; } break;                                                    \
+      case 32: { constexpr int D = 3, L = 2; CALL; } break;                                                    \
+      case 34: { constexpr int D = 3, L = 4; CALL; } break;                                                    \
+      case 36: { constexpr int D = 3, L = 6; CALL; } break;                                                    \
+      default: nsb_set_error("pmg: unsupported (ldim, lx2) = (%d, %d)", (c)->ldim, (c)->lx2); return 1;        \
+    }                                                                                                          \
+    nsb_count_launch();                                                                                        \
+    NSB_CUDA(cudaGetLastError());                                                                              \
+  } while (0)
+
+void pm_free(PMG& m) {
+  cudaFree(m.S); cudaFree(m.lam); cudaFree(m.vid); cudaFree(m.voff); cudaFree(m.vent); cudaFree(m.d1inv); cudaFree(m.agg);
+  cudaFree(m.aoff); cudaFree(m.aent); cudaFree(m.A2inv); cudaFree(m.rc); cudaFree(m.xv); cudaFree(m.ra); cudaFree(m.x2);
+  m = PMG();
+}
+
+// ---------------------------------------------------------------------------------------------- runtime pieces
+static int pm_restrict(Ctx* c, PMG& m, const double* r, const CGState* skip) {
+  PM_DISPATCH(c, (k_pm_restrict<D, L><<<(c->nel + 7) / 8, 256, 0, c->stream>>>(r, m.rc, c->nel, skip)));
+  return 0;
+}
+static int pm_coarse(Ctx* c, PMG& m, const double* d1inv, const CGState* skip) {
+  const int vthreads = ((m.nv + 31) / 32) * 32;
+  const long long nthr = vthreads + 32LL * m.nagg_loc;
+  k_pm_coarse<<<(int)((nthr + 127) / 128), 128, 0, c->stream>>>(m.nv, m.voff, m.vent, d1inv, m.rc, m.xv, m.nagg_loc, m.agg_first,
+                                                               m.aoff, m.aent, (c->ldim == 3) ? 8 : 4, m.ra, skip);
+  nsb_count_launch();
+  NSB_CUDA(cudaGetLastError());
+  return 0;
+}
+static int pm_gemv(Ctx* c, PMG& m, const CGState* skip) {
+  k_pm_gemv<<<(m.nagg * 32 + 127) / 128, 128, 0, c->stream>>>(m.nagg, m.A2inv, m.ra, m.x2, skip);
+  nsb_count_launch();
+  NSB_CUDA(cudaGetLastError());
+  return 0;
+}
+static int pm_prolong(Ctx* c, PMG& m, const double* xv, const double* x2, double* out) {
+  const long long n = c->n2;
+  PM_DISPATCH(c, (k_pm_prolong<D, L><<<(int)((n + 255) / 256), 256, 0, c->stream>>>(xv, m.vid, x2, m.agg, out, c->nel)));
+  return 0;
+}
+// pout = E pin for mask set `set`; uses wk[2]
+static int pm_apply_E(Ctx* c, int set, const double* pin, double* pout) {
+  NSB_TRY(ek_gradt(c, pin, c->wk[2]));
+  NSB_TRY(gs_dssum(c, c->wk[2], c->ldim, c->n, nullptr));
+  for (int d = 0; d < c->ldim; ++d) NSB_TRY(vk_mul(c, c->wk[2] + d * c->n, c->mbinv[set][d], c->n));
+  NSB_TRY(ek_div(c, c->wk[2], nullptr, pout, 1.0));
+  return 0;
+}
+
+// z = M^-1 r.  mode 0: plain operator; 1: inside the pressure CG (skips when converged, updates rtz1/beta)
+int pm_apply(Ctx* c, int set, const double* r, double* z, int mode) {
+  PMG& m = c->pmg[set];
+  if (!m.ready) { nsb_set_error("pmg: preconditioner not set up"); return 1; }
+  CGState* sp = c->cgs + 3;
+  const CGState* skip = mode ? sp : nullptr;
+  NSB_TRY(pm_restrict(c, m, r, skip));
+  NSB_TRY(pm_coarse(c, m, m.d1inv, skip));
+  if (c->nranks > 1) NSB_TRY(vk_allreduce_sum(c, m.ra, m.nagg));
+  NSB_TRY(pm_gemv(c, m, skip));
+  const int kmode = mode ? (c->nranks == 1 ? 1 : 2) : 0;
+  PM_DISPATCH(c, (k_pm_apply<D, L><<<(c->nel + 7) / 8, 256, 0, c->stream>>>(r, z, c->nel, m.S, m.lam, m.xv, m.vid, m.x2, m.agg, sp,
+                                                                           kmode, c->red_part, c->red_count, c->red_out)));
+  if (mode && c->nranks > 1) NSB_TRY(vk_cg_finalize_multi(c, sp, 1, 5));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- setup
+int pm_setup(Ctx* c, int set, int nagg_req) {
+  PMG& m = c->pmg[set];
+  pm_free(m);
+  const int D = c->ldim, L1 = c->lx1, L2 = c->lx2, nel = c->nel, np1 = c->np1, NK = (D == 3) ? 8 : 4;
+  const int N = L1 - 1, mid = L1 / 2;
+  if (c->nranks > 1) { nsb_set_error("pmg: multi-rank set-up not available in this build"); return 1; }
+  if (c->vglo.size() != (size_t)nel * NK) { nsb_set_error("pmg: vertex ids missing"); return 1; }
+  // ---- host copies of what the FDM factors are built from
+  std::vector<double> X[3], binv, bm1, mk[3];
+  for (int d = 0; d < D; ++d) NSB_TRY(pm_download(c, X[d], c->xyz[d], c->n));
+  NSB_TRY(pm_download(c, binv, c->binv, c->n));
+  NSB_TRY(pm_download(c, bm1, c->bm1, c->n));
+  for (int d = 0; d < D; ++d) NSB_TRY(pm_download(c, mk[d], c->mask[set][d], c->n));
+  // GL points and hat functions
+  double zg[16], wg[16], l01[2][8];
+  sem_zwgl(L2, zg, wg);
+  for (int i = 0; i < L2; ++i) { l01[0][i] = 0.5 * (1.0 - zg[i]); l01[1][i] = 0.5 * (1.0 + zg[i]); }
+  NSB_CUDA(cudaMemcpyToSymbol(pm_l, l01, sizeof(l01)));
+  // BD = diag(w2) D12, BJ = diag(w2) J12  (lx2 x lx1, row-major in ConstMats)
+  std::vector<double> BD(L2 * L1), BJ(L2 * L1);
+  for (int i = 0; i < L2; ++i)
+    for (int l = 0; l < L1; ++l) { BD[i * L1 + l] = c->cm.w2[i] * c->cm.D12[i * L1 + l]; BJ[i * L1 + l] = c->cm.w2[i] * c->cm.J12[i * L1 + l]; }
+  auto node = [&](int e, int i, int j, int k) { return (size_t)e * np1 + (size_t)(k * L1 + j) * L1 + i; };
+  std::vector<double> hS((size_t)nel * D * L2 * L2), hlam((size_t)nel * D * L2), cent((size_t)nel * D);
+  const int str1[3] = {1, L1, L1 * L1};
+  for (int e = 0; e < nel; ++e) {
+    double h[3] = {1, 1, 1};
+    // centroid
+    for (int d = 0; d < D; ++d) {
+      double s = 0.0;
+      for (int p = 0; p < np1; ++p) s += X[d][(size_t)e * np1 + p];
+      cent[(size_t)e * D + d] = s / np1;
+    }
+    for (int dr = 0; dr < D; ++dr) {
+      // face centroids: plain mean over the nodes with index 0 / N along direction dr
+      double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+      int cnt = 0;
+      for (int p = 0; p < np1; ++p) {
+        const int id = (p / str1[dr]) % L1;
+        if (id != 0) continue;
+        ++cnt;
+        for (int d = 0; d < D; ++d) { lo[d] += X[d][(size_t)e * np1 + p]; hi[d] += X[d][(size_t)e * np1 + p + (size_t)N * str1[dr]]; }
+      }
+      double s = 0.0;
+      for (int d = 0; d < D; ++d) s += (hi[d] - lo[d]) * (hi[d] - lo[d]) / ((double)cnt * cnt);
+      h[dr] = std::sqrt(s);
+    }
+    for (int dr = 0; dr < D; ++dr) {
+      int ijk[3] = {mid, mid, D == 3 ? mid : 0};
+      double wi[16];
+      for (int l = 0; l < L1; ++l) wi[l] = 1.0 / c->cm.w1[l];
+      for (int end = 0; end < 2; ++end) {
+        ijk[dr] = end ? N : 0;
+        const size_t g = node(e, ijk[0], ijk[1], ijk[2]);
+        const double ml = 1.0 / (binv[g] * bm1[g]);
+        double kk = 1.0;
+        for (int d = 0; d < D; ++d) kk *= mk[d][g];
+        wi[end ? N : 0] = kk / (c->cm.w1[end ? N : 0] * ml);
+      }
+      double A[64], M[64];
+      for (int i = 0; i < L2; ++i)
+        for (int j = 0; j < L2; ++j) {
+          double sa = 0.0, sm = 0.0;
+          for (int l = 0; l < L1; ++l) {
+            sa += BD[i * L1 + l] * wi[l] * BD[j * L1 + l];
+            sm += BJ[i * L1 + l] * wi[l] * BJ[j * L1 + l];
+          }
+          A[i * L2 + j] = sa; M[i * L2 + j] = sm;
+        }
+      double Sm[64], lm[8];
+      if (!gen_eig(L2, A, M, Sm, lm)) { nsb_set_error("pmg: FDM mass matrix of element %d not positive definite", e); return 1; }
+      double cd = (D == 3) ? 0.5 : 1.0;
+      for (int d = 0; d < D; ++d) cd *= (d == dr) ? 1.0 / h[d] : h[d];
+      for (int i = 0; i < L2 * L2; ++i) hS[((size_t)e * D + dr) * L2 * L2 + i] = Sm[i];
+      for (int i = 0; i < L2; ++i) hlam[((size_t)e * D + dr) * L2 + i] = cd * lm[i];
+    }
+  }
+  NSB_TRY(pm_upload(&m.S, hS));
+  NSB_TRY(pm_upload(&m.lam, hlam));
+  // ---- vertices: local numbering (ascending global id), CSR of (element, corner) entries
+  std::vector<long long> uv(c->vglo);
+  std::sort(uv.begin(), uv.end());
+  uv.erase(std::unique(uv.begin(), uv.end()), uv.end());
+  m.nv = (int)uv.size();
+  std::vector<int> vid((size_t)nel * NK), voff(m.nv + 1, 0), vent((size_t)nel * NK);
+  for (size_t i = 0; i < vid.size(); ++i) {
+    vid[i] = (int)(std::lower_bound(uv.begin(), uv.end(), c->vglo[i]) - uv.begin());
+    voff[vid[i] + 1]++;
+  }
+  for (int v = 0; v < m.nv; ++v) voff[v + 1] += voff[v];
+  {
+    std::vector<int> fill(voff.begin(), voff.end() - 1);
+    for (size_t i = 0; i < vid.size(); ++i) vent[fill[vid[i]]++] = (int)i;
+  }
+  NSB_TRY(pm_upload(&m.vid, vid));
+  NSB_TRY(pm_upload(&m.voff, voff));
+  NSB_TRY(pm_upload(&m.vent, vent));
+  // ---- aggregates (recursive coordinate bisection of the local elements)
+  int nagg = nagg_req > 0 ? nagg_req : std::max(1, nel / 32);
+  nagg = std::max(1, std::min(std::min(nagg, nel), 512 / c->nranks));
+  m.nagg_loc = nagg; m.nagg = nagg; m.agg_first = 0;
+  std::vector<int> agg(nel), idx(nel);
+  std::iota(idx.begin(), idx.end(), 0);
+  rcb(cent, D, idx, 0, nel, 0, nagg, agg);
+  std::vector<int> aoff(nagg + 1, 0), aent(nel);
+  for (int e = 0; e < nel; ++e) aoff[agg[e] + 1]++;
+  for (int a = 0; a < nagg; ++a) aoff[a + 1] += aoff[a];
+  {
+    std::vector<int> fill(aoff.begin(), aoff.end() - 1);
+    for (int e = 0; e < nel; ++e) aent[fill[agg[e]]++] = e;
+  }
+  m.h_agg = agg;
+  for (int e = 0; e < nel; ++e) agg[e] += m.agg_first;
+  NSB_TRY(pm_upload(&m.agg, agg));
+  NSB_TRY(pm_upload(&m.aoff, aoff));
+  NSB_TRY(pm_upload(&m.aent, aent));
+  NSB_TRY(pm_upload(&m.rc, std::vector<double>((size_t)nel * NK, 0.0)));
+  NSB_TRY(pm_upload(&m.xv, std::vector<double>(m.nv, 0.0)));
+  NSB_TRY(pm_upload(&m.ra, std::vector<double>(m.nagg, 0.0)));
+  NSB_TRY(pm_upload(&m.x2, std::vector<double>(m.nagg, 0.0)));
+  // ---- distance-2 colouring of the vertex graph (adjacent = share an element)
+  std::vector<std::vector<int>> adj(m.nv);
+  for (int e = 0; e < nel; ++e)
+    for (int a = 0; a < NK; ++a)
+      for (int b = 0; b < NK; ++b) adj[vid[(size_t)e * NK + a]].push_back(vid[(size_t)e * NK + b]);
+  for (auto& l : adj) { std::sort(l.begin(), l.end()); l.erase(std::unique(l.begin(), l.end()), l.end()); }
+  std::vector<int> col(m.nv, -1), stamp;
+  int ncol = 0;
+  for (int v = 0; v < m.nv; ++v) {
+    stamp.assign(ncol + 1, 0);
+    for (int u : adj[v])
+      for (int t : adj[u])
+        if (col[t] >= 0) stamp[col[t]] = 1;
+    int cc = 0;
+    while (cc < ncol && stamp[cc]) ++cc;
+    col[v] = cc;
+    if (cc == ncol) ++ncol;
+  }
+  m.ncolours = ncol;
+  // ---- diag(P^T E P) by probing, one E application per colour
+  std::vector<double> d1(m.nv, 0.0), xvh(m.nv), rvh;
+  for (int cc = 0; cc < ncol; ++cc) {
+    for (int v = 0; v < m.nv; ++v) xvh[v] = (col[v] == cc) ? 1.0 : 0.0;
+    NSB_CUDA(cudaMemcpyAsync(m.xv, xvh.data(), m.nv * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    NSB_TRY(pm_prolong(c, m, m.xv, nullptr, c->pk[2]));
+    NSB_TRY(pm_apply_E(c, set, c->pk[2], c->pk[3]));
+    NSB_TRY(pm_restrict(c, m, c->pk[3], nullptr));
+    NSB_TRY(pm_coarse(c, m, nullptr, nullptr));
+    NSB_TRY(pm_download(c, rvh, m.xv, m.nv));
+    for (int v = 0; v < m.nv; ++v)
+      if (col[v] == cc) d1[v] = rvh[v];
+  }
+  m.h_d1 = d1;
+  for (int v = 0; v < m.nv; ++v) {
+    if (!(d1[v] > 0)) { nsb_set_error("pmg: non-positive Q1 diagonal %g at vertex %d", d1[v], v); return 1; }
+    d1[v] = 1.0 / d1[v];
+  }
+  NSB_TRY(pm_upload(&m.d1inv, d1));
+  // ---- A2 = Pa^T E Pa by probing, one E application per aggregate
+  std::vector<double> A2((size_t)m.nagg * m.nagg, 0.0), x2h(m.nagg, 0.0), rah;
+  for (int a = 0; a < m.nagg; ++a) {
+    std::fill(x2h.begin(), x2h.end(), 0.0);
+    x2h[a] = 1.0;
+    NSB_CUDA(cudaMemcpyAsync(m.x2, x2h.data(), m.nagg * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    NSB_TRY(pm_prolong(c, m, nullptr, m.x2, c->pk[2]));
+    NSB_TRY(pm_apply_E(c, set, c->pk[2], c->pk[3]));
+    NSB_TRY(pm_restrict(c, m, c->pk[3], nullptr));
+    NSB_TRY(pm_coarse(c, m, nullptr, nullptr));
+    NSB_TRY(pm_download(c, rah, m.ra, m.nagg));
+    for (int b = 0; b < m.nagg; ++b) A2[(size_t)b * m.nagg + a] = rah[b];
+  }
+  double tr = 0.0;
+  for (int a = 0; a < m.nagg; ++a) {
+    tr += A2[(size_t)a * m.nagg + a];
+    for (int b = a + 1; b < m.nagg; ++b)
+      A2[(size_t)a * m.nagg + b] = A2[(size_t)b * m.nagg + a] = 0.5 * (A2[(size_t)a * m.nagg + b] + A2[(size_t)b * m.nagg + a]);
+  }
+  if (c->ifvcor[set]) {        // E 1 = 0  =>  A2 1 = 0: shift the null vector (the CG residual stays orthogonal to 1)
+    const double sh = tr / ((double)m.nagg * m.nagg);
+    for (auto& v : A2) v += sh;
+  }
+  if (c->ifvcor[set] && m.nagg == 1) {
+    A2[0] = 0.0;
+  } else if (!spd_inverse(m.nagg, A2)) {
+    nsb_set_error("pmg: aggregate operator not positive definite");
+    return 1;
+  }
+  m.h_A2inv = A2;
+  NSB_TRY(pm_upload(&m.A2inv, A2));
+  NSB_CUDA(cudaStreamSynchronize(c->stream));
+  m.ready = true;
+  return 0;
+}

@@ -217,8 +217,9 @@ static int proj_post(Ctx* c, int adj) {
   return 0;
 }
 
-// Solve E x = g with Jacobi-PCG, E = D (mask B~^-1 QQ^T) D^T [UPSTREAM navier1.f esolver/cdabdtp; the reference runs
-// GMRES+multigrid here, the north-star prescribes Jacobi-PCG].  In: c->pk[0] = g (destroyed). Out: c->pk[1].
+// Solve E x = g with PCG, E = D (mask B~^-1 QQ^T) D^T [UPSTREAM navier1.f esolver/cdabdtp; the reference runs
+// GMRES+multigrid here, the north-star prescribes Jacobi-PCG].  Preconditioner: Jacobi (pc_kind 0) or the three-level
+// additive Schwarz/multilevel operator of pmg.cu (pc_kind 1).  In: c->pk[0] = g (destroyed). Out: c->pk[1].
 int st_pressure(Ctx* c, int adj, int* iters) {
   CGState* sp = c->cgs + 3;
   if (c->ifvcor[adj]) {   // remove the constant null-space component from the right-hand side [UPSTREAM ortho]
@@ -230,6 +231,8 @@ int st_pressure(Ctx* c, int adj, int* iters) {
   if (proj) NSB_TRY(proj_pre(c, adj));
   NSB_TRY(cg_state_setup(c, 3, 1, c->tol_p, c->vol2, c->maxit_p));
   NSB_TRY(vk_pcg_init(c, adj));
+  const bool pc = c->pc_kind != 0;
+  if (pc) NSB_TRY(pm_apply(c, adj, c->pk[0], c->pz, 1));
   bool done = false;
   int issued = 0;
   Ctx::GraphEntry* ge = graphs_ok(c) ? &c->graph_p[adj] : nullptr;
@@ -246,6 +249,8 @@ int st_pressure(Ctx* c, int adj, int* iters) {
       prof_mark(c, sm, 7);
       NSB_TRY(vk_pcg_update(c, adj));
       prof_mark(c, sm, 8);
+      if (pc) NSB_TRY(pm_apply(c, adj, c->pk[0], c->pz, 1));
+      prof_mark(c, sm, 9);
     }
     return 0;
   };
@@ -255,7 +260,7 @@ int st_pressure(Ctx* c, int adj, int* iters) {
     else NSB_TRY(batch(sample));
     issued += c->check_every_p;
     NSB_TRY(cg_state_poll(c, 3, 1, &done));
-    if (sample) { const int kinds[4] = {0, 1, 2, 3}; prof_collect(c, kinds, 4, 4); }
+    if (sample) { const int kinds[5] = {0, 1, 2, 3, 8}; prof_collect(c, kinds, pc ? 5 : 4, 4); }
     if (issued > c->maxit_p + c->check_every_p) break;
   }
   NSB_TRY(p2p_check_error(c));

@@ -201,15 +201,38 @@ __device__ void cg_finalize_rho(CGState* s, const double* sums, int ncomp) {
       s[f].alpha = s[f].rtz1 / sums[f];
     }
 }
-// kind 0: init (2 sums/comp), 1: update (2 sums/comp), 2: rho (1 sum/comp)
+// variants for a preconditioner applied by separate kernels (pmg.cu): the update kernels only produce the residual norm,
+// z^T r arrives later (kind 5)
+__device__ void pcg_finalize_init_norm(CGState* s, const double* sums) {
+  s->rtz1 = 1.0; s->rtz2 = 1.0; s->beta = 0.0; s->alpha = 0.0;
+  s->rnorm = sqrt(fmax(sums[1], 0.0) / s->vol);
+  s->iter = 0;
+  s->done = (s->rnorm <= s->tol) || (s->maxit <= 0);
+}
+__device__ void pcg_finalize_update_norm(CGState* s, const double* sums) {
+  if (s->done) return;
+  s->rtz2 = s->rtz1;
+  s->rnorm = sqrt(fmax(sums[1], 0.0) / s->vol);
+  s->iter += 1;
+  s->done = (s->rnorm <= s->tol) || (s->iter >= s->maxit) || !(s->rnorm == s->rnorm);
+}
+__device__ void pcg_finalize_rtz(CGState* s, const double* sums) {
+  if (s->done) return;
+  s->rtz1 = sums[0];
+  s->beta = (s->iter == 0) ? 0.0 : sums[0] / s->rtz2;
+}
+// kind 0: init (2 sums/comp), 1: update (2 sums/comp), 2: rho (1 sum/comp), 3/4: init/update without z^T r, 5: z^T r
 __global__ void k_cg_finalize(CGState* s, const double* sums, int ncomp, int kind) {
   if (threadIdx.x || blockIdx.x) return;
   if (kind == 0) hcg_finalize_init(s, sums, ncomp);
   else if (kind == 1) hcg_finalize_update(s, sums, ncomp);
-  else cg_finalize_rho(s, sums, ncomp);
+  else if (kind == 2) cg_finalize_rho(s, sums, ncomp);
+  else if (kind == 3) pcg_finalize_init_norm(s, sums);
+  else if (kind == 4) pcg_finalize_update_norm(s, sums);
+  else pcg_finalize_rtz(s, sums);
 }
 int vk_cg_finalize_multi(Ctx* c, CGState* s, int ncomp, int kind) {   // multi-rank path: allreduce then finalize
-  int cnt = (kind == 2) ? ncomp : 2 * ncomp;
+  int cnt = (kind == 2 || kind == 5) ? ncomp : 2 * ncomp;
   if (kind == 2 && s == c->cgs) cnt = 3;
   if (c->p2p.on) return p2p_allreduce(c, c->red_out, cnt, 0, s, ncomp, kind);   // all-reduce + scalar update in one kernel
   NSB_TRY(vk_allreduce_sum(c, c->red_out, cnt));
@@ -269,8 +292,6 @@ __global__ void k_hcg_update(double* __restrict__ r, double* __restrict__ x, con
   }
   if (grid_sum_finish<6>(v, part, counter, out, sred) && finalize && threadIdx.x == 0) hcg_finalize_update(cgs, out, ncomp);
 }
-int vk_cg_finalize_multi(Ctx* c, CGState* s, int ncomp, int kind);
-
 int vk_hcg_init(Ctx* c, int ncomp) {
   LAUNCH1(k_hcg_init, c->n, c->rk, c->wk[3], c->wk[1], c->dinvH, c->mult, c->binv, c->n, ncomp, c->cgs, c->red_part,
           c->red_count, c->red_out, c->nranks == 1);
@@ -298,7 +319,10 @@ __global__ void k_pcg_init(const double* __restrict__ r, double* __restrict__ x,
     v[0] = fma(rr * rr, dinv[i], v[0]);
     v[1] = fma(rr * rr, bm2inv[i], v[1]);
   }
-  if (grid_sum_finish<2>(v, part, counter, out, sred) && finalize && threadIdx.x == 0) hcg_finalize_init(cgs, out, 1);
+  if (grid_sum_finish<2>(v, part, counter, out, sred) && finalize && threadIdx.x == 0) {
+    if (finalize == 1) hcg_finalize_init(cgs, out, 1);
+    else pcg_finalize_init_norm(cgs, out);
+  }
 }
 __global__ void k_pcg_update(double* __restrict__ r, double* __restrict__ x, const double* __restrict__ p,
                              const double* __restrict__ ep, const double* __restrict__ dinv,
@@ -315,18 +339,25 @@ __global__ void k_pcg_update(double* __restrict__ r, double* __restrict__ x, con
     v[0] = fma(rr * rr, dinv[i], v[0]);
     v[1] = fma(rr * rr, bm2inv[i], v[1]);
   }
-  if (grid_sum_finish<2>(v, part, counter, out, sred) && finalize && threadIdx.x == 0) hcg_finalize_update(cgs, out, 1);
+  if (grid_sum_finish<2>(v, part, counter, out, sred) && finalize && threadIdx.x == 0) {
+    if (finalize == 1) hcg_finalize_update(cgs, out, 1);
+    else pcg_finalize_update_norm(cgs, out);
+  }
 }
+// finalize argument of the two kernels: 0 = multi-rank (scalars updated after the all-reduce), 1 = Jacobi (z^T r fused),
+// 2 = separate preconditioner (norm only; pm_apply delivers z^T r)
 int vk_pcg_init(Ctx* c, int adj) {
+  const int pc = c->pc_kind != 0;
   LAUNCH1(k_pcg_init, c->n2, c->pk[0], c->pk[1], c->pk[2], c->dinvE[adj], c->bm2inv, c->n2, c->cgs + 3, c->red_part,
-          c->red_count, c->red_out, c->nranks == 1);
-  if (c->nranks > 1) NSB_TRY(vk_cg_finalize_multi(c, c->cgs + 3, 1, 0));
+          c->red_count, c->red_out, c->nranks == 1 ? 1 + pc : 0);
+  if (c->nranks > 1) NSB_TRY(vk_cg_finalize_multi(c, c->cgs + 3, 1, pc ? 3 : 0));
   return 0;
 }
 int vk_pcg_update(Ctx* c, int adj) {
+  const int pc = c->pc_kind != 0;
   LAUNCH1(k_pcg_update, c->n2, c->pk[0], c->pk[1], c->pk[2], c->pk[3], c->dinvE[adj], c->bm2inv, c->n2, c->cgs + 3,
-          c->red_part, c->red_count, c->red_out, c->nranks == 1);
-  if (c->nranks > 1) NSB_TRY(vk_cg_finalize_multi(c, c->cgs + 3, 1, 1));
+          c->red_part, c->red_count, c->red_out, c->nranks == 1 ? 1 + pc : 0);
+  if (c->nranks > 1) NSB_TRY(vk_cg_finalize_multi(c, c->cgs + 3, 1, pc ? 4 : 1));
   return 0;
 }
 

@@ -64,6 +64,9 @@ _SIGS = {
     "nsb_set_timestep": [C.c_double, C.c_int],
     "nsb_set_ifvcor": [C.c_int, C.c_int],
     "nsb_set_projection": [C.c_int],
+    "nsb_set_pressure_preconditioner": [C.c_int, C.c_int],
+    "nsb_op_pc_apply": [C.c_int, _dp, _dp],
+    "nsb_pc_get": [C.c_int, _dp, _lp],
     "nsb_set_adjoint_masks": [_dp] * 3,
     "nsb_vec_alloc": [C.c_int],
     "nsb_vec_upload": [C.c_int] + [_dp] * 4,
@@ -212,6 +215,22 @@ class NekStabB200:
         _ck(self.lib.nsb_prepare_linearized_solver(end_time, cfl_target, C.byref(dt), C.byref(ns), C.byref(ct)))
         return dt.value, ns.value, ct.value
 
+    def set_pressure_preconditioner(self, kind, nagg=0):
+        """0: Jacobi (north-star); 1: FDM element blocks + Q1 vertex-mesh Jacobi + aggregate coarse solve (csrc/pmg.cu)."""
+        _ck(self.lib.nsb_set_pressure_preconditioner(int(kind), int(nagg)))
+
+    def op_pc_apply(self, r, adjoint=False):
+        r = _arr(r).ravel(); z = np.empty(self.n2)
+        _ck(self.lib.nsb_op_pc_apply(int(adjoint), _p(r), _p(z)))
+        return z
+
+    def pc_get(self, which):
+        cnt = C.c_longlong(0)
+        _ck(self.lib.nsb_pc_get(which, None, C.byref(cnt)))
+        out = np.zeros(cnt.value)
+        _ck(self.lib.nsb_pc_get(which, _p(out), C.byref(cnt)))
+        return out
+
     def set_projection(self, mxprev):
         _ck(self.lib.nsb_set_projection(int(mxprev)))
 
@@ -230,10 +249,11 @@ class NekStabB200:
         _ck(self.lib.nsb_get_stats(C.byref(s), int(reset)))
         return {k: getattr(s, k) for k, _ in Stats._fields_}
 
-    PROFILE_KINDS = ["pcg_gradt", "dssum", "pcg_div", "pcg_update", "hcg_axhelm", "hcg_update", "advab", "hcg_dssum"]
+    PROFILE_KINDS = ["pcg_gradt", "dssum", "pcg_div", "pcg_update", "hcg_axhelm", "hcg_update", "advab", "hcg_dssum",
+                     "pcg_precond"]
 
     def profile(self, enable=-1):
-        ms = np.zeros(8); cnt = np.zeros(8, dtype=np.int64)
+        ms = np.zeros(12); cnt = np.zeros(12, dtype=np.int64)
         _ck(self.lib.nsb_profile(enable, _p(ms), _p(cnt)))
         return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.PROFILE_KINDS)}
 

@@ -156,9 +156,9 @@ int nsb_op_hmholtz(double* ux, double* uy, double* uz, const double* rx, const d
 int nsb_op_esolver(const double* g, double* phi, int* iters);
 /* z = M^-1 r, the preconditioner selected with nsb_set_pressure_preconditioner(1, ..), on mesh-2 arrays */
 int nsb_op_pc_apply(int adjoint, const double* r, double* z);
-/* set-up data of that preconditioner (direct mask set) as doubles: which 0: aggregate of every element [nelv];
+/* set-up data of that preconditioner (direct mask set) as doubles: which 0: local aggregate of every element [nelv];
  * 1: diag(P^T E P) per local vertex (ascending global corner id); 2: (Pa^T E Pa)^-1 [nagg*nagg];
- * 3: {vertices, aggregates, colours used for probing, local aggregates} */
+ * 3: {local vertices, aggregates (all ranks), colours used for probing, local aggregates, first global aggregate id} */
 int nsb_pc_get(int which, double* out, long long* count);
 int nsb_op_cfl(const double* ux, const double* uy, const double* uz, double dt, double* cfl);
 /* named geometry arrays for parity checks: "bm1","binvm1","jacm1","g1".."g6","bm2","ediag","hdiagA","vmult" */

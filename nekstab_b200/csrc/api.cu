@@ -260,7 +260,7 @@ extern "C" int nsb_set_adjoint_masks(const double* m0, const double* m1, const d
     c->dinvE[1] = c->dinvE[0];
     c->ifvcor[1] = c->ifvcor[0];
     c->mask_same[1] = c->mask_same[0];
-    if (c->pc_kind) NSB_TRY(pm_setup(c, 1, c->pc_nagg));
+    pm_free(c->pmg[1]);
     return 0;
   }
   for (int d = 0; d < 3; ++d) { c->mask[1][d] = nullptr; c->mbinv[1][d] = nullptr; }
@@ -340,13 +340,13 @@ extern "C" int nsb_set_pressure_preconditioner(int kind, int nagg) {
   }
   c->pc_nagg = nagg;
   NSB_TRY(pm_setup(c, 0, nagg));
-  NSB_TRY(pm_setup(c, 1, nagg));     // the adjoint mask set has its own E (identical factors when the masks coincide)
+  if (c->has_adj_masks) NSB_TRY(pm_setup(c, 1, nagg));     // separate adjoint masks => a different E => its own factors
   c->pc_kind = 1;
   return 0;
 }
 extern "C" int nsb_op_pc_apply(int adjoint, const double* r, double* z) {
   REQUIRE_CTX();
-  if (!c->pz || !c->pmg[adjoint ? 1 : 0].ready) { nsb_set_error("nsb_op_pc_apply: call nsb_set_pressure_preconditioner(1, ..) first"); return 1; }
+  if (!c->pz || !c->pmg[0].ready) { nsb_set_error("nsb_op_pc_apply: call nsb_set_pressure_preconditioner(1, ..) first"); return 1; }
   NSB_TRY(h2d(c, c->pk[3], r, c->n2));
   NSB_TRY(pm_apply(c, adjoint ? 1 : 0, c->pk[3], c->pz, 0));
   return d2h(c, z, c->pz, c->n2);
@@ -360,7 +360,7 @@ extern "C" int nsb_pc_get(int which, double* out, long long* count) {
     case 0: n = (long long)m.h_agg.size(); if (out) for (long long i = 0; i < n; ++i) out[i] = m.h_agg[i]; break;
     case 1: n = (long long)m.h_d1.size(); if (out) for (long long i = 0; i < n; ++i) out[i] = m.h_d1[i]; break;
     case 2: n = (long long)m.h_A2inv.size(); if (out) for (long long i = 0; i < n; ++i) out[i] = m.h_A2inv[i]; break;
-    case 3: n = 4; if (out) { out[0] = m.nv; out[1] = m.nagg; out[2] = m.ncolours; out[3] = m.nagg_loc; } break;
+    case 3: n = 5; if (out) { out[0] = m.nv; out[1] = m.nagg; out[2] = m.ncolours; out[3] = m.nagg_loc; out[4] = m.agg_first; } break;
     default: nsb_set_error("nsb_pc_get: bad selector %d", which); return 1;
   }
   if (count) *count = n;

@@ -13,9 +13,6 @@
 
 #include "nsb_internal.h"
 
-static int* d_send_base = nullptr;   // [nshared]
-static int* d_send_cnt = nullptr;    // [nshared]
-static int* d_rseg_cnt = nullptr;    // parallel to rseg_pos
 
 template <int NF>
 __global__ void k_gs_pack(int nshared, const int* __restrict__ send_seg, const int* __restrict__ send_base,
@@ -92,16 +89,18 @@ static int upload(T** dptr, const std::vector<T>& h) {
   return 0;
 }
 
-int gs_free(Ctx* c) {
-  GSMap& m = c->gs;
-  p2p_free(c);
+int gs_free_map(Ctx* c, GSMap& m, P2P& p) {
+  p2p_free(c, p);
   cudaFree(m.seg_off); cudaFree(m.seg_idx); cudaFree(m.send_seg); cudaFree(m.rseg_off); cudaFree(m.rseg_pos);
   cudaFree(m.rseg_nbefore); cudaFree(m.sendbuf); cudaFree(m.recvbuf);
-  cudaFree(d_send_base); cudaFree(d_send_cnt); cudaFree(d_rseg_cnt);
+  cudaFree(m.send_base); cudaFree(m.send_cnt); cudaFree(m.rseg_cnt);
   cudaFree(m.surf_pts); cudaFree(m.nb_off); cudaFree(m.nb_idx);
-  d_send_base = d_send_cnt = d_rseg_cnt = nullptr;
   m = GSMap();
   return 0;
+}
+int gs_free(Ctx* c) {
+  gs_free_map(c, c->gsv, c->p2pv);
+  return gs_free_map(c, c->gs, c->p2p);
 }
 
 // ------------------------------------------------------------------------------------------------ host-side plan
@@ -237,16 +236,18 @@ extern "C" int nsb_gs_host_get(int which, int* out) {
   return 0;
 }
 
-int gs_setup(Ctx* c, const long long* glo) {
-  GSMap& m = c->gs;
-  const long long n = c->n;
+int gs_setup(Ctx* c, const long long* glo) { return gs_build(c, c->gs, c->p2p, c->n, c->lx1, c->np1, glo, true); }
+
+// Build a gather-scatter map over `n` local dofs with global ids `glo` (np dofs per element on an N^ldim grid): the
+// velocity mesh (N = lx1) or the element-vertex mesh of the pressure preconditioner (N = 2).
+int gs_build(Ctx* c, GSMap& m, P2P& p2p, long long n, int N1, int np_e, const long long* glo, bool gather_table) {
   if (n >= (1LL << 31)) { nsb_set_error("gs_setup: more than 2^31 local dofs"); return 1; }
   HostPlan P;
   plan_sort(P, n, glo);
   std::vector<long long> cnts(c->nranks, 0), all;
   if (c->nranks > 1) {
     std::vector<long long> cand;
-    plan_candidates(P, c->lx1, c->ldim, c->np1, cand);
+    plan_candidates(P, N1, c->ldim, np_e, cand);
     // allgather counts then ids (padded) through NCCL
     long long mycnt = (long long)cand.size();
     long long* d_cnt = nullptr;
@@ -278,8 +279,8 @@ int gs_setup(Ctx* c, const long long* glo) {
   const std::vector<int>&order = P.order, &ustart = P.ustart;
   const int nu = (int)P.uid.size();
   // ---- per-element gather table (fused direct-stiffness sum; single rank only: no halo entries)
-  if (c->nranks == 1) {
-    const int N = c->lx1, D = c->ldim, np = c->np1;
+  if (c->nranks == 1 && gather_table) {
+    const int N = N1, D = c->ldim, np = np_e;
     std::vector<int> surf;
     for (int p = 0; p < np; ++p)
       if (is_surface(p, N, D)) surf.push_back(p);
@@ -309,11 +310,11 @@ int gs_setup(Ctx* c, const long long* glo) {
   NSB_TRY(upload(&m.seg_off, P.seg_off));
   NSB_TRY(upload(&m.seg_idx, P.seg_idx));
   NSB_TRY(upload(&m.send_seg, P.send_seg));
-  NSB_TRY(upload(&d_send_base, P.send_base));
-  NSB_TRY(upload(&d_send_cnt, P.send_cnt));
+  NSB_TRY(upload(&m.send_base, P.send_base));
+  NSB_TRY(upload(&m.send_cnt, P.send_cnt));
   NSB_TRY(upload(&m.rseg_off, P.rseg_off));
   NSB_TRY(upload(&m.rseg_pos, P.rseg_pos));
-  NSB_TRY(upload(&d_rseg_cnt, P.rseg_cnt));
+  NSB_TRY(upload(&m.rseg_cnt, P.rseg_cnt));
   NSB_TRY(upload(&m.rseg_nbefore, P.nbefore));
   size_t hb = std::max<size_t>((size_t)3 * m.nshared, 1) * sizeof(double);
   NSB_CUDA(cudaMalloc(&m.sendbuf, hb));
@@ -324,18 +325,17 @@ int gs_setup(Ctx* c, const long long* glo) {
     std::vector<int> send_nbr, send_j;
     for (int i = 0; i < m.nnbr; ++i)
       for (int j = 0; j < m.nbr_off[i + 1] - m.nbr_off[i]; ++j) { send_nbr.push_back(i); send_j.push_back(j); }
-    NSB_TRY(p2p_setup(c, send_nbr, send_j));
+    NSB_TRY(p2p_setup(c, p2p, m, send_nbr, send_j));
   }
   return 0;
 }
 
 template <int NF>
-static int dssum_nf(Ctx* c, double* u, long long stride, const CGState* skip) {
-  GSMap& m = c->gs;
+static int dssum_nf(Ctx* c, GSMap& m, P2P& p2p, double* u, long long stride, const CGState* skip) {
   const int T = 128;
-  if (c->p2p.on) return p2p_dssum(c, u, NF, stride, skip, m.send_seg, d_rseg_cnt);
+  if (p2p.on) return p2p_dssum(c, p2p, m, u, NF, stride, skip);
   if (m.nshared > 0) {
-    k_gs_pack<NF><<<(m.nshared + T - 1) / T, T, 0, c->stream>>>(m.nshared, m.send_seg, d_send_base, d_send_cnt, m.seg_off,
+    k_gs_pack<NF><<<(m.nshared + T - 1) / T, T, 0, c->stream>>>(m.nshared, m.send_seg, m.send_base, m.send_cnt, m.seg_off,
                                                                m.seg_idx, u, stride, m.sendbuf, skip);
     nsb_count_launch();
     NSB_NCCL(ncclGroupStart());
@@ -347,7 +347,7 @@ static int dssum_nf(Ctx* c, double* u, long long stride, const CGState* skip) {
     NSB_NCCL(ncclGroupEnd());
     if (m.nseg > 0) {
       k_gs_sum<NF, true><<<(m.nseg + T - 1) / T, T, 0, c->stream>>>(m.nseg, m.seg_off, m.seg_idx, m.rseg_off, m.rseg_pos,
-                                                                   d_rseg_cnt, m.rseg_nbefore, m.recvbuf, u, stride, skip);
+                                                                   m.rseg_cnt, m.rseg_nbefore, m.recvbuf, u, stride, skip);
       nsb_count_launch();
     }
   } else if (m.nseg > 0) {
@@ -359,12 +359,15 @@ static int dssum_nf(Ctx* c, double* u, long long stride, const CGState* skip) {
   return 0;
 }
 
-int gs_dssum(Ctx* c, double* u, int nfields, long long stride, const CGState* skip) {
+int gs_dssum_map(Ctx* c, GSMap& m, P2P& p2p, double* u, int nfields, long long stride, const CGState* skip) {
   switch (nfields) {
-    case 1: return dssum_nf<1>(c, u, stride, skip);
-    case 2: return dssum_nf<2>(c, u, stride, skip);
-    case 3: return dssum_nf<3>(c, u, stride, skip);
+    case 1: return dssum_nf<1>(c, m, p2p, u, stride, skip);
+    case 2: return dssum_nf<2>(c, m, p2p, u, stride, skip);
+    case 3: return dssum_nf<3>(c, m, p2p, u, stride, skip);
   }
   nsb_set_error("gs_dssum: nfields must be 1..3");
   return 1;
+}
+int gs_dssum(Ctx* c, double* u, int nfields, long long stride, const CGState* skip) {
+  return gs_dssum_map(c, c->gs, c->p2p, u, nfields, stride, skip);
 }

@@ -68,6 +68,9 @@ struct GSMap {
   int* rseg_off = nullptr;   // [nseg+1] into rseg_pos: recv-buffer positions contributing to a segment
   int* rseg_pos = nullptr;
   int* rseg_nbefore = nullptr;  // [nseg] how many of those come from lower ranks (summed before the local part)
+  int* send_base = nullptr;  // [nshared] position of every send entry inside the (NCCL) send buffer
+  int* send_cnt = nullptr;   // [nshared] entries of its neighbour block (field stride)
+  int* rseg_cnt = nullptr;   // parallel to rseg_pos
   double* sendbuf = nullptr; // [3*nshared]
   double* recvbuf = nullptr;
   // per-element gather table for kernels that fuse the direct-stiffness sum into their load phase (single rank):
@@ -157,6 +160,11 @@ struct Ctx {
   bool ifvcor[2] = {false, false};
   GSMap gs;
   P2P p2p;
+  GSMap gsv;                 // gather-scatter over the element-vertex mesh (pressure preconditioner, multi-rank)
+  P2P p2pv;                  // its own peer-memory halo channel
+  bool gsv_ready = false;
+  std::vector<int> pc_col;   // distance-2 colouring of the local vertices (consistent across ranks), reused by both mask sets
+  int pc_ncol = 0;
 
   // parameters
   double visc = 1.0, rho = 1.0, tol_v = 1e-9, tol_p = 1e-7;
@@ -238,11 +246,14 @@ void sem_build_constmats(int lx1, int lx2, int lxd, ConstMats* cm);
 int gs_setup(Ctx* c, const long long* glo_num);
 int gs_free(Ctx* c);
 int gs_dssum(Ctx* c, double* u, int nfields, long long stride, const CGState* skip_if_done = nullptr);
+int gs_build(Ctx* c, GSMap& m, P2P& p2p, long long n, int N1, int np_e, const long long* glo, bool gather_table);
+int gs_dssum_map(Ctx* c, GSMap& m, P2P& p2p, double* u, int nfields, long long stride, const CGState* skip_if_done);
+int gs_free_map(Ctx* c, GSMap& m, P2P& p);
 
 // ---- NVLink peer-memory collectives (p2p.cu)
-int p2p_setup(Ctx* c, const std::vector<int>& send_nbr, const std::vector<int>& send_j);
-int p2p_free(Ctx* c);
-int p2p_dssum(Ctx* c, double* u, int nfields, long long stride, const CGState* skip, const int* d_send_seg, const int* d_rseg_cnt);
+int p2p_setup(Ctx* c, P2P& p, const GSMap& m, const std::vector<int>& send_nbr, const std::vector<int>& send_j);
+int p2p_free(Ctx* c, P2P& p);
+int p2p_dssum(Ctx* c, P2P& p, GSMap& m, double* u, int nfields, long long stride, const CGState* skip);
 int p2p_allreduce(Ctx* c, double* dev, int count, int op, CGState* cgs, int ncomp, int kind);
 int p2p_check_error(Ctx* c);
 

@@ -46,8 +46,7 @@ static inline long long off_redflag(int parity, int rank, int nranks) { return 2
 static inline long long off_haloflag(int parity, int rank, int nranks) { return 2LL * nranks * RSLOT + 2LL * nranks + (long long)parity * nranks + rank; }
 static inline long long off_halo(int nranks) { return 2LL * nranks * RSLOT + 4LL * nranks; }
 
-int p2p_free(Ctx* c) {
-  P2P& p = c->p2p;
+int p2p_free(Ctx* c, P2P& p) {
   if (!p.on) return 0;
   for (int r = 0; r < c->nranks; ++r)
     if (r != c->rank && p.peer[r]) cudaIpcCloseMemHandle(p.peer[r]);
@@ -58,11 +57,9 @@ int p2p_free(Ctx* c) {
 }
 
 // called at the end of gs_setup (multi-rank); send_nbr/send_j: neighbour index and position of every send entry
-int p2p_setup(Ctx* c, const std::vector<int>& send_nbr, const std::vector<int>& send_j) {
-  P2P& p = c->p2p;
+int p2p_setup(Ctx* c, P2P& p, const GSMap& m, const std::vector<int>& send_nbr, const std::vector<int>& send_j) {
   const char* env = getenv("NSB_P2P");
   if (c->nranks <= 1 || c->nranks > 16 || (env && env[0] == '0')) return 0;
-  const GSMap& m = c->gs;
   const int R = c->nranks;
   // every peer must be reachable
   for (int r = 0; r < R; ++r) {
@@ -236,9 +233,9 @@ __global__ void k_gs_sum_p2p(int nseg, const int* __restrict__ seg_off, const in
 }
 
 template <int NF>
-static int dssum_p2p_nf(Ctx* c, double* u, long long stride, const CGState* skip, const int* d_send_seg, const int* d_rseg_cnt) {
-  P2P& p = c->p2p;
-  GSMap& m = c->gs;
+static int dssum_p2p_nf(Ctx* c, P2P& p, GSMap& m, double* u, long long stride, const CGState* skip) {
+  const int* d_send_seg = m.send_seg;
+  const int* d_rseg_cnt = m.rseg_cnt;
   const int T = 128, R = c->nranks;
   const unsigned long long epoch = ++p.epoch_halo;
   const int par = (int)(epoch & 1);
@@ -259,11 +256,11 @@ static int dssum_p2p_nf(Ctx* c, double* u, long long stride, const CGState* skip
   NSB_CUDA(cudaGetLastError());
   return 0;
 }
-int p2p_dssum(Ctx* c, double* u, int nfields, long long stride, const CGState* skip, const int* d_send_seg, const int* d_rseg_cnt) {
+int p2p_dssum(Ctx* c, P2P& p, GSMap& m, double* u, int nfields, long long stride, const CGState* skip) {
   switch (nfields) {
-    case 1: return dssum_p2p_nf<1>(c, u, stride, skip, d_send_seg, d_rseg_cnt);
-    case 2: return dssum_p2p_nf<2>(c, u, stride, skip, d_send_seg, d_rseg_cnt);
-    case 3: return dssum_p2p_nf<3>(c, u, stride, skip, d_send_seg, d_rseg_cnt);
+    case 1: return dssum_p2p_nf<1>(c, p, m, u, stride, skip);
+    case 2: return dssum_p2p_nf<2>(c, p, m, u, stride, skip);
+    case 3: return dssum_p2p_nf<3>(c, p, m, u, stride, skip);
   }
   return 1;
 }
@@ -356,9 +353,11 @@ int p2p_allreduce(Ctx* c, double* dev, int count, int op, CGState* cgs, int ncom
 }
 
 int p2p_check_error(Ctx* c) {
-  if (!c->p2p.on) return 0;
-  int e[4] = {0, 0, 0, 0};
-  NSB_CUDA(cudaMemcpy(e, c->p2p.d_err, sizeof(e), cudaMemcpyDeviceToHost));
-  if (e[0]) { nsb_set_error("peer-memory collective timed out (a rank stopped participating)"); return 3; }
+  for (P2P* p : {&c->p2p, &c->p2pv}) {
+    if (!p->on) continue;
+    int e[4] = {0, 0, 0, 0};
+    NSB_CUDA(cudaMemcpy(e, p->d_err, sizeof(e), cudaMemcpyDeviceToHost));
+    if (e[0]) { nsb_set_error("peer-memory collective timed out (a rank stopped participating)"); return 3; }
+  }
   return 0;
 }

@@ -70,21 +70,27 @@ __global__ void __launch_bounds__(256) k_pm_restrict(const double* __restrict__ 
 
 // threads [0, nv): xv[v] = d1inv[v] * sum of rc over the (element, corner) entries of vertex v (ascending order);
 // then one warp per local aggregate: ra[first + a] = sum over its elements of sum_k rc[e][k]  (sum_k phi_k = 1)
+// vmode 0: sum the entries (single rank); 1: the entries were already assembled across ranks by the vertex gather-scatter
+// (every copy holds the total): take the first; 2: skip the vertex part.  Entries of ra owned by other ranks are zeroed
+// (they are filled by the all-reduce that follows).
 __global__ void k_pm_coarse(int nv, const int* __restrict__ voff, const int* __restrict__ vent, const double* __restrict__ d1inv,
-                            const double* __restrict__ rc, double* __restrict__ xv, int nagg_loc, int agg_first,
+                            const double* __restrict__ rc, double* __restrict__ xv, int nagg, int nagg_loc, int agg_first,
                             const int* __restrict__ aoff, const int* __restrict__ aent, int nk, double* __restrict__ ra,
-                            const CGState* skip) {
+                            int vmode, int amode, const CGState* skip) {
   if (skip && skip->done) return;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int vthreads = ((nv + 31) / 32) * 32;
+  const int vthreads = ((max(nv, nagg) + 31) / 32) * 32;
   if (t < vthreads) {
-    if (t < nv) {
+    if (t < nv && vmode != 2) {
       double s = 0.0;
-      for (int j = voff[t]; j < voff[t + 1]; ++j) s += rc[vent[j]];
+      if (vmode == 0) for (int j = voff[t]; j < voff[t + 1]; ++j) s += rc[vent[j]];
+      else s = rc[vent[voff[t]]];
       xv[t] = d1inv ? d1inv[t] * s : s;
     }
+    if (amode && t < nagg && (t < agg_first || t >= agg_first + nagg_loc)) ra[t] = 0.0;
     return;
   }
+  if (!amode) return;
   const int a = (t - vthreads) >> 5, lane = t & 31;
   if (a >= nagg_loc) return;
   double s = 0.0;
@@ -416,14 +422,22 @@ static int pm_restrict(Ctx* c, PMG& m, const double* r, const CGState* skip) {
   PM_DISPATCH(c, (k_pm_restrict<D, L><<<(c->nel + 7) / 8, 256, 0, c->stream>>>(r, m.rc, c->nel, skip)));
   return 0;
 }
-static int pm_coarse(Ctx* c, PMG& m, const double* d1inv, const CGState* skip) {
-  const int vthreads = ((m.nv + 31) / 32) * 32;
+static int pm_coarse(Ctx* c, PMG& m, const double* d1inv, int vmode, int amode, const CGState* skip) {
+  const int vthreads = ((std::max(m.nv, m.nagg) + 31) / 32) * 32;
   const long long nthr = vthreads + 32LL * m.nagg_loc;
-  k_pm_coarse<<<(int)((nthr + 127) / 128), 128, 0, c->stream>>>(m.nv, m.voff, m.vent, d1inv, m.rc, m.xv, m.nagg_loc, m.agg_first,
-                                                               m.aoff, m.aent, (c->ldim == 3) ? 8 : 4, m.ra, skip);
+  k_pm_coarse<<<(int)((nthr + 127) / 128), 128, 0, c->stream>>>(m.nv, m.voff, m.vent, d1inv, m.rc, m.xv, m.nagg, m.nagg_loc,
+                                                               m.agg_first, m.aoff, m.aent, (c->ldim == 3) ? 8 : 4, m.ra, vmode,
+                                                               amode, skip);
   nsb_count_launch();
   NSB_CUDA(cudaGetLastError());
   return 0;
+}
+// vertex values xv = d1inv * (sum over all copies on all ranks) and aggregate sums ra (local entries) from the corner sums rc
+static int pm_coarse_levels(Ctx* c, PMG& m, const double* d1inv, const CGState* skip) {
+  if (c->nranks == 1) return pm_coarse(c, m, d1inv, 0, 1, skip);
+  NSB_TRY(pm_coarse(c, m, nullptr, 2, 1, skip));                                    // aggregate sums need the un-assembled rc
+  NSB_TRY(gs_dssum_map(c, c->gsv, c->p2pv, m.rc, 1, 0, skip));                      // vertex sums across elements and ranks
+  return pm_coarse(c, m, d1inv, 1, 0, skip);
 }
 static int pm_gemv(Ctx* c, PMG& m, const CGState* skip) {
   k_pm_gemv<<<(m.nagg * 32 + 127) / 128, 128, 0, c->stream>>>(m.nagg, m.A2inv, m.ra, m.x2, skip);
@@ -447,12 +461,12 @@ static int pm_apply_E(Ctx* c, int set, const double* pin, double* pout) {
 
 // z = M^-1 r.  mode 0: plain operator; 1: inside the pressure CG (skips when converged, updates rtz1/beta)
 int pm_apply(Ctx* c, int set, const double* r, double* z, int mode) {
-  PMG& m = c->pmg[set];
+  PMG& m = c->pmg[(set && c->has_adj_masks) ? 1 : 0];      // without separate adjoint masks both problems share one E
   if (!m.ready) { nsb_set_error("pmg: preconditioner not set up"); return 1; }
   CGState* sp = c->cgs + 3;
   const CGState* skip = mode ? sp : nullptr;
   NSB_TRY(pm_restrict(c, m, r, skip));
-  NSB_TRY(pm_coarse(c, m, m.d1inv, skip));
+  NSB_TRY(pm_coarse_levels(c, m, m.d1inv, skip));
   if (c->nranks > 1) NSB_TRY(vk_allreduce_sum(c, m.ra, m.nagg));
   NSB_TRY(pm_gemv(c, m, skip));
   const int kmode = mode ? (c->nranks == 1 ? 1 : 2) : 0;
@@ -462,13 +476,44 @@ int pm_apply(Ctx* c, int set, const double* r, double* z, int mode) {
   return 0;
 }
 
+// all ranks' corner-id lists, concatenated in rank order (NCCL all-gather of counts, then of padded data)
+static int pm_allgather_ids(Ctx* c, const std::vector<long long>& mine, std::vector<long long>& all) {
+  const int R = c->nranks;
+  std::vector<long long> cnts(R, 0);
+  long long mycnt = (long long)mine.size();
+  long long* d_cnt = nullptr;
+  NSB_CUDA(cudaMalloc(&d_cnt, sizeof(long long) * (R + 1)));
+  NSB_CUDA(cudaMemcpy(d_cnt + R, &mycnt, sizeof(long long), cudaMemcpyHostToDevice));
+  NSB_NCCL(ncclAllGather(d_cnt + R, d_cnt, 1, ncclInt64, c->comm, c->stream));
+  NSB_CUDA(cudaStreamSynchronize(c->stream));
+  NSB_CUDA(cudaMemcpy(cnts.data(), d_cnt, sizeof(long long) * R, cudaMemcpyDeviceToHost));
+  cudaFree(d_cnt);
+  const long long mx = std::max<long long>(1, *std::max_element(cnts.begin(), cnts.end()));
+  long long *d_my = nullptr, *d_all = nullptr;
+  NSB_CUDA(cudaMalloc(&d_my, sizeof(long long) * mx));
+  NSB_CUDA(cudaMalloc(&d_all, sizeof(long long) * mx * R));
+  NSB_CUDA(cudaMemset(d_my, 0, sizeof(long long) * mx));
+  NSB_CUDA(cudaMemcpy(d_my, mine.data(), sizeof(long long) * mine.size(), cudaMemcpyHostToDevice));
+  NSB_NCCL(ncclAllGather(d_my, d_all, mx, ncclInt64, c->comm, c->stream));
+  NSB_CUDA(cudaStreamSynchronize(c->stream));
+  std::vector<long long> padded((size_t)mx * R);
+  NSB_CUDA(cudaMemcpy(padded.data(), d_all, sizeof(long long) * padded.size(), cudaMemcpyDeviceToHost));
+  cudaFree(d_my); cudaFree(d_all);
+  all.clear();
+  for (int r = 0; r < R; ++r) all.insert(all.end(), padded.begin() + (size_t)r * mx, padded.begin() + (size_t)r * mx + cnts[r]);
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------- setup
 int pm_setup(Ctx* c, int set, int nagg_req) {
   PMG& m = c->pmg[set];
   pm_free(m);
   const int D = c->ldim, L1 = c->lx1, L2 = c->lx2, nel = c->nel, np1 = c->np1, NK = (D == 3) ? 8 : 4;
   const int N = L1 - 1, mid = L1 / 2;
-  if (c->nranks > 1) { nsb_set_error("pmg: multi-rank set-up not available in this build"); return 1; }
+  if (c->nranks > 1 && !c->gsv_ready) {    // gather-scatter over the element-vertex mesh: entries (e, corner), 2^ldim per element
+    NSB_TRY(gs_build(c, c->gsv, c->p2pv, (long long)nel * NK, 2, NK, c->vglo.data(), false));
+    c->gsv_ready = true;
+  }
   if (c->vglo.size() != (size_t)nel * NK) { nsb_set_error("pmg: vertex ids missing"); return 1; }
   // ---- host copies of what the FDM factors are built from
   std::vector<double> X[3], binv, bm1, mk[3];
@@ -561,9 +606,18 @@ int pm_setup(Ctx* c, int set, int nagg_req) {
   NSB_TRY(pm_upload(&m.voff, voff));
   NSB_TRY(pm_upload(&m.vent, vent));
   // ---- aggregates (recursive coordinate bisection of the local elements)
-  int nagg = nagg_req > 0 ? nagg_req : std::max(1, nel / 32);
+  int nagg = nagg_req > 0 ? std::max(1, nagg_req / c->nranks) : std::max(1, nel / 32);
   nagg = std::max(1, std::min(std::min(nagg, nel), 512 / c->nranks));
   m.nagg_loc = nagg; m.nagg = nagg; m.agg_first = 0;
+  if (c->nranks > 1) {      // global aggregate ids: rank-ordered blocks
+    std::vector<double> cnt(c->nranks, 0.0);
+    cnt[c->rank] = nagg;
+    NSB_CUDA(cudaMemcpyAsync(c->hbuf, cnt.data(), c->nranks * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    NSB_TRY(vk_allreduce_sum(c, c->hbuf, c->nranks));
+    NSB_TRY(pm_download(c, cnt, c->hbuf, c->nranks));
+    m.nagg = 0;
+    for (int r = 0; r < c->nranks; ++r) { if (r == c->rank) m.agg_first = m.nagg; m.nagg += (int)std::lround(cnt[r]); }
+  }
   std::vector<int> agg(nel), idx(nel);
   std::iota(idx.begin(), idx.end(), 0);
   rcb(cent, D, idx, 0, nel, 0, nagg, agg);
@@ -583,23 +637,41 @@ int pm_setup(Ctx* c, int set, int nagg_req) {
   NSB_TRY(pm_upload(&m.xv, std::vector<double>(m.nv, 0.0)));
   NSB_TRY(pm_upload(&m.ra, std::vector<double>(m.nagg, 0.0)));
   NSB_TRY(pm_upload(&m.x2, std::vector<double>(m.nagg, 0.0)));
-  // ---- distance-2 colouring of the vertex graph (adjacent = share an element)
-  std::vector<std::vector<int>> adj(m.nv);
-  for (int e = 0; e < nel; ++e)
-    for (int a = 0; a < NK; ++a)
-      for (int b = 0; b < NK; ++b) adj[vid[(size_t)e * NK + a]].push_back(vid[(size_t)e * NK + b]);
-  for (auto& l : adj) { std::sort(l.begin(), l.end()); l.erase(std::unique(l.begin(), l.end()), l.end()); }
-  std::vector<int> col(m.nv, -1), stamp;
+  // ---- distance-2 colouring of the GLOBAL vertex graph (adjacent = share an element): every rank gathers the corner ids
+  //      of all elements and runs the same greedy colouring, so that the probing below is consistent across ranks
+  std::vector<int> col(m.nv);
   int ncol = 0;
-  for (int v = 0; v < m.nv; ++v) {
+  if (c->pc_ncol > 0 && (int)c->pc_col.size() == m.nv) {
+    col = c->pc_col; ncol = c->pc_ncol;           // same mesh, other mask set: reuse
+  } else {
+  std::vector<long long> gv;                      // corner ids of all elements of all ranks
+  if (c->nranks == 1) gv = c->vglo;
+  else NSB_TRY(pm_allgather_ids(c, c->vglo, gv));
+  std::vector<long long> guv(gv);
+  std::sort(guv.begin(), guv.end());
+  guv.erase(std::unique(guv.begin(), guv.end()), guv.end());
+  const int gnv = (int)guv.size();
+  const size_t gnel = gv.size() / NK;
+  std::vector<int> gvid(gv.size());
+  for (size_t i = 0; i < gv.size(); ++i) gvid[i] = (int)(std::lower_bound(guv.begin(), guv.end(), gv[i]) - guv.begin());
+  std::vector<std::vector<int>> adj(gnv);
+  for (size_t e = 0; e < gnel; ++e)
+    for (int a = 0; a < NK; ++a)
+      for (int b = 0; b < NK; ++b) adj[gvid[e * NK + a]].push_back(gvid[e * NK + b]);
+  for (auto& l : adj) { std::sort(l.begin(), l.end()); l.erase(std::unique(l.begin(), l.end()), l.end()); }
+  std::vector<int> gcol(gnv, -1), stamp;
+  for (int v = 0; v < gnv; ++v) {
     stamp.assign(ncol + 1, 0);
     for (int u : adj[v])
       for (int t : adj[u])
-        if (col[t] >= 0) stamp[col[t]] = 1;
+        if (gcol[t] >= 0) stamp[gcol[t]] = 1;
     int cc = 0;
     while (cc < ncol && stamp[cc]) ++cc;
-    col[v] = cc;
+    gcol[v] = cc;
     if (cc == ncol) ++ncol;
+  }
+  for (int v = 0; v < m.nv; ++v) col[v] = gcol[(int)(std::lower_bound(guv.begin(), guv.end(), uv[v]) - guv.begin())];
+  c->pc_col = col; c->pc_ncol = ncol;
   }
   m.ncolours = ncol;
   // ---- diag(P^T E P) by probing, one E application per colour
@@ -610,7 +682,7 @@ int pm_setup(Ctx* c, int set, int nagg_req) {
     NSB_TRY(pm_prolong(c, m, m.xv, nullptr, c->pk[2]));
     NSB_TRY(pm_apply_E(c, set, c->pk[2], c->pk[3]));
     NSB_TRY(pm_restrict(c, m, c->pk[3], nullptr));
-    NSB_TRY(pm_coarse(c, m, nullptr, nullptr));
+    NSB_TRY(pm_coarse_levels(c, m, nullptr, nullptr));
     NSB_TRY(pm_download(c, rvh, m.xv, m.nv));
     for (int v = 0; v < m.nv; ++v)
       if (col[v] == cc) d1[v] = rvh[v];
@@ -630,9 +702,17 @@ int pm_setup(Ctx* c, int set, int nagg_req) {
     NSB_TRY(pm_prolong(c, m, nullptr, m.x2, c->pk[2]));
     NSB_TRY(pm_apply_E(c, set, c->pk[2], c->pk[3]));
     NSB_TRY(pm_restrict(c, m, c->pk[3], nullptr));
-    NSB_TRY(pm_coarse(c, m, nullptr, nullptr));
+    NSB_TRY(pm_coarse(c, m, nullptr, 2, 1, nullptr));
     NSB_TRY(pm_download(c, rah, m.ra, m.nagg));
-    for (int b = 0; b < m.nagg; ++b) A2[(size_t)b * m.nagg + a] = rah[b];
+    for (int b = 0; b < m.nagg; ++b) A2[(size_t)b * m.nagg + a] = rah[b];      // rows of other ranks' aggregates are zero here
+  }
+  if (c->nranks > 1) {      // sum the row blocks of all ranks
+    double* dA = nullptr;
+    NSB_CUDA(cudaMalloc(&dA, A2.size() * sizeof(double)));
+    NSB_CUDA(cudaMemcpy(dA, A2.data(), A2.size() * sizeof(double), cudaMemcpyHostToDevice));
+    NSB_TRY(vk_allreduce_sum(c, dA, (int)A2.size()));
+    NSB_TRY(pm_download(c, A2, dA, (long long)A2.size()));
+    cudaFree(dA);
   }
   double tr = 0.0;
   for (int a = 0; a < m.nagg; ++a) {

@@ -73,6 +73,37 @@ def main():
         refip = float(sum(np.sum(v0[k] ** 2 * bm1s) for k in range(d)))
         if abs(ip - refip) > 1e-11 * refip:
             failures.append((name, "inner_product", abs(ip - refip)))
+        # ---- pressure preconditioner (csrc/pmg.cu) across ranks: vertex sums over the peer-memory halo channel, aggregate
+        #      sums over the all-reduce; compared with the oracle on the GLOBAL mesh using the gathered aggregate map
+        from oracle import pmg
+        g.set_pressure_preconditioner(1, 2 * world)
+        info = g.pc_get(3)
+        mine = (sel, g.pc_get(0).astype(np.int64) + int(info[4]))
+        allagg = [None] * world
+        dist.all_gather_object(allagg, mine)
+        agg = np.zeros(gc.nel, dtype=np.int64)
+        for se, ag in allagg:
+            agg[se] = ag
+        M = pmg.PMG(s, agg=agg, ifvcor=bool(gc.ifvcor))
+        r = np.random.default_rng(8).standard_normal(s.eshape2)
+        if gc.ifvcor:
+            r -= r.mean()
+        check("pmg_apply", g.op_pc_apply(r.reshape(gc.nel, -1)[sel]), M.apply(r).reshape(gc.nel, -1)[sel], 1e-10)
+        gg = -s.opdiv(smooth_field(gc, 11).reshape((d,) + s.eshape))
+        g.set_params(1.0 / gc.re, 1.0, 1e-13, 1e-12, 2000, 50000)
+        phi1, it1 = g.op_esolver(gg.reshape(gc.nel, -1)[sel])
+        g.set_pressure_preconditioner(0)
+        phi0, it0 = g.op_esolver(gg.reshape(gc.nel, -1)[sel])
+        check("pmg_esolver", phi1, phi0, 1e-7)
+        if not it1 < it0:
+            failures.append((name, "pmg_iterations", (it1, it0)))
+        g.set_pressure_preconditioner(1, 2 * world)
+        g.set_params(1.0 / gc.re, 1.0, 1e-13, 1e-13, 3000, 100000)
+        for mode, adj in ((lib.DIRECT, False), (lib.ADJOINT, True)):
+            g.matvec(mode, 0, 1)
+            v, pp = g.vec_download(1)
+            vo, po = st.linearized_map(v0, p0, nsteps, dt, adjoint=adj)
+            check(f"pmg_matvec{mode}", v, vo.reshape(d, gc.nel, -1)[:, sel], 1e-10)
         g.close()
     t = torch.tensor([len(failures)])
     dist.all_reduce(t)

@@ -28,7 +28,7 @@ def ctx(request):
 
 def test_setup_data(ctx):
     c, s, g, M = ctx
-    nv, nagg, ncol, _ = g.pc_get(3)
+    nv, nagg, ncol, _, _ = g.pc_get(3)
     assert int(nv) == M.nv and int(nagg) == M.nagg and ncol >= 1
     agg = g.pc_get(0).astype(int)
     assert agg.min() == 0 and agg.max() == M.nagg - 1 and np.bincount(agg).min() >= 1     # a partition into non-empty groups

@@ -40,7 +40,11 @@ WORDS = {
     "dssum": 3 * 2 * FS + 0.5 * FS,                  # surface values R+W for 3 fields + int32 index
     "pcg_div": 3.0 + 1.0 + (9 + 1 + 1) * R2,         # read 3 fields + mask*binv; 9 metrics + pdir read, Ep write (mesh 2)
     "pcg_update": 8 * R2,                            # x,p,r,Ep,dinvE,bm2inv read; x,r write
-    "pcg_precond": (2 + 1 + 126.0 / 216.0) * R2,     # r read twice (restrict, apply), z write, 126 words of FDM factors per element
+    # three-level preconditioner (csrc/pmg.cu): restriction reads r; the element-block kernel reads r and 126 words of FDM
+    # factors per element (216 points) and writes z; the vertex/aggregate levels move O(nel) words (latency-bound launches)
+    "pcg_pc_restrict": 1.0 * R2,
+    "pcg_pc_coarse": 0.0,
+    "pcg_pc_apply": (2 + 126.0 / 216.0) * R2,
     # Helmholtz-CG iteration pieces (3 components batched)
     "hcg_axhelm": 3 * (1 + 1 + 1 + 1) + 6 + 1 + 1,   # per comp r,p read, p,w write; 6 G + bm1 + dinv once
     "hcg_dssum": 3 * 2 * FS + 0.5 * FS,
@@ -112,17 +116,18 @@ def hbm_peak():
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference arm
-def workload_iters():
+def workload_iters(precond="jacobi"):
     try:
         with open(ITERS_FILE) as f:
             d = json.load(f)
+        d = d.get(precond, d)
         return int(d["pres_iters_per_step"]), int(d["helm_iters_per_comp_per_step"])
     except Exception:
-        return 2500, 12
+        return (2500, 22) if precond == "jacobi" else (141, 22)
 
 
-def cpu_reference(nsteps: int, nwarm: int, max_seconds: float = 240.0):
-    """Times the CPU oracle port (oracle/stepper.py, Jacobi-PCG mode = the algorithm the GPU path runs) on a
+def cpu_reference(nsteps: int, nwarm: int, max_seconds: float = 240.0, precond: str = "jacobi"):
+    """Times the CPU oracle port (oracle/stepper.py, PCG mode = the algorithm the GPU path runs, same preconditioner) on a
     bounded sample of the workload: a compact patch of the same lx1=8 3-D mesh, each step forced to the
     per-step Helmholtz / pressure iteration counts measured on the GPU for the full workload
     (profiles/workload_iters.json), so the work per grid point per step matches.  Returns DOF*steps/s."""
@@ -144,8 +149,13 @@ def cpu_reference(nsteps: int, nwarm: int, max_seconds: float = 240.0):
     sub.extra = {}
     c3 = cases.extrude(sub, 2, 2 * np.pi / 5.0)
     s = SEM(3, 8, c3.xyz, c3.glo, c3.mask)
-    ip, iv = workload_iters()
-    st = LinearizedStepper(s, c3.ubase, c3.re, None, tol_v=0.0, tol_p=0.0, solver="pcg", max_iter_v=iv, max_iter_p=ip, ifvcor=False)
+    ip, iv = workload_iters(precond)
+    pc = None
+    if precond == "pmg":
+        from oracle.pmg import PMG
+        pc = PMG(s, nagg=max(1, c3.nel // 32))
+    st = LinearizedStepper(s, c3.ubase, c3.re, None, tol_v=0.0, tol_p=0.0, solver="pcg", max_iter_v=iv, max_iter_p=ip, ifvcor=False,
+                           pressure_precond=pc)
     v = cases.add_noise(c3).reshape((3,) + s.eshape)
     p = np.zeros(s.eshape2)
     dt = 0.5 / s.cfl_sum(c3.ubase.reshape((3,) + s.eshape))
@@ -164,7 +174,8 @@ def cpu_reference(nsteps: int, nwarm: int, max_seconds: float = 240.0):
     value = c3.n / tstep
     sample = (f"{c3.nel} hexahedra (48-element patch of the cylinder mesh x 2 layers, lx1=8, n={c3.n}); "
               f"{len(t_steps)} timed step(s) after {min(nwarm, done - len(t_steps))} warm-up, each forced to {ip} pressure-CG and "
-              f"{iv} Helmholtz-CG iterations/component (the full workload's GPU-measured per-step counts); numpy/scipy oracle port")
+              f"{iv} Helmholtz-CG iterations/component (the full workload's GPU-measured per-step counts, preconditioner: {precond}); "
+              f"numpy/scipy oracle port")
     return value, tstep, thr, sample, c3.n
 
 
@@ -178,7 +189,7 @@ def main():
     ap.add_argument("--small", action="store_true", help="tiny 3-layer mesh (debugging only; not a valid bench line)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tol", type=float, default=1e-8)
-    ap.add_argument("--precond", default=os.environ.get("NSB_BENCH_PRECOND", "jacobi"), choices=["jacobi", "pmg"],
+    ap.add_argument("--precond", default=os.environ.get("NSB_BENCH_PRECOND", "pmg"), choices=["jacobi", "pmg"],
                     help="pressure-CG preconditioner: jacobi (north-star) or pmg (FDM element blocks + vertex-mesh Jacobi + "
                          "aggregate coarse solve, csrc/pmg.cu: the reference's class of preconditioner)")
     ap.add_argument("--nagg", type=int, default=0)
@@ -194,12 +205,13 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        value, tstep, thr, sample, nsamp = cpu_reference(K, W)
+        value, tstep, thr, sample, nsamp = cpu_reference(K, W, precond=args.precond)
         line = {"impl": "reference", "metric": "linearized-NS DOF*timesteps/s", "value": value, "unit": "DOF*steps/s",
                 "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": tstep * 1e3, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": f"cyl3d_1996x{10 * args.gpus}_lx8 (bounded sample)", "lx1": 8, "lxd": 12, "lx2": 6,
-                           "pressure_solver": "Jacobi-PCG", "sample_points": nsamp},
+                           "pressure_solver": "Jacobi-PCG" if args.precond == "jacobi" else "PCG + three-level additive preconditioner",
+                           "sample_points": nsamp},
                 "cpu_baseline": {"value": value, "unit": "DOF*steps/s", "cores": thr, "kind": "port", "sample": sample},
                 "e2e": {"value": value, "unit": "DOF*steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
@@ -257,6 +269,9 @@ def main():
     ctx.set_timestep(dt, K)
     ctx.stats(reset=True)
     ctx.profile(1)
+    use_cuda_profiler = os.environ.get("NSB_CUDA_PROFILER") == "1"    # ncu --profile-from-start off: capture the timed call only
+    if use_cuda_profiler:
+        torch.cuda.profiler.start()
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
@@ -264,6 +279,8 @@ def main():
     ctx.matvec(lib.DIRECT, 1, 2)
     barrier()
     wall = time.perf_counter() - t0
+    if use_cuda_profiler:
+        torch.cuda.profiler.stop()
     sampler.stop_flag = True
     st = ctx.stats()
     prof = ctx.profile(0)
@@ -290,14 +307,15 @@ def main():
         kern = {}
         for kname, (ms, cnt) in prof.items():
             wkey = kname if kname in WORDS else None
-            if cnt > 0 and wkey:
+            if cnt > 0 and wkey and WORDS[wkey] > 0:
                 t = ms / cnt * 1e-3
                 gbs = WORDS[wkey] * 8.0 * n_loc / t / 1e9
                 kern[kname] = {"avg_ms": ms / cnt, "samples": cnt, "alg_GBs": gbs, "frac": gbs / peak}
             elif cnt > 0:
                 kern[kname] = {"avg_ms": ms / cnt, "samples": cnt}
-        pc = [k for k in ("pcg_gradt", "dssum", "pcg_div", "pcg_update", "pcg_precond") if k in kern]
-        dom = max(pc, key=lambda k: kern[k]["avg_ms"]) if pc else None
+        pc = [k for k in ("pcg_gradt", "dssum", "pcg_div", "pcg_update", "pcg_pc_restrict", "pcg_pc_coarse", "pcg_pc_apply") if k in kern]
+        cands = [k for k in pc if "frac" in kern[k]]
+        dom = max(cands, key=lambda k: kern[k]["avg_ms"]) if cands else None
         iter_ms = sum(kern[k]["avg_ms"] for k in pc) if pc else None
         iter_words = sum(WORDS.get(k, 0.0) for k in pc) if pc else None
         roof = None
@@ -327,12 +345,13 @@ def main():
             os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
             try:     # measured counts go to scratch; the committed profiles/workload_iters.json is updated by hand
                 with open(os.path.join(ROOT, "gpurun_out", "workload_iters.json"), "w") as f:
-                    json.dump({"pres_iters_per_step": int(round(st["pres_iters"] / K)),
-                               "helm_iters_per_comp_per_step": int(round(st["helm_iters"] / K / 3)), "tol": args.tol, "steps": K}, f)
+                    json.dump({args.precond: {"pres_iters_per_step": int(round(st["pres_iters"] / K)),
+                                              "helm_iters_per_comp_per_step": int(round(st["helm_iters"] / K / 3)), "tol": args.tol,
+                                              "steps": K}}, f)
             except Exception:
                 pass
         if world == 1 and not args.no_cpu_baseline:
-            cv, ct, thr, sample, _ = cpu_reference(1, 0, max_seconds=60.0)
+            cv, ct, thr, sample, _ = cpu_reference(1, 0, max_seconds=60.0, precond=args.precond)
             line["cpu_baseline"] = {"value": cv, "unit": "DOF*steps/s", "cores": thr, "kind": "port", "sample": sample}
         print(json.dumps(line))
     ctx.close()

@@ -134,8 +134,8 @@ int nsb_get_stats(nsb_stats* out, int reset);
 /* Sampling kernel profiler (CUDA events on the launching stream around single launches, one sample set per host
  * poll of a CG loop).  enable: 1 start (clears), 0 stop (clears), -1 just read.  Arrays of 12: accumulated ms and
  * sample count per kind: 0 pressure-CG gradt, 1 dssum (ldim fields), 2 pressure-CG div, 3 pressure-CG vector update,
- * 4 Helmholtz-CG axhelm, 5 Helmholtz-CG vector update, 6 advection, 7 Helmholtz dssum, 8 pressure preconditioner
- * (all its launches), 9-11 unused. */
+ * 4 Helmholtz-CG axhelm, 5 Helmholtz-CG vector update, 6 advection, 7 Helmholtz dssum, 8-10 pressure preconditioner
+ * (8 restriction to the element corners, 9 vertex / aggregate levels, 10 element blocks + prolongation + z.r), 11 unused. */
 int nsb_profile(int enable, double* ms_sum, long long* count);
 
 /* ------------------------------------------------------------------ operator-level entry points

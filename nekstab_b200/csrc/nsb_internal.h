@@ -318,7 +318,7 @@ int vk_rotate(Ctx* c, int k, int first_slot, const double* S_dev, int lds);
 
 // ---- pressure preconditioner (pmg.cu)
 int pm_setup(Ctx* c, int set, int nagg_req);
-int pm_apply(Ctx* c, int set, const double* r, double* z, int mode);
+int pm_apply(Ctx* c, int set, const double* r, double* z, int mode, int prof_slot = 0);
 void pm_free(PMG& m);
 int vk_cg_finalize_multi(Ctx* c, CGState* s, int ncomp, int kind);
 

@@ -48,23 +48,31 @@ __global__ void __launch_bounds__(256) k_pm_restrict(const double* __restrict__ 
                                                      const CGState* skip) {
   if (skip && skip->done) return;
   using S = PmShape<D, L>;
+  __shared__ double sphi[S::NK * S::NP];           // hat functions at the element's points (the constant bank serialises
+  for (int t = threadIdx.x; t < S::NK * S::NP; t += blockDim.x) sphi[t] = pm_phi<D, L>(t / S::NP, t % S::NP);   // lane-varying indices)
+  __syncthreads();
   const int lane = threadIdx.x & 31;
-  const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (e >= nel) return;
-  double acc[S::NK];
+  const int wpb = blockDim.x >> 5;
+  for (int e = blockIdx.x * wpb + (threadIdx.x >> 5); e < nel; e += gridDim.x * wpb) {
+    double acc[S::NK];
 #pragma unroll
-  for (int k = 0; k < S::NK; ++k) acc[k] = 0.0;
-  for (int p = lane; p < S::NP; p += 32) {
-    const double v = r[(long long)e * S::NP + p];
+    for (int k = 0; k < S::NK; ++k) acc[k] = 0.0;
 #pragma unroll
-    for (int k = 0; k < S::NK; ++k) acc[k] = fma(pm_phi<D, L>(k, p), v, acc[k]);
-  }
+    for (int q = 0; q < S::NPL; ++q) {
+      const int p = lane + 32 * q;
+      if (p < S::NP) {
+        const double v = r[(long long)e * S::NP + p];
 #pragma unroll
-  for (int k = 0; k < S::NK; ++k) {
-    double x = acc[k];
+        for (int k = 0; k < S::NK; ++k) acc[k] = fma(sphi[k * S::NP + p], v, acc[k]);
+      }
+    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
-    if (lane == 0) rc[(long long)e * S::NK + k] = x;
+    for (int k = 0; k < S::NK; ++k) {
+      double x = acc[k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+      if (lane == 0) rc[(long long)e * S::NK + k] = x;
+    }
   }
 }
 
@@ -229,6 +237,152 @@ __global__ void __launch_bounds__(256) k_pm_apply(const double* __restrict__ r, 
         dot[0] = fma(v, rr[q], dot[0]);
       }
     }
+  }
+  if (grid_sum_finish<1>(dot, part, counter, out, sred) && mode == 1 && threadIdx.x == 0) {
+    cgs->rtz1 = out[0];
+    cgs->beta = (cgs->iter == 0) ? 0.0 : out[0] / cgs->rtz2;
+  }
+}
+
+// Second-generation element-block kernel (default): the CTA holds EPB elements in shared memory and every thread owns one
+// COLUMN of one element per tensor stage (L loads, L*L DFMAs against rows of the element's S read as 128-bit broadcasts,
+// L stores) -- ncu on the first generation (one warp per element, one point per lane and stage) showed the shared-memory
+// pipe as the limiter (12 LDS per 6 DFMA) and the Q1 hat functions served from the constant bank with lane-varying indices.
+// Rows are padded to an odd length so that column accesses along every axis stay at the 64-bit minimum of 2 wavefronts.
+template <int D, int L>
+struct Pm2 {
+  static constexpr int NCOL = (D == 3) ? L * L : L;
+  static constexpr int EPB = (D == 3) ? (L == 6 ? 8 : (L == 4 ? 16 : 32)) : 32;
+  static constexpr int NT = EPB * NCOL;
+  static constexpr int PI = (L % 2 == 0) ? L + 1 : L;
+  static constexpr int ESZ = (D == 3) ? L * L * PI : L * PI;
+  static constexpr int NP = (D == 3) ? L * L * L : L * L;
+  static constexpr int NK = (D == 3) ? 8 : 4;
+};
+
+template <int D, int L>
+__global__ void __launch_bounds__(Pm2<D, L>::NT) k_pm_apply2(const double* __restrict__ r, double* __restrict__ z, int nel,
+                                                            const double* __restrict__ Sg, const double* __restrict__ lamg,
+                                                            const double* __restrict__ xv, const int* __restrict__ vid,
+                                                            const double* __restrict__ x2, const int* __restrict__ agg,
+                                                            CGState* cgs, int mode, double* part, unsigned* counter, double* out) {
+  using P = Pm2<D, L>;
+  constexpr int NP = P::NP, NK = P::NK, LL = L * L, PI = P::PI, ESZ = P::ESZ, EPB = P::EPB, NT = P::NT, NCOL = P::NCOL;
+  if (mode && cgs->done) return;
+  __shared__ __align__(16) double sS[EPB * D * LL];
+  __shared__ double sA[EPB * ESZ], sB[EPB * ESZ], sL[EPB * D * L], sX[EPB * (NK + 2)], sl1[8], sred[32];
+  const int tid = threadIdx.x;
+  const int e0 = blockIdx.x * EPB;
+  const int ne = min(EPB, nel - e0);
+  // ---- load phase (coalesced): residual -> sA (padded rows), FDM factors, corner values, aggregate value
+  for (int t = tid; t < ne * NP; t += NT) {
+    const int el = t / NP, p = t - el * NP;
+    sA[el * ESZ + (p / L) * PI + (p % L)] = r[(long long)e0 * NP + t];
+  }
+  for (int t = tid; t < ne * D * LL; t += NT) sS[t] = Sg[(long long)e0 * D * LL + t];
+  for (int t = tid; t < ne * D * L; t += NT) sL[t] = lamg[(long long)e0 * D * L + t];
+  for (int t = tid; t < ne * NK; t += NT) {
+    const int el = t / NK, k = t - el * NK;
+    sX[el * (NK + 2) + k] = xv ? xv[vid[(long long)(e0 + el) * NK + k]] : 0.0;
+  }
+  if (tid < ne) sX[tid * (NK + 2) + NK] = x2 ? x2[agg[e0 + tid]] : 0.0;
+  if (tid < L) sl1[tid] = pm_l[1][tid];
+  __syncthreads();
+  if (tid < ne) {                                   // threshold scale of the element: sum_d max_i lam_d[i]
+    double mx = 0.0;
+    for (int d = 0; d < D; ++d) {
+      double m = sL[(tid * D + d) * L];
+      for (int i = 1; i < L; ++i) m = fmax(m, sL[(tid * D + d) * L + i]);
+      mx += m;
+    }
+    sX[tid * (NK + 2) + NK + 1] = mx;
+  }
+  __syncthreads();
+  const int el = tid / NCOL, c = tid - el * NCOL;
+  const bool act = el < ne;
+  double* in = sA + el * ESZ;
+  double* ou = sB + el * ESZ;
+  const int ca = c % L, cb = c / L;                 // the two (3-D) or one (2-D: cb = 0) indices that label the column
+#pragma unroll
+  for (int pass = 0; pass < 2 * D; ++pass) {
+    const int d = (pass < D) ? pass : (2 * D - 1 - pass);      // forward 0..D-1, backward D-1..0 (the operators commute)
+    const bool fwd = pass < D;
+    if (act) {
+      int base, str;
+      if (D == 3) {
+        if (d == 0) { base = (cb * L + ca) * PI; str = 1; }
+        else if (d == 1) { base = cb * L * PI + ca; str = PI; }
+        else { base = cb * PI + ca; str = L * PI; }
+      } else {
+        if (d == 0) { base = c * PI; str = 1; }
+        else { base = c; str = PI; }
+      }
+      const double* Sd = sS + (el * D + d) * LL;
+      double v[L], o[L];
+#pragma unroll
+      for (int a = 0; a < L; ++a) v[a] = in[base + a * str];
+      if (fwd) {
+#pragma unroll
+        for (int i = 0; i < L; ++i) o[i] = 0.0;
+#pragma unroll
+        for (int a = 0; a < L; ++a) {
+          const double2* row = reinterpret_cast<const double2*>(Sd + a * L);
+#pragma unroll
+          for (int i2 = 0; i2 < L / 2; ++i2) {
+            const double2 s2 = row[i2];
+            o[2 * i2] = fma(s2.x, v[a], o[2 * i2]);
+            o[2 * i2 + 1] = fma(s2.y, v[a], o[2 * i2 + 1]);
+          }
+        }
+        if (d == D - 1) {                           // all axes are modal now: divide by the eigenvalue sum
+          const double* lam = sL + el * D * L;
+          const double mx = sX[el * (NK + 2) + NK + 1];
+          const double l01 = (D == 3) ? lam[ca] + lam[L + cb] : lam[c];
+#pragma unroll
+          for (int i = 0; i < L; ++i) {
+            const double den = l01 + lam[(D - 1) * L + i];
+            o[i] = (den > 1e-12 * mx) ? o[i] / den : 0.0;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int a = 0; a < L; ++a) {
+          const double2* row = reinterpret_cast<const double2*>(Sd + a * L);
+          double sacc = 0.0;
+#pragma unroll
+          for (int i2 = 0; i2 < L / 2; ++i2) {
+            const double2 s2 = row[i2];
+            sacc = fma(s2.x, v[2 * i2], sacc);
+            sacc = fma(s2.y, v[2 * i2 + 1], sacc);
+          }
+          o[a] = sacc;
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < L; ++a) ou[base + a * str] = o[a];
+    }
+    __syncthreads();
+    double* tmp = in; in = ou; ou = tmp;
+  }
+  // ---- z = block solve + trilinear interpolation of the corner values + aggregate value;  partial z.r
+  const double* res = ((2 * D) % 2 == 0) ? sA : sB;  // an even number of passes ends in the buffer it started from
+  double dot[1] = {0.0};
+  for (int t = tid; t < ne * NP; t += NT) {
+    const int e1 = t / NP, p = t - e1 * NP;
+    const int i0 = p % L, i1 = (p / L) % L;
+    const double* X = sX + e1 * (NK + 2);
+    const double a0 = sl1[i0], a1 = sl1[i1];
+    double c0 = fma(X[1] - X[0], a0, X[0]), c1 = fma(X[3] - X[2], a0, X[2]);
+    double q = fma(c1 - c0, a1, c0);
+    if (D == 3) {
+      const double d0 = fma(X[5] - X[4], a0, X[4]), d1 = fma(X[7] - X[6], a0, X[6]);
+      const double q1 = fma(d1 - d0, a1, d0);
+      q = fma(q1 - q, sl1[p / LL], q);
+    }
+    const double val = res[e1 * ESZ + (p / L) * PI + i0] + q + X[NK];
+    const long long gi = (long long)e0 * NP + t;
+    z[gi] = val;
+    dot[0] = fma(val, r[gi], dot[0]);
   }
   if (grid_sum_finish<1>(dot, part, counter, out, sred) && mode == 1 && threadIdx.x == 0) {
     cgs->rtz1 = out[0];
@@ -419,7 +573,7 @@ void pm_free(PMG& m) {
 
 // ---------------------------------------------------------------------------------------------- runtime pieces
 static int pm_restrict(Ctx* c, PMG& m, const double* r, const CGState* skip) {
-  PM_DISPATCH(c, (k_pm_restrict<D, L><<<(c->nel + 7) / 8, 256, 0, c->stream>>>(r, m.rc, c->nel, skip)));
+  PM_DISPATCH(c, (k_pm_restrict<D, L><<<std::min((c->nel + 7) / 8, 148 * 8), 256, 0, c->stream>>>(r, m.rc, c->nel, skip)));
   return 0;
 }
 static int pm_coarse(Ctx* c, PMG& m, const double* d1inv, int vmode, int amode, const CGState* skip) {
@@ -460,18 +614,26 @@ static int pm_apply_E(Ctx* c, int set, const double* pin, double* pout) {
 }
 
 // z = M^-1 r.  mode 0: plain operator; 1: inside the pressure CG (skips when converged, updates rtz1/beta)
-int pm_apply(Ctx* c, int set, const double* r, double* z, int mode) {
+int pm_apply(Ctx* c, int set, const double* r, double* z, int mode, int prof_slot) {
   PMG& m = c->pmg[(set && c->has_adj_masks) ? 1 : 0];      // without separate adjoint masks both problems share one E
   if (!m.ready) { nsb_set_error("pmg: preconditioner not set up"); return 1; }
   CGState* sp = c->cgs + 3;
   const CGState* skip = mode ? sp : nullptr;
   NSB_TRY(pm_restrict(c, m, r, skip));
+  if (prof_slot > 0) cudaEventRecord(c->prof_ev[prof_slot], c->stream);
   NSB_TRY(pm_coarse_levels(c, m, m.d1inv, skip));
   if (c->nranks > 1) NSB_TRY(vk_allreduce_sum(c, m.ra, m.nagg));
   NSB_TRY(pm_gemv(c, m, skip));
+  if (prof_slot > 0) cudaEventRecord(c->prof_ev[prof_slot + 1], c->stream);
   const int kmode = mode ? (c->nranks == 1 ? 1 : 2) : 0;
-  PM_DISPATCH(c, (k_pm_apply<D, L><<<(c->nel + 7) / 8, 256, 0, c->stream>>>(r, z, c->nel, m.S, m.lam, m.xv, m.vid, m.x2, m.agg, sp,
-                                                                           kmode, c->red_part, c->red_count, c->red_out)));
+  static const int gen = [] { const char* e = getenv("NSB_PM_APPLY"); return (e && e[0] == '1') ? 1 : 2; }();
+  if (gen == 1) {
+    PM_DISPATCH(c, (k_pm_apply<D, L><<<(c->nel + 7) / 8, 256, 0, c->stream>>>(r, z, c->nel, m.S, m.lam, m.xv, m.vid, m.x2, m.agg, sp,
+                                                                             kmode, c->red_part, c->red_count, c->red_out)));
+  } else {
+    PM_DISPATCH(c, (k_pm_apply2<D, L><<<(c->nel + Pm2<D, L>::EPB - 1) / Pm2<D, L>::EPB, Pm2<D, L>::NT, 0, c->stream>>>(
+                       r, z, c->nel, m.S, m.lam, m.xv, m.vid, m.x2, m.agg, sp, kmode, c->red_part, c->red_count, c->red_out)));
+  }
   if (mode && c->nranks > 1) NSB_TRY(vk_cg_finalize_multi(c, sp, 1, 5));
   return 0;
 }

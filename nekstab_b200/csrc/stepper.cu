@@ -249,8 +249,8 @@ int st_pressure(Ctx* c, int adj, int* iters) {
       prof_mark(c, sm, 7);
       NSB_TRY(vk_pcg_update(c, adj));
       prof_mark(c, sm, 8);
-      if (pc) NSB_TRY(pm_apply(c, adj, c->pk[0], c->pz, 1));
-      prof_mark(c, sm, 9);
+      if (pc) NSB_TRY(pm_apply(c, adj, c->pk[0], c->pz, 1, sm ? 9 : 0));
+      prof_mark(c, sm, 11);
     }
     return 0;
   };
@@ -260,7 +260,7 @@ int st_pressure(Ctx* c, int adj, int* iters) {
     else NSB_TRY(batch(sample));
     issued += c->check_every_p;
     NSB_TRY(cg_state_poll(c, 3, 1, &done));
-    if (sample) { const int kinds[5] = {0, 1, 2, 3, 8}; prof_collect(c, kinds, pc ? 5 : 4, 4); }
+    if (sample) { const int kinds[7] = {0, 1, 2, 3, 8, 9, 10}; prof_collect(c, kinds, pc ? 7 : 4, 4); }
     if (issued > c->maxit_p + c->check_every_p) break;
   }
   NSB_TRY(p2p_check_error(c));

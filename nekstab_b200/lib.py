@@ -250,7 +250,7 @@ class NekStabB200:
         return {k: getattr(s, k) for k, _ in Stats._fields_}
 
     PROFILE_KINDS = ["pcg_gradt", "dssum", "pcg_div", "pcg_update", "hcg_axhelm", "hcg_update", "advab", "hcg_dssum",
-                     "pcg_precond"]
+                     "pcg_pc_restrict", "pcg_pc_coarse", "pcg_pc_apply"]
 
     def profile(self, enable=-1):
         ms = np.zeros(12); cnt = np.zeros(12, dtype=np.int64)

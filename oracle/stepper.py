@@ -39,7 +39,7 @@ def prepare_linearized_solver(sem: SEM, ubase, end_time, cfl_target=0.5):
 
 class LinearizedStepper:
     def __init__(self, sem: SEM, ubase, re, spng_fun=None, tol_v=1e-9, tol_p=1e-7, solver="direct",
-                 max_iter_v=1000, max_iter_p=20000, ifvcor=None):
+                 max_iter_v=1000, max_iter_p=20000, ifvcor=None, pressure_precond=None):
         self.s = sem
         d = sem.ldim
         self.ub = ubase.reshape((d,) + sem.eshape)
@@ -57,6 +57,7 @@ class LinearizedStepper:
         self._lu_h = {}
         self._lu_e = None
         self._ediag = None
+        self.pressure_precond = pressure_precond     # None: Jacobi; else an object with .apply(r) (oracle/pmg.py PMG)
         self.iters_v, self.iters_p = [], []
         self.dt = None
 
@@ -135,7 +136,7 @@ class LinearizedStepper:
         rtz1 = 1.0
         it = 0
         while True:
-            z = dinv * r
+            z = dinv * r if self.pressure_precond is None else self.pressure_precond.apply(r)
             rtz2 = rtz1
             rtz1 = float(np.sum(z * r))
             rn = math.sqrt(float(np.sum(r * r / s.bm2)) / s.vol2)

@@ -119,6 +119,7 @@ extern "C" int nsb_finalize(void) {
   }
   if (c->projX) { cudaFree(c->projX); cudaFree(c->projEX); }
   pm_free(c->pmg[0]); pm_free(c->pmg[1]);
+  if (c->adv_scratch) cudaFree(c->adv_scratch);
   if (c->pz) cudaFree(c->pz);
   if (c->ones2) cudaFree(c->ones2);
   if (c->cgs) cudaFree(c->cgs);

@@ -392,11 +392,35 @@ __device__ __forceinline__ void fine_expand(const double* su, double* sa, double
   }
 }
 
+// SCR = true (3-D default): the persistent fine-mesh arrays (6-9 x lxd^3 doubles per element, 83-124 KB) live in a per-CTA
+// global scratch slot instead of shared memory and the CTAs are persistent (grid = resident CTAs), so the slots stay in
+// L2; with 256 threads this lets 2 CTAs share an SM (first generation: 512 threads x 128 registers + 156 KB = 1 CTA/SM,
+// 6 % of the FP64 peak, most threads idle in the 64-column first tensor stage).
+// one element; `fine` = the persistent fine-mesh arrays (shared memory or the CTA's global scratch slot).  Kept out of line:
+// inlined into the persistent element loop nvcc hoists the constant-bank matrices into registers and spills (see k_div3p).
 template <int D, int N, int ADJ>
-__global__ void __launch_bounds__(Cfg<D, N>::TPB_ADV)
+__device__ __noinline__ void advab_element(const double* __restrict__ up, const double* __restrict__ ub,
+                                           const double* __restrict__ Rd, const double* __restrict__ bm1,
+                                           const double* __restrict__ spng, double* __restrict__ fout, long long n, long long nd,
+                                           double* __restrict__ fine, int e);
+
+template <int D, int N, int ADJ, bool SCR>
+__global__ void __launch_bounds__(SCR ? 256 : Cfg<D, N>::TPB_ADV, SCR ? 2 : 1)
 k_advab(const double* __restrict__ up, const double* __restrict__ ub, const double* __restrict__ Rd,
         const double* __restrict__ bm1, const double* __restrict__ spng, double* __restrict__ fout, long long n,
-        long long nd) {
+        long long nd, double* __restrict__ scratch, int nel) {
+  using C = Cfg<D, N>;
+  using A = AdvSmem<D, N>;
+  extern __shared__ double smem[];
+  double* fine = SCR ? scratch + (size_t)blockIdx.x * (3 * D * C::NPD) : smem + A::work;
+  for (int e = blockIdx.x; e < nel; e += gridDim.x) advab_element<D, N, ADJ>(up, ub, Rd, bm1, spng, fout, n, nd, fine, e);
+}
+
+template <int D, int N, int ADJ>
+__device__ __noinline__ void advab_element(const double* __restrict__ up, const double* __restrict__ ub,
+                                           const double* __restrict__ Rd, const double* __restrict__ bm1,
+                                           const double* __restrict__ spng, double* __restrict__ fout, long long n, long long nd,
+                                           double* __restrict__ fine, int e) {
   using C = Cfg<D, N>;
   using A = AdvSmem<D, N>;
   using S1 = typename C::S1;
@@ -409,13 +433,13 @@ k_advab(const double* __restrict__ up, const double* __restrict__ ub, const doub
   double* sa = su + S1::size;
   double* sb = sa + 2 * SA::size;
   double* sF = sb + 3 * SB::size;
-  double* fine = sF + SD::size;          // own-point (unpitched) persistent arrays
   double* crb = fine;                    // [D][NPD]   contravariant base flow  (Rd . U)
   double* crp = fine + D * NPD;          // [D][NPD]   direct: contravariant perturbation ; adjoint: u'_j on the fine mesh
   double* accf = fine + 2 * D * NPD;     // adjoint only: [D][NPD] accumulators
   const int tid = threadIdx.x, nthr = blockDim.x;
-  const long long e1 = (long long)blockIdx.x * NP1;
-  const long long ed = (long long)blockIdx.x * NPD;
+  {
+  const long long e1 = (long long)e * NP1;
+  const long long ed = (long long)e * NPD;
 
   for (int q = tid; q < 2 * D * NPD; q += nthr) fine[q] = 0.0;
   if (ADJ) for (int q = tid; q < D * NPD; q += nthr) accf[q] = 0.0;
@@ -510,6 +534,7 @@ k_advab(const double* __restrict__ up, const double* __restrict__ ub, const doub
     }
     __syncthreads();
   }
+  }   // element loop
 }
 
 // --------------------------------------------------------------------------------------------- geometry (setup; generic, slow, run once)
@@ -870,13 +895,35 @@ int ek_pcg_div(Ctx* c, int adj) {
 template <int D, int N, int ADJ>
 static int launch_advab(Ctx* c, const double* up, const double* ub, const double* spng, double* f) {
   using A = AdvSmem<D, N>;
+  static const bool scr_env = [] { const char* e = getenv("NSB_ADV_SCRATCH"); return !(e && e[0] == '0'); }();
+  if (D == 3 && scr_env) {
+    const size_t smem = (size_t)A::work * sizeof(double);
+    static int grid = 0;
+    if (!grid) {
+      NSB_CUDA(cudaFuncSetAttribute(k_advab<D, N, ADJ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int per_sm = 0, sms = 148;
+      NSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_advab<D, N, ADJ, true>, 256, smem));
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+      grid = std::max(1, per_sm) * sms;
+    }
+    const int g = std::min(grid, c->nel);
+    const size_t need = (size_t)g * 3 * D * Cfg<D, N>::NPD;
+    if (c->adv_scratch_words < need) {
+      if (c->adv_scratch) cudaFree(c->adv_scratch);
+      NSB_CUDA(cudaMalloc(&c->adv_scratch, need * sizeof(double)));
+      c->adv_scratch_words = need;
+    }
+    k_advab<D, N, ADJ, true><<<g, 256, smem, c->stream>>>(up, ub, c->Rd, c->bm1, spng, f, c->n, c->nd, c->adv_scratch, c->nel);
+    return 0;
+  }
   size_t smem = (size_t)(A::work + (ADJ ? A::fine_adj : (A::fine_direct + Cfg<D, N>::NPD))) * sizeof(double);
   static bool attr_set = false;
   if (!attr_set) {
-    NSB_CUDA(cudaFuncSetAttribute(k_advab<D, N, ADJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NSB_CUDA(cudaFuncSetAttribute(k_advab<D, N, ADJ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  k_advab<D, N, ADJ><<<c->nel, Cfg<D, N>::TPB_ADV, smem, c->stream>>>(up, ub, c->Rd, c->bm1, spng, f, c->n, c->nd);
+  k_advab<D, N, ADJ, false><<<c->nel, Cfg<D, N>::TPB_ADV, smem, c->stream>>>(up, ub, c->Rd, c->bm1, spng, f, c->n, c->nd, nullptr,
+                                                                            c->nel);
   return 0;
 }
 

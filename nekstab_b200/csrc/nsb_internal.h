@@ -176,6 +176,9 @@ struct Ctx {
   bool persistent_pcg = true; // 3-D: persistent, TMA-pipelined k_gradt3p / k_div3p in the pressure-CG loop (NSB_PERSISTENT=0 disables)
   bool fused_gs = false;      // 3-D, single rank: k_div3 gathers the surface sums itself (no dssum in the pressure loop)
 
+  double* adv_scratch = nullptr;   // per-CTA fine-mesh work arrays of the advection kernel (L2-resident)
+  size_t adv_scratch_words = 0;
+
   // base flow, sponge
   double* ub = nullptr;     // [d][n]
   double* spng = nullptr;   // [n] or null

@@ -52,6 +52,14 @@
         import :: c_int
         integer(c_int), value :: direct, adjoint
       end function
+      integer(c_int) function nsb_set_pressure_preconditioner(kind, nagg) bind(C, name='nsb_set_pressure_preconditioner')
+         import :: c_int
+         integer(c_int), value :: kind, nagg
+      end function
+      integer(c_int) function nsb_set_projection(mxprev) bind(C, name='nsb_set_projection')
+         import :: c_int
+         integer(c_int), value :: mxprev
+      end function
       integer(c_int) function nsb_set_adjoint_masks(m1, m2, m3) bind(C, name='nsb_set_adjoint_masks')
         import :: c_int, c_double
         real(c_double) :: m1(*), m2(*), m3(*)

@@ -39,6 +39,9 @@
       call nsb_b200_check(nsb_set_weights(bm1s), 'nsb_set_weights')
       if (spng_str .ne. 0) call nsb_b200_check(nsb_set_sponge(spng_fun), 'nsb_set_sponge')
       call nsb_b200_check(nsb_set_ifvcor(merge(1, 0, ifvcor), -1), 'nsb_set_ifvcor')
+      ! [PRESSURE] preconditioner = semg_xxt in every shipped .par (1cyl.par:28): the multilevel Schwarz class (kind 1);
+      ! kind 0 keeps Jacobi.  nagg = 0: automatic number of coarse aggregates.
+      call nsb_b200_check(nsb_set_pressure_preconditioner(1, 0), 'nsb_set_pressure_preconditioner')
       call nsb_b200_check(nsb_vec_alloc(k_dim + 8), 'nsb_vec_alloc')
       end subroutine
 

@@ -537,6 +537,231 @@ __device__ __noinline__ void advab_element(const double* __restrict__ up, const 
   }   // element loop
 }
 
+// --------------------------------------------------------------------------------------------- advection, second generation (3-D)
+// Plane streaming: the CTA keeps the six coarse fields (u'_c, U_c) as k-columns in REGISTERS (thread = field x (i,j)) and
+// walks over the lxd fine k-planes.  Per plane: (1) every column thread contracts its k-column with row kf of Jd and Dd
+// -> twelve coarse (i,j) slices in shared memory; (2) stage i and (3) stage j expand the slices to the 12x12 plane of the
+// value and the three reference derivatives of all six fields -- 144 resp. 288 column tasks, one per thread, the task
+// TYPE (which matrix, which source) uniform per warp, matrices from the constant bank; (4) one thread per fine point
+// combines the 24 values with the nine fine-mesh metrics Rd of the plane (prefetched one plane ahead with cp.async into
+// a double buffer: they are the kernel's HBM traffic) into the three integrands; (5)(6) two transposed stages project
+// the plane back to (i,j) and (7) the column threads accumulate it into their k-column of the result with row kf of Jd.
+// Shared memory per CTA: 73 KB; nothing but the metrics, the six input fields and the three outputs touches HBM.
+// First generation: one field and one derivative at a time through full lxd^3 shared arrays, 64 column tasks in the
+// first stage for 512 threads, 6 % of the FP64 peak.
+template <int N>
+struct Adv2 {
+  static constexpr int M = 3 * N / 2;
+  static constexpr int NN = N * N, MM = M * M;
+  static constexpr int c32(int x) { return (x + 31) / 32 * 32; }
+  static constexpr int mx(int a, int b) { return a > b ? a : b; }
+  static constexpr int SI_T = c32(6 * N);          // threads reserved per task type in stage i (6 fields x N rows)
+  static constexpr int SJ_T = c32(6 * M);          // ... in stage j (6 fields x M columns)
+  static constexpr int NT = mx(mx(c32(6 * NN), 3 * SI_T), mx(4 * SJ_T, c32(MM)));
+  static constexpr int PN = N + 1, PM = M + 1;     // odd row pitches
+  static constexpr int SL = 2 * 6 * N * PN;        // slices  [J|D][field][j][i]
+  static constexpr int MID = 3 * 6 * N * PM;       // stage-i outputs [aJ|aD|cJ][field][j][if]; later aliased by P, Q1, Q
+  static constexpr int FS = M * PM;                // one fine plane
+  static constexpr int FINE = 6 * 4 * FS;          // [field][F|Gs|Gr|Gt][jf][if]
+  static constexpr int RD = 2 * 9 * MM;            // double-buffered metric planes
+  static constexpr int TOTAL = SL + MID + FINE + RD;
+  static_assert(3 * FS + 3 * N * PM + 3 * N * PN <= MID, "P/Q1/Q must fit in the stage-i buffer");
+};
+
+// out[m] = sum_l Mat[m*NL + l] in[l*istr], m < NO, stored with stride ostr (Mat: constant bank, compile-time offsets)
+template <int NO, int NL>
+__device__ __forceinline__ void col_apply(const double* __restrict__ in, int istr, double* __restrict__ out, int ostr,
+                                          const double* __restrict__ Mat) {
+  double v[NL];
+#pragma unroll
+  for (int l = 0; l < NL; ++l) v[l] = in[l * istr];
+#pragma unroll
+  for (int m = 0; m < NO; ++m) {
+    double sacc = 0.0;
+#pragma unroll
+    for (int l = 0; l < NL; ++l) sacc = fma(Mat[m * NL + l], v[l], sacc);
+    out[m * ostr] = sacc;
+  }
+}
+
+// stages (2)-(6) of one plane; out of line so that nvcc does not hoist the constant-bank matrices out of the plane loop
+template <int N, int ADJ>
+__device__ __noinline__ void adv2_plane(double* __restrict__ sm, int tid, int buf, int last) {
+  using A = Adv2<N>;
+  constexpr int M = A::M, PN = A::PN, PM = A::PM, FS = A::FS, MM = A::MM;
+  double* sl = sm;
+  double* mid = sm + A::SL;
+  double* fine = mid + A::MID;
+  const double* rd = fine + A::FINE + buf * 9 * MM;
+  double* P = mid;                      // aliases (the stage-i arrays are dead after stage j)
+  double* Q1 = mid + 3 * FS;
+  double* Q = Q1 + 3 * N * PM;
+  // ---- (2) stage i: rows of the slices -> aJ = Jd row, aD = Dd row (from the J-slice), cJ = Jd row (from the D-slice)
+  if (tid < 3 * A::SI_T) {
+    const int type = tid / A::SI_T, r = tid - type * A::SI_T;
+    if (r < 6 * N) {
+      const double* src = sl + (type == 2 ? 6 * N * PN : 0) + r * PN;          // r = f*N + j
+      double* dst = mid + type * (6 * N * PM) + r * PM;
+      if (type == 1) col_apply<M, N>(src, 1, dst, 1, cm.Dd);
+      else col_apply<M, N>(src, 1, dst, 1, cm.Jd);
+    }
+  }
+  __syncthreads();
+  // ---- (3) stage j: columns -> F = Jd aJ, Gs = Dd aJ, Gr = Jd aD, Gt = Jd cJ
+  if (tid < 4 * A::SJ_T) {
+    const int type = tid / A::SJ_T, r = tid - type * A::SJ_T;
+    if (r < 6 * M) {
+      const int f = r / M, i = r - f * M;
+      const int srcsel = (type == 2) ? 1 : (type == 3 ? 2 : 0);
+      const double* src = mid + srcsel * (6 * N * PM) + f * (N * PM) + i;
+      double* dst = fine + (f * 4 + type) * FS + i;
+      if (type == 1) col_apply<M, N>(src, PM, dst, PM, cm.Dd);
+      else col_apply<M, N>(src, PM, dst, PM, cm.Jd);
+    }
+  }
+  if (last) asm volatile("cp.async.wait_group 0;" ::: "memory");
+  else asm volatile("cp.async.wait_group 1;" ::: "memory");
+  __syncthreads();
+  // ---- (4) pointwise: fields 0..2 = u'_c, 3..5 = U_c; derivative order (r, s, t) = types (2, 1, 3)
+  if (tid < MM) {
+    const int q = tid, o = (q / M) * PM + (q % M);
+    double R[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) R[i][c] = rd[(i * 3 + c) * MM + q];
+    double val[6], gr[6][3];
+#pragma unroll
+    for (int f = 0; f < 6; ++f) {
+      val[f] = fine[(f * 4 + 0) * FS + o];
+      gr[f][0] = fine[(f * 4 + 2) * FS + o];
+      gr[f][1] = fine[(f * 4 + 1) * FS + o];
+      gr[f][2] = fine[(f * 4 + 3) * FS + o];
+    }
+    double crb[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) crb[i] = R[i][0] * val[3] + R[i][1] * val[4] + R[i][2] * val[5];
+    double acc[3];
+    if (ADJ) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        double a = 0.0;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const double g = R[0][i] * gr[3 + j][0] + R[1][i] * gr[3 + j][1] + R[2][i] * gr[3 + j][2];   // dU_j/dx_i (weighted)
+          a = fma(val[j], g, a);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) a = fma(-crb[k], gr[i][k], a);
+        acc[i] = a;
+      }
+    } else {
+      double crp[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) crp[i] = R[i][0] * val[0] + R[i][1] * val[1] + R[i][2] * val[2];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        double a = 0.0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) a = fma(crp[i], gr[3 + k][i], fma(crb[i], gr[k][i], a));
+        acc[k] = a;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) P[c * FS + o] = acc[c];
+  }
+  __syncthreads();
+  // ---- (5) Jd^T along j: P[c][jf][if] -> Q1[c][j][if]
+  if (tid < 3 * M) {
+    const int c = tid / M, i = tid - c * M;
+    col_apply<N, M>(P + c * FS + i, PM, Q1 + c * (N * PM) + i, PM, cm.Jdt);
+  }
+  __syncthreads();
+  // ---- (6) Jd^T along i: Q1[c][j][if] -> Q[c][j][i]
+  if (tid < 3 * N) {
+    const int c = tid / N, j = tid - c * N;
+    col_apply<N, M>(Q1 + c * (N * PM) + j * PM, 1, Q + c * (N * PN) + j * PN, 1, cm.Jdt);
+  }
+  __syncthreads();
+}
+
+template <int N, int ADJ>
+__global__ void __launch_bounds__(Adv2<N>::NT, 2)
+k_advab2(const double* __restrict__ up, const double* __restrict__ ub, const double* __restrict__ Rd,
+         const double* __restrict__ bm1, const double* __restrict__ spng, double* __restrict__ fout, long long n,
+         long long nd) {
+  using A = Adv2<N>;
+  constexpr int M = A::M, NN = A::NN, MM = A::MM, PN = A::PN, PM = A::PM, NT = A::NT;
+  extern __shared__ __align__(16) double sm2[];
+  double* sl = sm2;
+  double* Q = sm2 + A::SL + 3 * A::FS + 3 * N * PM;
+  double* rdbuf = sm2 + A::SL + A::MID + A::FINE;
+  const int tid = threadIdx.x;
+  const long long e1 = (long long)blockIdx.x * (NN * N);
+  const long long ed = (long long)blockIdx.x * (MM * M);
+  // metric plane kf -> buffer kf&1 with cp.async: 16 bytes per copy when the planes are 16-byte aligned (lxd^2 even), else 8
+  auto prefetch = [&](int kf) {
+    const unsigned base = (unsigned)__cvta_generic_to_shared(rdbuf + (kf & 1) * 9 * MM);
+    if constexpr (MM % 2 == 0) {
+      for (int t = tid; t < 9 * MM / 2; t += NT) {
+        const int a = t / (MM / 2), w2 = t - a * (MM / 2);
+        const double* g = Rd + (long long)a * nd + ed + (long long)kf * MM + 2 * w2;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(base + (unsigned)((a * MM + 2 * w2) * 8)), "l"(g) : "memory");
+      }
+    } else {
+      for (int t = tid; t < 9 * MM; t += NT) {
+        const int a = t / MM, w1 = t - a * MM;
+        const double* g = Rd + (long long)a * nd + ed + (long long)kf * MM + w1;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(base + (unsigned)((a * MM + w1) * 8)), "l"(g) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  prefetch(0);
+  const bool colthread = tid < 6 * NN;
+  const int f = tid / NN, ij = tid - f * NN;
+  const int slo = (ij / N) * PN + (ij % N);
+  double col[N], res[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) { col[k] = 0.0; res[k] = 0.0; }
+  if (colthread) {
+    const double* src = (f < 3) ? up + (long long)f * n : ub + (long long)(f - 3) * n;
+#pragma unroll
+    for (int k = 0; k < N; ++k) col[k] = src[e1 + k * NN + ij];
+  }
+  for (int kf = 0; kf < M; ++kf) {
+    if (kf + 1 < M) prefetch(kf + 1);
+    // ---- (1) k-contraction of the register columns with row kf of Jd / Dd
+    if (colthread) {
+      double wj = 0.0, wd = 0.0;
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        wj = fma(cm.Jd[kf * N + k], col[k], wj);
+        wd = fma(cm.Dd[kf * N + k], col[k], wd);
+      }
+      sl[f * (N * PN) + slo] = wj;
+      sl[6 * N * PN + f * (N * PN) + slo] = wd;
+    }
+    __syncthreads();
+    adv2_plane<N, ADJ>(sm2, tid, kf & 1, kf + 1 == M);
+    // ---- (7) accumulate the projected plane into the k-columns of the three outputs
+    if (tid < 3 * NN) {
+      const double qv = Q[f * (N * PN) + slo];
+#pragma unroll
+      for (int k = 0; k < N; ++k) res[k] = fma(cm.Jd[kf * N + k], qv, res[k]);
+    }
+  }
+  if (tid < 3 * NN) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const long long gi = e1 + k * NN + ij;
+      double v = -res[k];
+      if (spng) v -= bm1[gi] * spng[gi] * col[k];
+      fout[(long long)f * n + gi] = v;
+    }
+  }
+}
+
 // --------------------------------------------------------------------------------------------- geometry (setup; generic, slow, run once)
 __global__ void k_metrics(int D, int N, long long n, const double* __restrict__ x, const double* __restrict__ y,
                           const double* __restrict__ z, const double* __restrict__ Dm /*N*N global*/,
@@ -895,6 +1120,20 @@ int ek_pcg_div(Ctx* c, int adj) {
 template <int D, int N, int ADJ>
 static int launch_advab(Ctx* c, const double* up, const double* ub, const double* spng, double* f) {
   using A = AdvSmem<D, N>;
+  static const int gen = [] { const char* e = getenv("NSB_ADV_GEN"); return (e && e[0] == '1') ? 1 : 2; }();
+  if constexpr (D == 3) {
+    if (gen == 2) {
+      using A2 = Adv2<N>;
+      const size_t smem2 = (size_t)A2::TOTAL * sizeof(double);
+      static bool attr2 = false;
+      if (!attr2) {
+        NSB_CUDA(cudaFuncSetAttribute(k_advab2<N, ADJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        attr2 = true;
+      }
+      k_advab2<N, ADJ><<<c->nel, A2::NT, smem2, c->stream>>>(up, ub, c->Rd, c->bm1, spng, f, c->n, c->nd);
+      return 0;
+    }
+  }
   static const bool scr_env = [] { const char* e = getenv("NSB_ADV_SCRATCH"); return !(e && e[0] == '0'); }();
   if (D == 3 && scr_env) {
     const size_t smem = (size_t)A::work * sizeof(double);

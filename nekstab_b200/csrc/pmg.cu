@@ -42,36 +42,97 @@ __device__ __forceinline__ double pm_phi(int k, int p) {
   return f;
 }
 
-// rc[e][k] = sum_p phi_k(p) r_e(p); one warp per element, fixed-shape shuffle tree (deterministic)
+// rc[e][k] = sum_p phi_k(p) r_e(p); one warp per element (grid-stride).  The hat-function factors of a lane's points sit in
+// registers (they do not depend on the element), the 2^D sums are built by successive splitting (k2, k1, k0) and reduced
+// with a transposed butterfly: 9 shuffles instead of 40, fixed tree => deterministic.  (First generation: hats from the
+// constant bank with lane-varying index, then from a shared table: 0.039 / 0.029 ms for 34 MB.)
 template <int D, int L>
 __global__ void __launch_bounds__(256) k_pm_restrict(const double* __restrict__ r, double* __restrict__ rc, int nel,
                                                      const CGState* skip) {
   if (skip && skip->done) return;
   using S = PmShape<D, L>;
-  __shared__ double sphi[S::NK * S::NP];           // hat functions at the element's points (the constant bank serialises
-  for (int t = threadIdx.x; t < S::NK * S::NP; t += blockDim.x) sphi[t] = pm_phi<D, L>(t / S::NP, t % S::NP);   // lane-varying indices)
+  constexpr int NK = S::NK, NP = S::NP, NPL = S::NPL;
+  __shared__ double sl1[8];
+  if (threadIdx.x < L) sl1[threadIdx.x] = pm_l[1][threadIdx.x];
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
+  double fa[NPL], fb[NPL], fc[NPL];
+#pragma unroll
+  for (int q = 0; q < NPL; ++q) {
+    const int p = lane + 32 * q;
+    const bool in = p < NP;
+    fa[q] = in ? sl1[p % L] : 0.0;
+    fb[q] = in ? sl1[(p / L) % L] : 0.0;
+    fc[q] = (in && D == 3) ? sl1[p / (L * L)] : 0.0;
+  }
   for (int e = blockIdx.x * wpb + (threadIdx.x >> 5); e < nel; e += gridDim.x * wpb) {
-    double acc[S::NK];
+    double acc[NK];
 #pragma unroll
-    for (int k = 0; k < S::NK; ++k) acc[k] = 0.0;
+    for (int k = 0; k < NK; ++k) acc[k] = 0.0;
+    const double* re = r + (long long)e * NP;
 #pragma unroll
-    for (int q = 0; q < S::NPL; ++q) {
+    for (int q = 0; q < NPL; ++q) {
       const int p = lane + 32 * q;
-      if (p < S::NP) {
-        const double v = r[(long long)e * S::NP + p];
-#pragma unroll
-        for (int k = 0; k < S::NK; ++k) acc[k] = fma(sphi[k * S::NP + p], v, acc[k]);
+      if (p < NP) {
+        const double v = re[p];
+        if (D == 3) {
+          const double t1 = v * fc[q], t0 = v - t1;
+          const double t01 = t0 * fb[q], t00 = t0 - t01, t11 = t1 * fb[q], t10 = t1 - t11;
+          double h;
+          h = t00 * fa[q]; acc[1] += h; acc[0] += t00 - h;
+          h = t01 * fa[q]; acc[3] += h; acc[2] += t01 - h;
+          h = t10 * fa[q]; acc[5] += h; acc[4] += t10 - h;
+          h = t11 * fa[q]; acc[7] += h; acc[6] += t11 - h;
+        } else {
+          const double t1 = v * fb[q], t0 = v - t1;
+          double h;
+          h = t0 * fa[q]; acc[1] += h; acc[0] += t0 - h;
+          h = t1 * fa[q]; acc[3] += h; acc[2] += t1 - h;
+        }
       }
     }
+    // transposed butterfly: after the steps with offsets 16, 8 (, 4) every lane holds ONE of the 2^D sums, partially reduced
+    double b1;
+    if (D == 3) {
+      double b4[4], b2[2];
 #pragma unroll
-    for (int k = 0; k < S::NK; ++k) {
-      double x = acc[k];
+      for (int j = 0; j < 4; ++j) {
+        const bool hi = lane & 16;
+        const double mine = hi ? acc[4 + j] : acc[j], send = hi ? acc[j] : acc[4 + j];
+        b4[j] = mine + __shfl_xor_sync(0xffffffffu, send, 16);
+      }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
-      if (lane == 0) rc[(long long)e * S::NK + k] = x;
+      for (int j = 0; j < 2; ++j) {
+        const bool hi = lane & 8;
+        const double mine = hi ? b4[2 + j] : b4[j], send = hi ? b4[j] : b4[2 + j];
+        b2[j] = mine + __shfl_xor_sync(0xffffffffu, send, 8);
+      }
+      {
+        const bool hi = lane & 4;
+        const double mine = hi ? b2[1] : b2[0], send = hi ? b2[0] : b2[1];
+        b1 = mine + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+      b1 += __shfl_xor_sync(0xffffffffu, b1, 2);
+      b1 += __shfl_xor_sync(0xffffffffu, b1, 1);
+      if ((lane & 3) == 0) rc[(long long)e * NK + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)] = b1;
+    } else {
+      double b2[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const bool hi = lane & 16;
+        const double mine = hi ? acc[2 + j] : acc[j], send = hi ? acc[j] : acc[2 + j];
+        b2[j] = mine + __shfl_xor_sync(0xffffffffu, send, 16);
+      }
+      {
+        const bool hi = lane & 8;
+        const double mine = hi ? b2[1] : b2[0], send = hi ? b2[0] : b2[1];
+        b1 = mine + __shfl_xor_sync(0xffffffffu, send, 8);
+      }
+      b1 += __shfl_xor_sync(0xffffffffu, b1, 4);
+      b1 += __shfl_xor_sync(0xffffffffu, b1, 2);
+      b1 += __shfl_xor_sync(0xffffffffu, b1, 1);
+      if ((lane & 7) == 0) rc[(long long)e * NK + ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1)] = b1;
     }
   }
 }

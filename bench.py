@@ -217,6 +217,8 @@ def main():
         print(json.dumps(line))
         return
 
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"     # the box sets VERSION: NCCL would print its banner on stdout before the JSON line
     import torch
     import torch.distributed as dist
     from nekstab_b200 import lib

@@ -1,0 +1,77 @@
+"""CPU tests of the checkpoint/restart file protocol (nekstab_b200/restart.py; reference: core/eigensolvers.f:284-325,
+802-905, core/IO.f:15-60): text formats pinned byte for byte to the shipped spectrum files, binary round trips exact."""
+import os
+
+import numpy as np
+
+from nekstab_b200 import restart
+from util import GOLD, small_cases
+
+
+def test_spectrum_writer_matches_shipped_text(tmp_path):
+    for name in ("Spectre_Hd_head.dat", "Spectre_NSd_head.dat"):
+        ref = open(os.path.join(GOLD, name)).read()
+        rows = np.loadtxt(os.path.join(GOLD, name), ndmin=2)
+        out = tmp_path / name
+        restart.write_spectrum(str(out), rows[:, 0] + 1j * rows[:, 1], rows[:, 2])
+        assert open(out).read() == ref                      # '(3E15.7)': 0.dddddddE+ee, byte for byte
+
+
+def test_log_transform_reproduces_shipped_ns_spectrum():
+    g = np.load(os.path.join(GOLD, "cyl.npz"))
+    h, ns = g["Spectre_Hd"], g["Spectre_NSd"]
+    lam = restart.log_transform(h[:, 0] + 1j * h[:, 1], 1.0)    # tau = dt*nsteps = 1 (SURVEY 8c relation check)
+    big = np.abs(h[:, 0] + 1j * h[:, 1]) > 1e-3
+    assert np.abs(lam.real - ns[:, 0])[big].max() < 2e-6 and np.abs(np.abs(lam.imag) - np.abs(ns[:, 1]))[big].max() < 2e-6
+
+
+def test_fortran_e_edge_cases():
+    assert restart.fortran_e(0.0) == "  0.0000000E+00"
+    assert restart.fortran_e(-0.6972442) == " -0.6972442E+00"
+    assert restart.fortran_e(9.99999999e-4) == "  0.1000000E-02"      # rounding carries into the exponent
+    assert restart.fortran_e(5.095353e-19) == "  0.5095353E-18"
+
+
+def test_hessenberg_round_trip(tmp_path):
+    rng = np.random.default_rng(0)
+    k = 7
+    H = np.triu(rng.standard_normal((k + 1, k)), -1)
+    path = str(tmp_path / restart.hes_filename("1cyl", k))
+    assert os.path.basename(path) == "HES1cyl0007"
+    restart.write_hessenberg(path, H, k)
+    assert np.array_equal(restart.read_hessenberg(path, k), H)          # %.17E is exact for float64
+    # Fortran list-directed output may wrap lines and use D exponents
+    with open(path, "w") as f:
+        f.write("\n".join("  %.15E" % v for v in H.ravel()).replace("E", "D"))
+    assert np.abs(restart.read_hessenberg(path, k) - H).max() < 1e-14
+
+
+def test_pressure_mesh_maps_are_inverse():
+    rng = np.random.default_rng(1)
+    for ldim, lx1 in ((2, 6), (3, 8), (3, 4)):
+        p2 = rng.standard_normal((5, (lx1 - 2) ** ldim))
+        p1 = restart.pressure_to_mesh1(p2, lx1, ldim)
+        assert p1.shape == (5, lx1 ** ldim)
+        assert np.abs(restart.pressure_to_mesh2(p1, lx1, ldim) - p2).max() < 1e-12
+
+
+def test_krylov_vector_file_round_trip(tmp_path):
+    assert restart.kry_filename("1cyl", 12) == "KRY1cyl0.f00012"
+    for name in ("box2d_n6_outflow", "box3d_n8_outflow"):
+        c = small_cases()[name]
+        rng = np.random.default_rng(2)
+        v = rng.standard_normal((c.ldim, c.nel, c.npts))
+        p = rng.standard_normal((c.nel, c.lx2 ** c.ldim))
+        path = str(tmp_path / restart.kry_filename(name, 3))
+        restart.write_krylov_vector(path, c, v, p, time=2.0, istep=2, wdsize=8)
+        v2, p2 = restart.read_krylov_vector(path, c)
+        assert np.array_equal(v2, v) and np.abs(p2 - p).max() < 1e-12
+        # a rank's share reads its own elements out of a file written in another element order
+        part = c.local_part(1, 2)
+        v3, p3 = restart.read_krylov_vector(path, part)
+        sel = part.lglel - 1
+        assert np.array_equal(v3, v[:, sel]) and np.abs(p3 - p[sel]).max() < 1e-12
+        # single precision files (writeDoublePrecision = no, 1cyl.par:20) lose digits but keep the layout
+        restart.write_krylov_vector(path, c, v, p, wdsize=4)
+        v4, _ = restart.read_krylov_vector(path, c)
+        assert np.abs(v4 - v).max() < 1e-6 * np.abs(v).max()

@@ -17,7 +17,8 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from nekstab_b200 import nekio  # noqa: E402
 
-REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
+_pos = [a for a in sys.argv[1:] if not a.startswith("--")]
+REF = _pos[0] if _pos else "/root/reference"
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 os.makedirs(OUT, exist_ok=True)
 
@@ -92,6 +93,17 @@ def bfs():
     print("bfs.npz", os.path.getsize(f"{OUT}/bfs.npz") / 1e6, "MB")
 
 
+def spectrum_text():
+    """First lines of the shipped spectrum files as TEXT: pins the '(3E15.7)' writer of nekstab_b200/restart.py byte for byte."""
+    d = f"{REF}/examples/cylinder/stability/direct"
+    for name in ("Spectre_Hd.dat", "Spectre_NSd.dat"):
+        lines = open(f"{d}/{name}").read().splitlines()[:24]
+        with open(f"{OUT}/{name.replace('.dat', '_head.dat')}", "w") as f:
+            f.write("\n".join(lines) + "\n")
+
+
 if __name__ == "__main__":
-    cyl()
-    bfs()
+    if "--spectrum-only" not in sys.argv:
+        cyl()
+        bfs()
+    spectrum_text()

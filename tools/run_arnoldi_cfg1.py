@@ -3,7 +3,8 @@
 (examples/cylinder/stability/direct as shipped: k_dim=200, schur_tgt=0, endTime 1, tol 1e-7/1e-9, sponge 5/5/1.7), i.e.
 `krylov_schur` of core/eigensolvers.f:141-388 with every matvec on the device.  Writes Spectre_Hd.dat / Spectre_NSd.dat /
 Spectre_NSd_conv.dat in the reference's format (core/eigensolvers.f:590-604) under gpurun_out/ and compares with the
-shipped spectra (tests/golden/cyl.npz).  Usage: python tools/run_arnoldi_cfg1.py [k_dim] [tol_p] [tol_v]"""
+shipped spectra (tests/golden/cyl.npz).
+Usage: python tools/run_arnoldi_cfg1.py [k_dim] [tol_p] [tol_v] [precond: pmg|jacobi] [mxprev]"""
 import json
 import os
 import sys
@@ -20,11 +21,16 @@ def main():
     k_dim = int(sys.argv[1]) if len(sys.argv) > 1 else 200
     tol_p = float(sys.argv[2]) if len(sys.argv) > 2 else 1e-7
     tol_v = float(sys.argv[3]) if len(sys.argv) > 3 else 1e-9
+    precond = sys.argv[4] if len(sys.argv) > 4 else "pmg"
+    mxprev = int(sys.argv[5]) if len(sys.argv) > 5 else 0
     g = np.load(os.path.join(ROOT, "tests", "golden", "cyl.npz"))
     c = cases.cylinder_case(g)
     t0 = time.time()
     ctx = lib.NekStabB200(c)
     ctx.set_params(1.0 / c.re, 1.0, tol_v, tol_p, 2000, 100000)
+    if precond == "pmg":
+        ctx.set_pressure_preconditioner(1, 64)
+    ctx.set_projection(mxprev)
     dt, nsteps, ctarg = ctx.prepare_linearized_solver(c.end_time)
     ctx.vec_alloc(k_dim + 3)
     # seed: noise -> normalise -> one matvec ("smoothing") -> normalise   (core/eigensolvers.f:222-278)
@@ -40,13 +46,13 @@ def main():
     lam = np.log(vals.astype(complex)) / tau
     out = os.path.join(ROOT, "gpurun_out")
     os.makedirs(out, exist_ok=True)
-    with open(os.path.join(out, "Spectre_Hd.dat"), "w") as f1, open(os.path.join(out, "Spectre_NSd.dat"), "w") as f2, \
-            open(os.path.join(out, "Spectre_NSd_conv.dat"), "w") as f3:
+    from nekstab_b200 import restart
+    restart.write_spectrum(os.path.join(out, "Spectre_Hd.dat"), vals, res)          # '(3E15.7)', core/eigensolvers.f:590-604
+    restart.write_spectrum(os.path.join(out, "Spectre_NSd.dat"), lam, res)
+    with open(os.path.join(out, "Spectre_NSd_conv.dat"), "w") as f3:
         for i in range(k_dim):
-            f1.write("%15.7E%15.7E%15.7E\n" % (vals[i].real, vals[i].imag, res[i]))
-            f2.write("%15.7E%15.7E%15.7E\n" % (lam[i].real, lam[i].imag, res[i]))
             if res[i] < 1e-6:
-                f3.write("%15.7E%15.7E\n" % (lam[i].real, lam[i].imag))
+                f3.write(restart.fortran_e(lam[i].real) + restart.fortran_e(lam[i].imag) + "\n")
     ref_h = g["Spectre_Hd"]
     ref_mu = ref_h[:, 0] + 1j * ref_h[:, 1]
     nconv_ref = int((ref_h[:, 2] < 1e-6).sum())
@@ -57,7 +63,7 @@ def main():
         errs.append(float(abs(vals[j] - m) / abs(m)))
     ref_lam = g["Spectre_NSd_conv"][0, 0] + 1j * g["Spectre_NSd_conv"][0, 1]
     jl = int(np.argmin(np.abs(lam - ref_lam)))
-    summary = {"case": "cylinder Re=50 direct (cfg 1)", "k_dim": k_dim, "nsteps": nsteps, "dt": dt, "tol_p": tol_p, "tol_v": tol_v,
+    summary = {"case": "cylinder Re=50 direct (cfg 1)", "pressure_preconditioner": precond, "residual_projection_mxprev": mxprev, "k_dim": k_dim, "nsteps": nsteps, "dt": dt, "tol_p": tol_p, "tol_v": tol_v,
                "matvecs": k_dim + 1, "time_steps": st["steps"], "wall_s_arnoldi": wall, "setup_s": t1 - t0,
                "pres_iters_per_step": st["pres_iters"] / max(st["steps"], 1), "helm_iters_per_step": st["helm_iters"] / max(st["steps"], 1),
                "converged_ritz_pairs(res<1e-6)": int(ncv), "reference_converged": nconv_ref,

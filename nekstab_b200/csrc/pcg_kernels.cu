@@ -622,7 +622,10 @@ struct AxCfg {
   static constexpr int TPB = (((NT > NP1) ? NT : NP1) + 31) / 32 * 32;
 };
 
-template <int N, int MODE>
+// PF: the six stiffness factors and bm1 of the element are fetched with cp.async into shared memory at kernel entry and
+// consumed two barriers later (r1d ncu: 8.6 long-scoreboard stall warps per issue, most of them at the G loads that sat
+// right behind a barrier).
+template <int N, int MODE, bool PF>
 __global__ void __launch_bounds__(AxCfg<N>::TPB, 2)
 k_axhelm3(const double* __restrict__ u, double* __restrict__ w, const double* __restrict__ b, const double* __restrict__ G,
           const double* __restrict__ bm1, const double* __restrict__ dinv, double* __restrict__ pdir, CGState* __restrict__ cgs,
@@ -645,6 +648,16 @@ k_axhelm3(const double* __restrict__ u, double* __restrict__ w, const double* __
     beta[f] = (MODE == 2 && f < nfields) ? cgs[f].beta : 0.0;
   }
   if (MODE == 2 && !(act[0] || act[1] || act[2])) return;
+  double* sG = dsm + 12 * S1::size;     // [7][NP1]: g1..g6, bm1 (PF only)
+  if (PF) {
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(sG);
+    for (int t = tid; t < 7 * NP1 / 2; t += AxCfg<N>::TPB) {
+      const int a = t / (NP1 / 2), w2 = t - a * (NP1 / 2);
+      const double* src = (a < 6 ? G + (long long)a * n : bm1) + e0 + 2 * w2;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + (unsigned)((a * NP1 + 2 * w2) * 8)), "l"(src) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
   double uo[3] = {0.0, 0.0, 0.0};
   if (tid < NP1) {
     const int o = S1::lin(tid);
@@ -677,13 +690,14 @@ k_axhelm3(const double* __restrict__ u, double* __restrict__ w, const double* __
     for (int l = 0; l < N; ++l) v[l] = pin[l * cstr];
     apply_store<N, N>(cm.D, v, sr + (tf * 3 + tdir) * S1::size + cbase, cstr);
   }
+  if (PF) asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   // ---- geometric factors, all fields of a point at once
   if (tid < NP1) {
     const int o = S1::lin(tid);
     double g[6];
 #pragma unroll
-    for (int q = 0; q < 6; ++q) g[q] = G[(long long)q * n + e0 + tid];
+    for (int q = 0; q < 6; ++q) g[q] = PF ? sG[q * NP1 + tid] : G[(long long)q * n + e0 + tid];
 #pragma unroll
     for (int f = 0; f < 3; ++f)
       if (act[f]) {
@@ -707,7 +721,7 @@ k_axhelm3(const double* __restrict__ u, double* __restrict__ w, const double* __
   double rho[3] = {0.0, 0.0, 0.0};
   if (tid < NP1) {
     const int o = S1::lin(tid);
-    const double bm = bm1[e0 + tid];
+    const double bm = PF ? sG[6 * NP1 + tid] : bm1[e0 + tid];
 #pragma unroll
     for (int f = 0; f < 3; ++f)
       if (act[f]) {
@@ -832,21 +846,33 @@ int pk_pcg_div(Ctx* c, int adj, int fused) {
   return 0;
 }
 
-template <int N>
-static constexpr size_t ax3_smem() { return sizeof(double) * 12 * Shp<N, N, N>::size; }
+template <int N, bool PF>
+static constexpr size_t ax3_smem() { return sizeof(double) * (12 * Shp<N, N, N>::size + (PF ? 7 * N * N * N : 0)); }
+
+template <int N, bool PF>
+static int launch_axhelm3(Ctx* c, int mode, const double* u, double* w, const double* b, int nfields, double h1, double h2) {
+  constexpr size_t sm = ax3_smem<N, PF>();
+  if (mode == 0) {
+    NSB_TRY(set_smem(k_axhelm3<N, 0, PF>, sm));
+    k_axhelm3<N, 0, PF><<<c->nel, AxCfg<N>::TPB, sm, c->stream>>>(u, w, nullptr, c->G, c->bm1, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                                                   nullptr, 0, nfields, c->n, h1, h2);
+  } else if (mode == 1) {
+    NSB_TRY(set_smem(k_axhelm3<N, 1, PF>, sm));
+    k_axhelm3<N, 1, PF><<<c->nel, AxCfg<N>::TPB, sm, c->stream>>>(u, w, b, c->G, c->bm1, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                                                   0, nfields, c->n, h1, h2);
+  } else {
+    NSB_TRY(set_smem(k_axhelm3<N, 2, PF>, sm));
+    k_axhelm3<N, 2, PF><<<c->nel, AxCfg<N>::TPB, sm, c->stream>>>(c->rk, c->wk[2], nullptr, c->G, c->bm1, c->dinvH, c->wk[1], c->cgs,
+                                                                   c->red_part, c->red_count, c->red_out, c->nranks == 1, nfields, c->n,
+                                                                   h1, h2);
+  }
+  return 0;
+}
 
 int pk_axhelm(Ctx* c, int mode, const double* u, double* w, const double* b, int nfields, double h1, double h2) {
-  if (mode == 0) {
-    DISPATCH_N(c, NSB_TRY(set_smem(k_axhelm3<N, 0>, ax3_smem<N>())); k_axhelm3<N, 0><<<c->nel, AxCfg<N>::TPB, ax3_smem<N>(), c->stream>>>(
-                      u, w, nullptr, c->G, c->bm1, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nfields, c->n, h1, h2));
-  } else if (mode == 1) {
-    DISPATCH_N(c, NSB_TRY(set_smem(k_axhelm3<N, 1>, ax3_smem<N>())); k_axhelm3<N, 1><<<c->nel, AxCfg<N>::TPB, ax3_smem<N>(), c->stream>>>(
-                      u, w, b, c->G, c->bm1, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nfields, c->n, h1, h2));
-  } else {
-    DISPATCH_N(c, NSB_TRY(set_smem(k_axhelm3<N, 2>, ax3_smem<N>())); k_axhelm3<N, 2><<<c->nel, AxCfg<N>::TPB, ax3_smem<N>(), c->stream>>>(
-                      c->rk, c->wk[2], nullptr, c->G, c->bm1, c->dinvH, c->wk[1], c->cgs, c->red_part, c->red_count, c->red_out,
-                      c->nranks == 1, nfields, c->n, h1, h2));
-  }
+  static const bool pf = [] { const char* e = getenv("NSB_AX_PREFETCH"); return !(e && e[0] == '0'); }();
+  if (pf) DISPATCH_N(c, NSB_TRY((launch_axhelm3<N, true>(c, mode, u, w, b, nfields, h1, h2))));
+  else DISPATCH_N(c, NSB_TRY((launch_axhelm3<N, false>(c, mode, u, w, b, nfields, h1, h2))));
   nsb_count_launch();
   NSB_CUDA(cudaGetLastError());
   return 0;

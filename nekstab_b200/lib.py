@@ -103,6 +103,10 @@ _SIGS = {
     "nsb_gs_host_candidates": [C.c_int, C.c_int, C.c_int, _lp, _lp, _lp],
     "nsb_gs_host_plan": [C.c_int, C.c_int, _lp, _lp, _ip],
     "nsb_gs_host_get": [C.c_int, _ip],
+    "nsb_pm_host_aggregates": [C.c_int, C.c_int, _dp, C.c_int, _ip],
+    "nsb_pm_host_colouring": [C.c_int, C.c_int, _lp, _ip, _ip],
+    "nsb_pm_host_fdm_1d": [C.c_int, C.c_double, C.c_double, _dp, _dp],
+    "nsb_pm_host_spd_inverse": [C.c_int, _dp],
     "nsb_arnoldi_factorization": [C.c_int, C.c_int, _dp, C.c_int, C.c_int, C.c_int, C.c_int],
     "nsb_krylov_schur": [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, _dp, _dp, _dp, _dp, _ip, _ip, C.c_int],
     "nsb_schur_condensation": [_ip, _dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double],

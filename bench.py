@@ -331,6 +331,18 @@ def main():
                                            "frac": iter_words * 8.0 * n_loc / (iter_ms * 1e-3) / 1e9 / peak, "ms": iter_ms,
                                            "share_of_step": iter_ms * st["pres_iters"] / max(st["step_ms"], 1e-9)},
                     "kernels": kern}
+        if roof:
+            # whole-step roofline: algorithmic bytes of everything a step executes (SURVEY 8d W_step with the measured iteration
+            # counts; the advection's HBM traffic = the fine-mesh metrics + fields) over the measured device time per step
+            ip, ih = st["pres_iters"] / K, st["helm_iters"] / K / 3
+            iter_w = sum(WORDS.get(k, 0.0) for k in ("pcg_gradt", "dssum", "pcg_div", "pcg_update")) + \
+                (sum(WORDS[k] for k in ("pcg_pc_restrict", "pcg_pc_coarse", "pcg_pc_apply")) if args.precond == "pmg" else 0.0)
+            helm_w = WORDS["hcg_axhelm"] + WORDS["hcg_dssum"] + WORDS["hcg_update"]
+            other_w = 39.4 + 26.0 + 20.6 + 15.0                     # ADV + RHS + RES + PCOR
+            step_words = ip * iter_w + ih * helm_w + other_w
+            step_gbs = step_words * 8.0 * n_loc / (dev_ms / K * 1e-3) / 1e9
+            roof["step"] = {"alg_words_per_point": step_words, "alg_GBs": step_gbs, "frac": step_gbs / peak,
+                            "note": "algorithmic bytes of the whole time step / device time per step (this rank's points)"}
         line = {"metric": "linearized-NS DOF*timesteps/s", "value": value, "unit": "DOF*steps/s", "n_gpus": world, "steps": K,
                 "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",

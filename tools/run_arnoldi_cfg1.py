@@ -4,7 +4,9 @@
 `krylov_schur` of core/eigensolvers.f:141-388 with every matvec on the device.  Writes Spectre_Hd.dat / Spectre_NSd.dat /
 Spectre_NSd_conv.dat in the reference's format (core/eigensolvers.f:590-604) under gpurun_out/ and compares with the
 shipped spectra (tests/golden/cyl.npz).
-Usage: python tools/run_arnoldi_cfg1.py [k_dim] [tol_p] [tol_v] [precond: pmg|jacobi] [mxprev]"""
+Usage: python tools/run_arnoldi_cfg1.py [k_dim] [tol_p] [tol_v] [precond: pmg|jacobi] [mxprev] [direct|adjoint]
+`adjoint` runs examples/cylinder/stability/adjoint (uparam(1) = 3.2, outflow 'O' -> 'v' masks, 1cyl.usr:126-132) and compares
+with the shipped Spectre_Ha.dat."""
 import json
 import os
 import sys
@@ -23,6 +25,9 @@ def main():
     tol_v = float(sys.argv[3]) if len(sys.argv) > 3 else 1e-9
     precond = sys.argv[4] if len(sys.argv) > 4 else "pmg"
     mxprev = int(sys.argv[5]) if len(sys.argv) > 5 else 0
+    which = sys.argv[6] if len(sys.argv) > 6 else "direct"
+    mode = lib.ADJOINT if which == "adjoint" else lib.DIRECT
+    tag = "a" if which == "adjoint" else "d"
     g = np.load(os.path.join(ROOT, "tests", "golden", "cyl.npz"))
     c = cases.cylinder_case(g)
     t0 = time.time()
@@ -36,10 +41,10 @@ def main():
     # seed: noise -> normalise -> one matvec ("smoothing") -> normalise   (core/eigensolvers.f:222-278)
     ctx.vec_upload(k_dim + 1, cases.add_noise(c), None)
     ctx.normalize(k_dim + 1)
-    ctx.matvec(lib.DIRECT, k_dim + 1, 0)
+    ctx.matvec(mode, k_dim + 1, 0)
     ctx.normalize(0)
     t1 = time.time()
-    vals, res, V, ncv, scnt = ctx.krylov_schur(lib.DIRECT, k_dim, 0, eigen_tol=1e-6, schur_del=0.1, seed_slot=0)
+    vals, res, V, ncv, scnt = ctx.krylov_schur(mode, k_dim, 0, eigen_tol=1e-6, schur_del=0.1, seed_slot=0)
     wall = time.time() - t1
     st = ctx.stats()
     tau = dt * nsteps
@@ -47,13 +52,13 @@ def main():
     out = os.path.join(ROOT, "gpurun_out")
     os.makedirs(out, exist_ok=True)
     from nekstab_b200 import restart
-    restart.write_spectrum(os.path.join(out, "Spectre_Hd.dat"), vals, res)          # '(3E15.7)', core/eigensolvers.f:590-604
-    restart.write_spectrum(os.path.join(out, "Spectre_NSd.dat"), lam, res)
-    with open(os.path.join(out, "Spectre_NSd_conv.dat"), "w") as f3:
+    restart.write_spectrum(os.path.join(out, f"Spectre_H{tag}.dat"), vals, res)          # '(3E15.7)', core/eigensolvers.f:590-604
+    restart.write_spectrum(os.path.join(out, f"Spectre_NS{tag}.dat"), lam, res)
+    with open(os.path.join(out, f"Spectre_NS{tag}_conv.dat"), "w") as f3:
         for i in range(k_dim):
             if res[i] < 1e-6:
                 f3.write(restart.fortran_e(lam[i].real) + restart.fortran_e(lam[i].imag) + "\n")
-    ref_h = g["Spectre_Hd"]
+    ref_h = g["Spectre_Ha"] if which == "adjoint" else g["Spectre_Hd"]
     ref_mu = ref_h[:, 0] + 1j * ref_h[:, 1]
     nconv_ref = int((ref_h[:, 2] < 1e-6).sum())
     # match converged reference Ritz values to ours (nearest neighbour)
@@ -61,9 +66,10 @@ def main():
     for m in ref_mu[:min(nconv_ref, 12)]:
         j = int(np.argmin(np.abs(vals - m)))
         errs.append(float(abs(vals[j] - m) / abs(m)))
-    ref_lam = g["Spectre_NSd_conv"][0, 0] + 1j * g["Spectre_NSd_conv"][0, 1]
+    conv = g["Spectre_NSa_conv"] if which == "adjoint" else g["Spectre_NSd_conv"]
+    ref_lam = conv[0, 0] + 1j * conv[0, 1]
     jl = int(np.argmin(np.abs(lam - ref_lam)))
-    summary = {"case": "cylinder Re=50 direct (cfg 1)", "pressure_preconditioner": precond, "residual_projection_mxprev": mxprev, "k_dim": k_dim, "nsteps": nsteps, "dt": dt, "tol_p": tol_p, "tol_v": tol_v,
+    summary = {"case": f"cylinder Re=50 {which} (cfg 1)", "pressure_preconditioner": precond, "residual_projection_mxprev": mxprev, "k_dim": k_dim, "nsteps": nsteps, "dt": dt, "tol_p": tol_p, "tol_v": tol_v,
                "matvecs": k_dim + 1, "time_steps": st["steps"], "wall_s_arnoldi": wall, "setup_s": t1 - t0,
                "pres_iters_per_step": st["pres_iters"] / max(st["steps"], 1), "helm_iters_per_step": st["helm_iters"] / max(st["steps"], 1),
                "converged_ritz_pairs(res<1e-6)": int(ncv), "reference_converged": nconv_ref,
@@ -72,7 +78,7 @@ def main():
                "rel_err_leading_lambda": float(abs(lam[jl] - ref_lam) / abs(ref_lam)),
                "rel_err_first_converged_ritz_values": errs, "leading_residual": float(res[0]),
                "dof_steps_per_s": c.n * st["steps"] / (st["step_ms"] * 1e-3)}
-    with open(os.path.join(out, "arnoldi_cfg1_summary.json"), "w") as f:
+    with open(os.path.join(out, f"arnoldi_cfg1_{which}_summary.json"), "w") as f:
         json.dump(summary, f, indent=1)
     print(json.dumps(summary, indent=1))
     ctx.close()

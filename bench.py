@@ -126,36 +126,57 @@ def workload_iters(precond="jacobi"):
         return (2500, 22) if precond == "jacobi" else (141, 22)
 
 
-def cpu_reference(nsteps: int, nwarm: int, max_seconds: float = 240.0, precond: str = "jacobi"):
-    """Times the CPU oracle port (oracle/stepper.py, PCG mode = the algorithm the GPU path runs, same preconditioner) on a
-    bounded sample of the workload: a compact patch of the same lx1=8 3-D mesh, each step forced to the
-    per-step Helmholtz / pressure iteration counts measured on the GPU for the full workload
-    (profiles/workload_iters.json), so the work per grid point per step matches.  Returns DOF*steps/s."""
-    from oracle.ops import SEM
-    from oracle.stepper import LinearizedStepper
-    try:
-        from threadpoolctl import threadpool_info
-        thr = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
-    except Exception:
-        thr = os.cpu_count() or 1
+def _cpu_sample(n2d: int, nz: int):
+    """A compact patch of the bench mesh: the first n2d elements of the 2-D cylinder mesh in RSB key order x nz layers."""
     g = np.load(os.path.join(ROOT, "tests", "golden", "cyl.npz"))
     c2 = cases.cylinder_case(g, lx1=8, sponge=False)
-    order = np.argsort(c2.key, kind="stable")[:48]               # RSB key order => spatially compact patch
+    order = np.argsort(c2.key, kind="stable")[:n2d]               # RSB key order => spatially compact patch
     sub = c2.local_part(0, 1)
     sel = np.sort(order)
     sub.nel, sub.xyz, sub.glo, sub.mask = sel.size, c2.xyz[:, sel], c2.glo[sel], c2.mask[:, sel]
     sub.key, sub.ubase = c2.key[sel], c2.ubase[:, sel]
     sub.glo = cases._compress(sub.glo)
     sub.extra = {}
-    c3 = cases.extrude(sub, 2, 2 * np.pi / 5.0)
-    s = SEM(3, 8, c3.xyz, c3.glo, c3.mask)
+    return cases.extrude(sub, nz, 2 * np.pi * nz / 10.0)
+
+
+def cpu_reference(nsteps: int, nwarm: int, max_seconds: float = 240.0, precond: str = "jacobi"):
+    """Times the CPU restatement of the step (same algorithm and preconditioner as the GPU path) on a bounded sample of the
+    workload: a compact patch of the same lx1=8 3-D mesh, each step forced to the per-step Helmholtz / pressure iteration
+    counts measured on the GPU for the full workload (profiles/workload_iters.json), so the work per grid point per step
+    matches.  Preferred: the C / OpenMP port (oracle/cport.c, all host cores, 1 996 elements = 1.02e6 points, out of cache);
+    fallback when gcc is unavailable: the numpy port on 96 elements.  Returns DOF*steps/s."""
+    from oracle.ops import SEM
     ip, iv = workload_iters(precond)
-    pc = None
-    if precond == "pmg":
-        from oracle.pmg import PMG
-        pc = PMG(s, nagg=max(1, c3.nel // 32))
-    st = LinearizedStepper(s, c3.ubase, c3.re, None, tol_v=0.0, tol_p=0.0, solver="pcg", max_iter_v=iv, max_iter_p=ip, ifvcor=False,
-                           pressure_precond=pc)
+    try:
+        from oracle import cport
+        thr = cport.set_threads(0)
+        c3 = _cpu_sample(499, 4)
+        s = SEM(3, 8, c3.xyz, c3.glo, c3.mask)
+        pc = None
+        if precond == "pmg":
+            from oracle.pmg import PMG
+            cp0 = cport.CPort(s, None)
+            pc = PMG(s, nagg=max(1, c3.nel // 32), apply_e=lambda p: cp0.cdabdtp(p).reshape(s.eshape2))
+        st = cport.CStepper(s, c3.ubase, c3.re, None, tol_v=0.0, tol_p=0.0, max_iter_v=iv, max_iter_p=ip, ifvcor=False, pmg=pc)
+        port = "C/OpenMP port (oracle/cport.c)"
+    except Exception as exc:                                          # no compiler on this host: numpy port, small sample
+        from oracle.stepper import LinearizedStepper
+        sys.stderr.write(f"cpu_reference: C port unavailable ({exc}); using the numpy port\n")
+        try:
+            from threadpoolctl import threadpool_info
+            thr = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+        except Exception:
+            thr = os.cpu_count() or 1
+        c3 = _cpu_sample(48, 2)
+        s = SEM(3, 8, c3.xyz, c3.glo, c3.mask)
+        pc = None
+        if precond == "pmg":
+            from oracle.pmg import PMG
+            pc = PMG(s, nagg=max(1, c3.nel // 32))
+        st = LinearizedStepper(s, c3.ubase, c3.re, None, tol_v=0.0, tol_p=0.0, solver="pcg", max_iter_v=iv, max_iter_p=ip, ifvcor=False,
+                               pressure_precond=pc)
+        port = "numpy/scipy oracle port"
     v = cases.add_noise(c3).reshape((3,) + s.eshape)
     p = np.zeros(s.eshape2)
     dt = 0.5 / s.cfl_sum(c3.ubase.reshape((3,) + s.eshape))
@@ -172,10 +193,10 @@ def cpu_reference(nsteps: int, nwarm: int, max_seconds: float = 240.0, precond: 
             break
     tstep = float(np.mean(t_steps))
     value = c3.n / tstep
-    sample = (f"{c3.nel} hexahedra (48-element patch of the cylinder mesh x 2 layers, lx1=8, n={c3.n}); "
-              f"{len(t_steps)} timed step(s) after {min(nwarm, done - len(t_steps))} warm-up, each forced to {ip} pressure-CG and "
-              f"{iv} Helmholtz-CG iterations/component (the full workload's GPU-measured per-step counts, preconditioner: {precond}); "
-              f"numpy/scipy oracle port")
+    sample = (f"{c3.nel} hexahedra (compact {c3.nel // (4 if c3.nel > 500 else 2)}-element patch of the cylinder mesh x "
+              f"{4 if c3.nel > 500 else 2} layers, lx1=8, n={c3.n}); {len(t_steps)} timed step(s) after "
+              f"{min(nwarm, done - len(t_steps))} warm-up, each forced to {ip} pressure-CG and {iv} Helmholtz-CG iterations/component "
+              f"(the full workload's GPU-measured per-step counts, preconditioner: {precond}); {port}, {thr} threads")
     return value, tstep, thr, sample, c3.n
 
 

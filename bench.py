@@ -238,8 +238,9 @@ def main():
         print(json.dumps(line))
         return
 
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"     # the box sets VERSION: NCCL would print its banner on stdout before the JSON line
+    # NCCL writes its debug output (the "NCCL version ..." banner at NCCL_DEBUG >= VERSION) to stdout: keep stdout for the one
+    # JSON line and send NCCL's output to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as dist
     from nekstab_b200 import lib

@@ -19,7 +19,6 @@
 // CPU restatement: oracle/pmg.py (tests/test_gpu_pmg.py compares M^-1 r, solutions and iteration counts).
 #include <algorithm>
 #include <cmath>
-#include <map>
 #include <numeric>
 
 #include "elem_common.cuh"

@@ -451,8 +451,8 @@ int vk_multidot(Ctx* c, int k, int first_slot, int slot_f, double* h_dev) {
 
 // out[i] = a*f[i] + sign * sum_j h_j Q_j[i] over the whole vector (velocity and pressure)
 __global__ void __launch_bounds__(256)
-k_multiaxpy(const double* __restrict__ Q, long long vlen, int k, const double* __restrict__ f, double a,
-            const double* __restrict__ h, double sign, double* __restrict__ out) {
+k_multiaxpy(const double* __restrict__ Q, long long vlen, int k, const double* f, double a,
+            const double* __restrict__ h, double sign, double* out) {      // f and out may be the same vector: no __restrict__
   extern __shared__ double sh[];
   for (int j = threadIdx.x; j < k; j += blockDim.x) sh[j] = sign * h[j];
   __syncthreads();

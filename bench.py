@@ -240,6 +240,9 @@ def main():
 
     # NCCL writes its debug output (the "NCCL version ..." banner at NCCL_DEBUG >= VERSION) to stdout: keep stdout for the one
     # JSON line and send NCCL's output to stderr
+    # (NCCL honours NCCL_DEBUG_FILE only above the VERSION level, so a bare VERSION setting is dropped instead)
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        del os.environ["NCCL_DEBUG"]
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as dist

@@ -2,7 +2,6 @@
 per field), where the oracle is too slow to serve as the checker: averaging projector of the gather-scatter, symmetry and
 positivity of E and of the pressure preconditioner, the converged pressure solve, linearity of the matvec, orthonormality
 of the Gram-Schmidt step.  Everything goes through the C ABI."""
-import os
 import sys
 
 import numpy as np

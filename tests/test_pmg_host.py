@@ -7,7 +7,7 @@ import pytest
 import scipy.linalg as sla
 
 from nekstab_b200 import cases, lib
-from util import GOLD, make_oracle, small_cases
+from util import GOLD, small_cases
 
 
 @pytest.fixture(scope="module")

@@ -1,5 +1,5 @@
 """Scratch study 2 (CPU, oracle): cheap multilevel additive variants for the pressure preconditioner."""
-import sys, os, time
+import sys, os
 import numpy as np, scipy.sparse as sp, scipy.sparse.linalg as spla, scipy.linalg as sla
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from nekstab_b200 import cases

@@ -1,6 +1,6 @@
 """Scratch study 3 (CPU, oracle): overlapping (depth-1) FDM Schwarz on the extended (lx2+2)^2 grid vs the non-overlapping blocks."""
-import sys, os, time
-import numpy as np, scipy.sparse as sp, scipy.sparse.linalg as spla, scipy.linalg as sla
+import sys, os
+import numpy as np, scipy.linalg as sla
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from nekstab_b200 import cases
 from oracle.ops import SEM

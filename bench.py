@@ -82,7 +82,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([t.strip() for t in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.05)
 
     def summary(self):
         if not self.rows:

@@ -43,9 +43,14 @@ def rcb_aggregates(cent: np.ndarray, nagg: int) -> np.ndarray:
 
 
 class PMG:
-    def __init__(self, s: SEM, agg: np.ndarray | None = None, nagg: int = 0, ifvcor: bool = False, apply_e=None):
-        """apply_e: callable p -> E p on element-shaped arrays (default: s.cdabdtp)."""
+    def __init__(self, s: SEM, agg: np.ndarray | None = None, nagg: int = 0, ifvcor: bool = False, apply_e=None, q1_cycle=None):
+        """apply_e: callable p -> E p on element-shaped arrays (default: s.cdabdtp).
+        q1_cycle = (nu, omega): PROTOTYPE of the next coarse-level design (tools/precond_study5.py; not in the CUDA
+        path yet): the Q1 level becomes a symmetric V-cycle on the assembled A_c = P^T E P (nu damped-Jacobi sweeps before and
+        after an exact solve on vertex aggregates) instead of one Jacobi sweep + the element-aggregate level."""
         self.s = s
+        self.q1_cycle = q1_cycle
+        self.ifvcor = bool(ifvcor)
         d, nel, L1, L2 = s.ldim, s.nel, s.lx1, s.lx2
         self.apply_e = apply_e or s.cdabdtp
         X = s.X                                              # (d, nel, [k,] j, i)
@@ -131,6 +136,8 @@ class PMG:
             A2 = A2 + np.trace(A2) / self.nagg ** 2
         self.A2 = A2
         self.A2inv = np.zeros_like(A2) if (ifvcor and self.nagg == 1) else np.linalg.inv(A2)
+        if q1_cycle is not None:
+            self._setup_q1_cycle()
 
     # ------------------------------------------------------------------ pieces
     def restrict_q1(self, r):
@@ -178,6 +185,64 @@ class PMG:
         self.ncolours = int(col.max()) + 1
         return d1
 
+    # ------------------------------------------------------------------ prototype: Q1 V-cycle (see __init__)
+    def _neighbourhoods(self):
+        nv = self.nv
+        adj = [set() for _ in range(nv)]
+        for row in self.vid:
+            for a in row:
+                adj[a].update(int(x) for x in row)
+        n2 = [set().union(*(adj[u] for u in adj[v])) for v in range(nv)]          # graph distance <= 2
+        return adj, n2
+
+    def _setup_q1_cycle(self):
+        """Assemble A_c = P^T E P column by column: vertices of one colour are more than 4 apart (distance-4 colouring), so the
+        columns probed together (support: distance <= 2) do not overlap; vertex aggregates = aggregate of the first element
+        holding the vertex; A2v = P2^T A_c P2 solved exactly (constant shifted when E is singular)."""
+        import scipy.sparse as sp
+        nv = self.nv
+        _, n2 = self._neighbourhoods()
+        col = -np.ones(nv, dtype=np.int64)
+        for v in range(nv):
+            forb = set()
+            for u in n2[v]:
+                for t in n2[u]:
+                    if col[t] >= 0:
+                        forb.add(int(col[t]))
+            c = 0
+            while c in forb:
+                c += 1
+            col[v] = c
+        self.ncolours4 = int(col.max()) + 1
+        rows, cols, vals = [], [], []
+        for c in range(self.ncolours4):
+            xv = (col == c).astype(float)
+            y = self._assemble_v(self.restrict_q1(self.apply_e(self.prolong_q1(xv[self.vid]))))
+            for v in np.flatnonzero(col == c):
+                for w in n2[v]:
+                    rows.append(w); cols.append(v); vals.append(y[w])
+        A = sp.coo_matrix((vals, (rows, cols)), shape=(nv, nv)).tocsr()
+        self.Ac = (0.5 * (A + A.T)).tocsr()
+        self.dAc = self.Ac.diagonal()
+        vagg = np.zeros(nv, dtype=np.int64)
+        for e in range(self.s.nel - 1, -1, -1):
+            vagg[self.vid[e]] = self.agg[e]
+        self.P2 = sp.coo_matrix((np.ones(nv), (np.arange(nv), vagg)), shape=(nv, self.nagg)).tocsr()
+        A2v = (self.P2.T @ self.Ac @ self.P2).toarray()
+        if self.ifvcor:
+            A2v = A2v + np.trace(A2v) / self.nagg ** 2
+        self.A2vinv = np.zeros_like(A2v) if (self.ifvcor and self.nagg == 1) else np.linalg.inv(A2v)
+
+    def _q1_vcycle(self, rc):
+        nu, om = self.q1_cycle
+        x = np.zeros_like(rc)
+        for _ in range(nu):
+            x = x + om * (rc - self.Ac @ x) / self.dAc
+        x = x + self.P2 @ (self.A2vinv @ (self.P2.T @ (rc - self.Ac @ x)))
+        for _ in range(nu):
+            x = x + om * (rc - self.Ac @ x) / self.dAc
+        return x
+
     def fdm(self, r):
         d = self.s.ldim
         t = r
@@ -191,6 +256,9 @@ class PMG:
     def apply(self, r):
         """z = M^-1 r on element-shaped mesh-2 arrays."""
         rc = self.restrict_q1(r)
+        if self.q1_cycle is not None:
+            xv = self._q1_vcycle(self._assemble_v(rc))
+            return self.fdm(r) + self.prolong_q1(xv[self.vid])
         xv = self._assemble_v(rc) / self.d1
         x2 = self.A2inv @ np.bincount(self.agg, weights=rc.sum(1), minlength=self.nagg)
         shp = [self.s.nel] + [1] * self.s.ldim

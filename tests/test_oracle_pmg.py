@@ -70,3 +70,32 @@ def test_cylinder_iteration_count():
     x, it = pmg.pcg(ae, M.apply, b, 1e-8)
     assert it < 260, it
     assert np.linalg.norm((ae(x) - b).ravel()) <= 1.01e-8 * np.linalg.norm(b.ravel())
+
+
+def test_q1_vcycle_prototype():
+    """Prototype of the next coarse-level design: assembled P^T E P by distance-4 probing equals the Galerkin
+    matrix, the resulting operator is symmetric positive definite and needs fewer iterations than the additive coarse levels."""
+    from nekstab_b200 import cases
+    from oracle import pmg
+    c = CASES["box2d_n6_outflow"]
+    s = make_oracle(c)
+    M = pmg.PMG(s, nagg=3, q1_cycle=(1, 0.7))
+    for v in (0, M.nv // 2, M.nv - 1):                       # columns of the probed matrix = E applied to a single hat
+        xv = np.zeros(M.nv); xv[v] = 1.0
+        col = M._assemble_v(M.restrict_q1(s.cdabdtp(M.prolong_q1(xv[M.vid]))))
+        assert np.abs(M.Ac[:, v].toarray().ravel() - col).max() < 1e-10 * np.abs(col).max()
+    rng = np.random.default_rng(2)
+    a, b = rng.standard_normal(s.eshape2), rng.standard_normal(s.eshape2)
+    za, zb = M.apply(a), M.apply(b)
+    assert abs(np.sum(a * zb) - np.sum(b * za)) < 1e-10 * np.linalg.norm(a) * np.linalg.norm(zb)
+    assert np.sum(a * za) > 0
+    cyl = cases.cylinder_case(np.load(GOLD + "/cyl.npz"), sponge=False)
+    sc = make_oracle(cyl)
+    E = sc.e_sparse().tocsr()
+    ae = lambda p: (E @ p.ravel()).reshape(p.shape)
+    u = rng.standard_normal((2,) + sc.eshape)
+    u = np.stack([sc.dssum(u[k]) * sc.mult * sc.mask[k] for k in range(2)])
+    rhs = -sc.opdiv(u)
+    it_add = pmg.pcg(ae, pmg.PMG(sc, nagg=64, apply_e=ae).apply, rhs, 1e-8)[1]
+    it_cyc = pmg.pcg(ae, pmg.PMG(sc, nagg=64, apply_e=ae, q1_cycle=(1, 0.7)).apply, rhs, 1e-8)[1]
+    assert it_cyc < 0.9 * it_add, (it_cyc, it_add)

@@ -75,7 +75,9 @@ int nsb_set_projection(int mxprev);
  * 1cyl.par:28; [UPSTREAM] hsmg.f): element blocks by fast diagonalisation + Jacobi on the Q1 space of the element-vertex
  * mesh + an exactly solved problem on `nagg` element aggregates (0 = automatic: nelv/32, at most 512).  Changes the
  * iteration count (measured 2 787 -> 206 on the cylinder mesh), not the converged pressure.  Rebuilt automatically when
- * nsb_set_adjoint_masks changes the adjoint operator.  Environment NSB_PRECOND=1 selects kind 1 at nsb_init. */
+ * nsb_set_adjoint_masks changes the adjoint operator.  Environment NSB_PRECOND=1 selects kind 1 at nsb_init.
+ * kind 2 (EXPERIMENTAL, single GPU, not yet validated on hardware): as kind 1 with the vertex-mesh level replaced by a V-cycle on
+ * the assembled P^T E P (CPU prototype: oracle/pmg.py `q1_cycle`; 201 -> 169 iterations on the cylinder mesh). */
 int nsb_set_pressure_preconditioner(int kind, int nagg);
 
 /* ------------------------------------------------------------------ krylov_vector algebra

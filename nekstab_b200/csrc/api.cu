@@ -270,6 +270,7 @@ extern "C" int nsb_set_adjoint_masks(const double* m0, const double* m1, const d
   c->has_adj_masks = true;
   NSB_CUDA(cudaStreamSynchronize(c->stream));
   if (c->pc_kind) NSB_TRY(pm_setup(c, 1, c->pc_nagg));
+  if (c->pc_kind == 2) NSB_TRY(pm_setup_vcycle(c, 1));
   return 0;
 }
 
@@ -329,7 +330,7 @@ extern "C" int nsb_set_projection(int mxprev) {
 }
 extern "C" int nsb_set_pressure_preconditioner(int kind, int nagg) {
   REQUIRE_CTX();
-  if (kind != 0 && kind != 1) { nsb_set_error("nsb_set_pressure_preconditioner: kind must be 0 (Jacobi) or 1 (pmg)"); return 1; }
+  if (kind < 0 || kind > 2) { nsb_set_error("nsb_set_pressure_preconditioner: kind must be 0 (Jacobi), 1 (pmg) or 2 (experimental)"); return 1; }
   if (nagg < 0 || nagg > 512) { nsb_set_error("nsb_set_pressure_preconditioner: nagg must be in [0, 512]"); return 1; }
   drop_graphs(c);
   c->pc_kind = 0;
@@ -342,7 +343,11 @@ extern "C" int nsb_set_pressure_preconditioner(int kind, int nagg) {
   c->pc_nagg = nagg;
   NSB_TRY(pm_setup(c, 0, nagg));
   if (c->has_adj_masks) NSB_TRY(pm_setup(c, 1, nagg));     // separate adjoint masks => a different E => its own factors
-  c->pc_kind = 1;
+  if (kind == 2) {                                          // experimental Q1 V-cycle on top of the kind-1 set-up
+    NSB_TRY(pm_setup_vcycle(c, 0));
+    if (c->has_adj_masks) NSB_TRY(pm_setup_vcycle(c, 1));
+  }
+  c->pc_kind = kind;
   return 0;
 }
 extern "C" int nsb_op_pc_apply(int adjoint, const double* r, double* z) {

@@ -115,6 +115,16 @@ struct PMG {
   double *rc = nullptr, *xv = nullptr, *ra = nullptr, *x2 = nullptr;   // work: corner sums, vertex values, aggregate sums/values
   std::vector<int> h_agg;
   std::vector<double> h_d1, h_A2inv;
+  // EXPERIMENTAL (kind 2, single rank, not yet validated on a GPU): Q1 level as a V-cycle on the assembled A_c = P^T E P
+  bool vc_ready = false;
+  int vc_ncolours = 0;
+  int *vc_off = nullptr, *vc_col = nullptr;   // CSR of A_c (rows = local vertices)
+  double* vc_val = nullptr;
+  double* vc_odinv = nullptr;                 // omega / diag(A_c)
+  int* vc_vagg = nullptr;                     // vertex -> aggregate
+  int *vc_aoff = nullptr, *vc_aent = nullptr; // CSR aggregate -> vertices
+  double* vc_A2inv = nullptr;                 // (P2^T A_c P2)^-1
+  double *vc_rv = nullptr, *vc_x = nullptr, *vc_r1 = nullptr;   // work [nv]
 };
 
 struct Ctx {
@@ -321,6 +331,7 @@ int vk_rotate(Ctx* c, int k, int first_slot, const double* S_dev, int lds);
 
 // ---- pressure preconditioner (pmg.cu)
 int pm_setup(Ctx* c, int set, int nagg_req);
+int pm_setup_vcycle(Ctx* c, int set);
 int pm_apply(Ctx* c, int set, const double* r, double* z, int mode, int prof_slot = 0);
 void pm_free(PMG& m);
 int vk_cg_finalize_multi(Ctx* c, CGState* s, int ncomp, int kind);

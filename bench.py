@@ -392,8 +392,11 @@ def main():
             except Exception:
                 pass
         if world == 1 and not args.no_cpu_baseline:
-            cv, ct, thr, sample, _ = cpu_reference(1, 0, max_seconds=60.0, precond=args.precond)
-            line["cpu_baseline"] = {"value": cv, "unit": "DOF*steps/s", "cores": thr, "kind": "port", "sample": sample}
+            try:
+                cv, ct, thr, sample, _ = cpu_reference(1, 0, max_seconds=60.0, precond=args.precond)
+                line["cpu_baseline"] = {"value": cv, "unit": "DOF*steps/s", "cores": thr, "kind": "port", "sample": sample}
+            except Exception as exc:      # the GPU line must be printed whatever happens to the CPU leg
+                line["cpu_baseline"] = {"value": None, "unit": "DOF*steps/s", "cores": 0, "kind": "port", "sample": f"failed: {exc}"}
         print(json.dumps(line))
     ctx.close()
     if world > 1:

@@ -121,6 +121,22 @@ def main():
                 if k in mine_vals and mine_vals[k] != v:
                     bad.append((name, "not bit-identical across ranks", k))
                     break
+        # ---- the same plan code on the element-VERTEX mesh (lx1 = 2): the gather-scatter of the pressure preconditioner's Q1
+        #      level across GPUs (csrc/pmg.cu builds it with gs_build(.., N1 = 2, ..) from the corner ids)
+        from types import SimpleNamespace
+        N = gc.lx1 - 1
+        G = gc.glo.reshape((gc.nel,) + (gc.lx1,) * gc.ldim)
+        nk = 2 ** gc.ldim
+        vg = np.stack([G[(slice(None),) + tuple(N * ((k >> (gc.ldim - 1 - a)) & 1) for a in range(gc.ldim))] for k in range(nk)], axis=1)
+        vc = SimpleNamespace(ldim=gc.ldim, lx1=2, nel=sel.size, glo=np.ascontiguousarray(vg[sel]))
+        vplan = get_plan(L, lib, vc, rank, world, dist, torch)
+        rc_g = rng.standard_normal((1, gc.nel * nk))                       # one value per (element, corner) entry
+        vref = np.bincount(vg.ravel(), weights=rc_g[0], minlength=vg.max() + 1)[vg.ravel()]
+        rc_l = rc_g.reshape(1, gc.nel, nk)[:, sel].reshape(1, -1)
+        vgot = emulate_dssum(vplan, rc_l, 1, rank, dist, torch)
+        verr = np.abs(vgot[0] - vref.reshape(gc.nel, nk)[sel].ravel()).max()
+        if not verr < 1e-12:
+            bad.append((name, "vertex dssum", verr))
     t = torch.tensor([len(bad)])
     dist.all_reduce(t)
     if bad:

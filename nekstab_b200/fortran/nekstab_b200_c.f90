@@ -135,5 +135,27 @@
         import :: c_int
         integer(c_int), value :: mode, slot_in, slot_out
       end function
+      integer(c_int) function nsb_vec_norm(p, alpha) bind(C, name='nsb_vec_norm')
+        import :: c_int, c_double
+        integer(c_int), value :: p
+        real(c_double) :: alpha
+      end function
+      integer(c_int) function nsb_nonlinear_forward_map(slot_q, slot_f) bind(C, name='nsb_nonlinear_forward_map')
+        import :: c_int
+        integer(c_int), value :: slot_q, slot_f
+      end function
+      integer(c_int) function nsb_prepare_solver_from_slot(slot, endt, cfl, dt, nsteps, ctarg) &
+          bind(C, name='nsb_prepare_solver_from_slot')
+        import :: c_int, c_double
+        integer(c_int), value :: slot
+        real(c_double), value :: endt, cfl
+        real(c_double) :: dt, ctarg
+        integer(c_int) :: nsteps
+      end function
+      integer(c_int) function nsb_basis_gemv_complex(k, first, yre, yim, slot_re, slot_im) bind(C, name='nsb_basis_gemv_complex')
+        import :: c_int, c_double
+        integer(c_int), value :: k, first, slot_re, slot_im
+        real(c_double) :: yre(*), yim(*)
+      end function
       end interface
       end module nekstab_b200_c

@@ -55,6 +55,16 @@
       if (uparam(1) .eq. 2.1) alpha = alpha + p%time * q%time
       end subroutine
 
+      subroutine krylov_norm(alpha, p)                    ! :58
+      use nekstab_b200_c
+      use krylov_subspace
+      implicit none
+      type(krylov_vector), intent(in) :: p
+      real, intent(out) :: alpha
+      call nsb_b200_check(nsb_vec_norm(p%slot, alpha), 'krylov_norm')
+      if (uparam(1) .eq. 2.1) alpha = sqrt(alpha**2 + p%time**2)
+      end subroutine
+
       subroutine krylov_normalize(p, alpha)               ! :71
       use nekstab_b200_c
       use krylov_subspace
@@ -158,4 +168,38 @@
       if (floor(uparam(1)) .eq. 2) then; evop = 'n'; mode = NSB_NEWTON; init = .false.; endif
       call nsb_b200_check(nsb_matvec(mode, q%slot, f%slot), 'matvec')
       f%time = 0.0d0
+      end subroutine
+
+      subroutine nonlinear_forward_map(f, q)             ! core/newton_krylov.f:336-378
+      use nekstab_b200_c
+      use krylov_subspace
+      implicit none
+      include 'SIZE'
+      include 'TOTAL'
+      type(krylov_vector) :: f, q
+      integer(c_int) :: nst
+      real(c_double) :: ddt, ct
+      ! newton_krylov re-prepares the solver on every iterate (core/newton_krylov.f:69): CFL of the current q
+      call nsb_b200_check(nsb_prepare_solver_from_slot(q%slot, param(10), param(26), ddt, nst, ct), 'prepare_linearized_solver')
+      dt = ddt; nsteps = nst; ctarg = ct; param(12) = -abs(dt)
+      call nsb_b200_check(nsb_nonlinear_forward_map(q%slot, f%slot), 'nonlinear_forward_map')   ! f = phi_T(q) - q ; ubase <- q
+      f%time = 0.0d0
+      end subroutine
+
+!     Host mirror <-> device slot, to be called at the field-access sites listed in SURVEY.md 8b (seeding from vxp.., load_files,
+!     outpost of KRY / mode files, arnoldi_checkpoint): the Fortran members vx,vy,vz,pr stay the I/O view of the vector.
+      subroutine krylov_to_device(p)
+      use nekstab_b200_c
+      use krylov_subspace
+      implicit none
+      type(krylov_vector) :: p
+      call nsb_b200_check(nsb_vec_upload(p%slot, p%vx, p%vy, p%vz, p%pr), 'krylov_to_device')
+      end subroutine
+
+      subroutine krylov_to_host(p)
+      use nekstab_b200_c
+      use krylov_subspace
+      implicit none
+      type(krylov_vector) :: p
+      call nsb_b200_check(nsb_vec_download(p%slot, p%vx, p%vy, p%vz, p%pr), 'krylov_to_host')
       end subroutine

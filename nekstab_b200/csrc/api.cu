@@ -484,11 +484,23 @@ extern "C" int nsb_orthonormalize(int k, int first, int slot_f, double* hcol) {
   double* h1 = c->hbuf;
   double* h2 = c->hbuf + (1 << 15);
   std::vector<double> a(k), b(k);
+  const bool pr = c->prof_on != 0;                          // sampling profiler: kinds 11 (multidot) and 12 (multiaxpy)
+  if (pr) cudaEventRecord(c->prof_ev[16], c->stream);
   NSB_TRY(vk_multidot(c, k, first, slot_f, h1));            // h1 = Q^T W f
+  if (pr) cudaEventRecord(c->prof_ev[17], c->stream);
   NSB_TRY(vk_multiaxpy(c, k, first, slot_f, h1, -1.0));     // f -= Q h1
+  if (pr) cudaEventRecord(c->prof_ev[18], c->stream);
   NSB_TRY(vk_multidot(c, k, first, slot_f, h2));            // re-orthogonalisation (DGKS)
+  if (pr) cudaEventRecord(c->prof_ev[19], c->stream);
   NSB_TRY(vk_multiaxpy(c, k, first, slot_f, h2, -1.0));
+  if (pr) cudaEventRecord(c->prof_ev[20], c->stream);
   NSB_TRY(d2h(c, a.data(), h1, k));
+  if (pr) {
+    for (int i = 0; i < 4; ++i) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, c->prof_ev[16 + i], c->prof_ev[17 + i]) == cudaSuccess) { c->prof_ms[11 + (i & 1)] += ms; c->prof_cnt[11 + (i & 1)] += 1; }
+    }
+  }
   NSB_TRY(d2h(c, b.data(), h2, k));
   for (int i = 0; i < k; ++i) {
     hcol[i] = a[i] + b[i];
@@ -567,12 +579,12 @@ extern "C" int nsb_get_stats(nsb_stats* out, int reset) {
 extern "C" int nsb_profile(int enable, double* ms_sum, long long* count) {
   REQUIRE_CTX();
   if (enable > 0 && !c->prof_ev[0])
-    for (int i = 0; i < 16; ++i) NSB_CUDA(cudaEventCreate(&c->prof_ev[i]));
-  if (ms_sum) for (int i = 0; i < 12; ++i) ms_sum[i] = c->prof_ms[i];
-  if (count) for (int i = 0; i < 12; ++i) count[i] = c->prof_cnt[i];
+    for (int i = 0; i < 24; ++i) NSB_CUDA(cudaEventCreate(&c->prof_ev[i]));
+  if (ms_sum) for (int i = 0; i < 16; ++i) ms_sum[i] = c->prof_ms[i];
+  if (count) for (int i = 0; i < 16; ++i) count[i] = c->prof_cnt[i];
   if (enable >= 0) {
     c->prof_on = enable;
-    for (int i = 0; i < 12; ++i) { c->prof_ms[i] = 0; c->prof_cnt[i] = 0; }
+    for (int i = 0; i < 16; ++i) { c->prof_ms[i] = 0; c->prof_cnt[i] = 0; }
   }
   return 0;
 }
@@ -686,6 +698,10 @@ extern "C" int nsb_get_field(const char* name, double* out, long long* count) {
     src = c->G + (long long)q * c->n;
   } else if (s == "ifvcor") {
     if (out) out[0] = c->ifvcor[0] ? 1.0 : 0.0;
+    if (count) *count = 1;
+    return 0;
+  } else if (s == "p2p") {          // 1: NVLink peer-memory data plane (csrc/p2p.cu), 0: NCCL / single rank
+    if (out) out[0] = c->p2p.on ? 1.0 : 0.0;
     if (count) *count = 1;
     return 0;
   } else if (s == "vol") {

@@ -236,9 +236,9 @@ struct Ctx {
 
   // per-kernel sampling profiler (CUDA events on the launching stream; one sample set per host poll)
   int prof_on = 0;
-  cudaEvent_t prof_ev[16] = {nullptr};
-  double prof_ms[12] = {0};
-  long long prof_cnt[12] = {0};
+  cudaEvent_t prof_ev[24] = {nullptr};
+  double prof_ms[16] = {0};
+  long long prof_cnt[16] = {0};
 
   // stats
   nsb_stats stats = {0, 0, 0, 0, 0.0};

@@ -51,7 +51,7 @@ int p2p_free(Ctx* c, P2P& p) {
   for (int r = 0; r < c->nranks; ++r)
     if (r != c->rank && p.peer[r]) cudaIpcCloseMemHandle(p.peer[r]);
   cudaFree(p.arena); cudaFree(p.d_peer_dst); cudaFree(p.d_peer_flag); cudaFree(p.d_nbr_rank); cudaFree(p.d_err);
-  cudaFree(p.d_send_nbr); cudaFree(p.d_send_j); cudaFree(p.d_cnt);
+  cudaFree(p.d_send_nbr); cudaFree(p.d_send_j); cudaFree(p.d_cnt); cudaFree(p.d_peer_base);
   p = P2P();
   return 0;
 }
@@ -59,15 +59,34 @@ int p2p_free(Ctx* c, P2P& p) {
 // called at the end of gs_setup (multi-rank); send_nbr/send_j: neighbour index and position of every send entry
 int p2p_setup(Ctx* c, P2P& p, const GSMap& m, const std::vector<int>& send_nbr, const std::vector<int>& send_j) {
   const char* env = getenv("NSB_P2P");
-  if (c->nranks <= 1 || c->nranks > 16 || (env && env[0] == '0')) return 0;
+  if (c->nranks <= 1 || c->nranks > 16) return 0;         // the same on every rank
   const int R = c->nranks;
-  // every peer must be reachable
-  for (int r = 0; r < R; ++r) {
+  // The decision "peer-memory path usable" must be identical on all ranks, or some would enter the collectives below while
+  // others fall back to NCCL: exchange the real device ordinals (CUDA_VISIBLE_DEVICES may remap them: a peer's ordinal is
+  // not its rank), test peer access locally, then take the MINIMUM of the local verdicts over the communicator.
+  int* d_dev = nullptr;
+  NSB_CUDA(cudaMalloc(&d_dev, sizeof(int) * (R + 1)));
+  NSB_CUDA(cudaMemcpy(d_dev + R, &c->device, sizeof(int), cudaMemcpyHostToDevice));
+  NSB_NCCL(ncclAllGather(d_dev + R, d_dev, 1, ncclInt32, c->comm, c->stream));
+  NSB_CUDA(cudaStreamSynchronize(c->stream));
+  std::vector<int> devs(R);
+  NSB_CUDA(cudaMemcpy(devs.data(), d_dev, sizeof(int) * R, cudaMemcpyDeviceToHost));
+  int ok = (env && env[0] == '0') ? 0 : 1;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess) ok = 0;
+  for (int r = 0; r < R && ok; ++r) {
     if (r == c->rank) continue;
     int can = 0;
-    // device ordinals = local ranks on one node (one process per GPU)
-    if (cudaDeviceCanAccessPeer(&can, c->device, r) != cudaSuccess || !can) return 0;   // fall back to NCCL
+    // one process per GPU on ONE node: the peer's ordinal must be visible here and distinct from ours
+    if (devs[r] < 0 || devs[r] >= ndev || devs[r] == c->device) { ok = 0; break; }
+    if (cudaDeviceCanAccessPeer(&can, c->device, devs[r]) != cudaSuccess || !can) ok = 0;
   }
+  NSB_CUDA(cudaMemcpy(d_dev, &ok, sizeof(int), cudaMemcpyHostToDevice));
+  NSB_NCCL(ncclAllReduce(d_dev, d_dev, 1, ncclInt32, ncclMin, c->comm, c->stream));
+  NSB_CUDA(cudaStreamSynchronize(c->stream));
+  NSB_CUDA(cudaMemcpy(&ok, d_dev, sizeof(int), cudaMemcpyDeviceToHost));
+  cudaFree(d_dev);
+  if (!ok) return 0;                                       // every rank falls back to NCCL together
   // allgather nshared and the table "where does rank q receive data from rank r" (in doubles, -1: not a neighbour)
   std::vector<long long> mine(R + 1, -1), all((size_t)R * (R + 1));
   for (int i = 0; i < m.nnbr; ++i) mine[m.nbr_rank[i]] = 3LL * m.nbr_off[i];

@@ -254,10 +254,10 @@ class NekStabB200:
         return {k: getattr(s, k) for k, _ in Stats._fields_}
 
     PROFILE_KINDS = ["pcg_gradt", "dssum", "pcg_div", "pcg_update", "hcg_axhelm", "hcg_update", "advab", "hcg_dssum",
-                     "pcg_pc_restrict", "pcg_pc_coarse", "pcg_pc_apply"]
+                     "pcg_pc_restrict", "pcg_pc_coarse", "pcg_pc_apply", "orth_multidot", "orth_multiaxpy"]
 
     def profile(self, enable=-1):
-        ms = np.zeros(12); cnt = np.zeros(12, dtype=np.int64)
+        ms = np.zeros(16); cnt = np.zeros(16, dtype=np.int64)
         _ck(self.lib.nsb_profile(enable, _p(ms), _p(cnt)))
         return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.PROFILE_KINDS)}
 

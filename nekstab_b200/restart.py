@@ -48,7 +48,10 @@ def write_spectrum(path: str, vals: np.ndarray, residual: np.ndarray) -> None:
 def log_transform(vals: np.ndarray, tau: float) -> np.ndarray:
     """Eigenvalues of the linearised Navier-Stokes operator from those of exp(tau L) (core/eigensolvers.f:908-915)."""
     vals = np.asarray(vals, dtype=complex)
-    return (np.log(np.abs(vals)) + 1j * np.arctan2(vals.imag, vals.real)) / tau
+    out = (np.log(np.abs(vals)) + 1j * np.arctan2(vals.imag, vals.real)) / tau
+    # `if (aimag(x) .eq. 0) logx = cmplx(real(logx), 0)` (:912-913): a negative real Ritz value gets imaginary part 0, not pi/tau
+    out.imag[vals.imag == 0.0] = 0.0
+    return out
 
 
 def kry_filename(session: str, i: int, prefix: str = "KRY") -> str:
@@ -96,14 +99,54 @@ def pressure_to_mesh2(p1: np.ndarray, lx1: int, ldim: int) -> np.ndarray:
     return _interp_tensor(a, J, ldim).reshape(a.shape[0], -1)
 
 
-def write_krylov_vector(path: str, case, v: np.ndarray, p: np.ndarray, *, time: float = 0.0, istep: int = 0, wdsize: int = 8) -> None:
-    """One Krylov vector as a Nek field file (velocity + pressure on mesh 1), element order = the case's local order."""
+class GatherComm:
+    """Host plumbing for multi-rank checkpoints: `rank`, `world` and `gather(obj)` -> list of every rank's object on rank 0
+    (None elsewhere).  `from_torch()` wraps an initialised torch.distributed group; in a drop-in the reference's own `outpost`
+    does this gather over MPI [UPSTREAM prepost.f]."""
+
+    def __init__(self, rank: int, world: int, gather):
+        self.rank, self.world, self.gather = rank, world, gather
+
+    @staticmethod
+    def from_torch():
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+
+        def gather(obj):
+            out = [None] * world if rank == 0 else None
+            dist.gather_object(obj, out, dst=0)
+            return out
+        return GatherComm(rank, world, gather)
+
+
+def _is_partial(case) -> bool:
+    return case.nelg is not None and int(case.nelg) != int(case.nel)
+
+
+def write_krylov_vector(path: str, case, v: np.ndarray, p: np.ndarray, *, time: float = 0.0, istep: int = 0, wdsize: int = 8,
+                        comm: "GatherComm | None" = None) -> None:
+    """One Krylov vector as ONE global Nek field file (velocity + pressure on mesh 1), like the reference's `outpost`: element
+    order = rank-major, ascending global id within a rank, `nelg` = the global element count.  A case that holds
+    only one rank's share of the mesh needs `comm` (every rank calls; rank 0 writes); without it this raises instead of writing
+    a truncated file that `read_krylov_vector` would later accept."""
     d, nel, L = case.ldim, case.nel, case.lx1
     shp = (nel,) + ((L,) * 3 if d == 3 else (1, L, L))
     U = np.asarray(v, float).reshape(d, nel, -1).transpose(1, 0, 2).reshape((nel, d) + shp[1:])
     P = pressure_to_mesh1(np.asarray(p, float).reshape(nel, -1), L, d).reshape(shp)
-    elmap = case.lglel if case.lglel is not None else np.arange(1, nel + 1)
-    nekio.write_field(path, U=U, P=P, time=time, istep=istep, wdsize=wdsize, elmap=np.asarray(elmap, dtype=np.int32))
+    elmap = np.asarray(case.lglel if case.lglel is not None else np.arange(1, nel + 1), dtype=np.int32)
+    if _is_partial(case):
+        if comm is None:
+            raise ValueError(f"write_krylov_vector: the case holds {nel} of {case.nelg} elements (one rank's share); pass comm= "
+                             "(restart.GatherComm) so that rank 0 can write one global file")
+        parts = comm.gather((elmap, U, P))
+        if comm.rank != 0:
+            return
+        elmap = np.concatenate([q[0] for q in parts])
+        U = np.concatenate([q[1] for q in parts])
+        P = np.concatenate([q[2] for q in parts])
+        if elmap.size != int(case.nelg) or np.unique(elmap).size != elmap.size:
+            raise ValueError(f"write_krylov_vector: gathered {elmap.size} elements, expected {case.nelg} distinct ones")
+    nekio.write_field(path, U=U, P=P, time=time, istep=istep, wdsize=wdsize, elmap=elmap)
 
 
 def read_krylov_vector(path: str, case) -> Tuple[np.ndarray, np.ndarray]:
@@ -124,15 +167,19 @@ def read_krylov_vector(path: str, case) -> Tuple[np.ndarray, np.ndarray]:
 
 
 def arnoldi_checkpoint(ctx, case, session: str, H: np.ndarray, k: int, slot: int, *, outdir: str = ".", evop: str = "d",
-                       tau: float = 1.0, eigen_tol: float = 1e-6, wdsize: int = 8) -> int:
+                       tau: float = 1.0, eigen_tol: float = 1e-6, wdsize: int = 8, comm: "GatherComm | None" = None) -> int:
     """core/eigensolvers.f:802-905: write Krylov vector k+1 (device slot `slot`), the spectra of H(1:k,1:k) and H itself.
-    Returns the number of Ritz pairs with residual |H(k+1,k) y_k| below eigen_tol (the count the reference logs)."""
+    Returns the number of Ritz pairs with residual |H(k+1,k) y_k| below eigen_tol (the count the reference logs).
+    Multi-rank: every rank calls with `comm`; the KRY file is gathered into one global file and, like the reference
+    (`if (nid .eq. 0)` :866-889), only rank 0 writes the HES and Spectre files."""
     v, p = ctx.vec_download(slot)
-    write_krylov_vector(os.path.join(outdir, kry_filename(session, k + 1)), case, v, p, time=tau * k, istep=k, wdsize=wdsize)
+    write_krylov_vector(os.path.join(outdir, kry_filename(session, k + 1)), case, v, p, time=tau * k, istep=k, wdsize=wdsize, comm=comm)
     vals, vecs = np.linalg.eig(H[:k, :k])
     order = np.argsort(-np.abs(vals), kind="stable")          # `eig` sorts by decreasing magnitude (core/lapack_wrapper.f:129)
     vals, vecs = vals[order], vecs[:, order]
     residual = np.abs(H[k, k - 1] * vecs[k - 1, :])
+    if comm is not None and comm.rank != 0:
+        return int(np.count_nonzero(residual < eigen_tol))
     write_spectrum(os.path.join(outdir, "Spectre_H%s%04d.dat" % (evop, k)), vals, residual)
     write_spectrum(os.path.join(outdir, "Spectre_NS%s%04d.dat" % (evop, k)), log_transform(vals, tau), residual)
     write_hessenberg(os.path.join(outdir, hes_filename(session, k)), H, k)

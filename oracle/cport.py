@@ -223,7 +223,13 @@ class CStepper:
         self.ifvcor = bool(ifvcor)
         self.iters_v, self.iters_p = [], []
 
-    def linearized_map(self, v, p, nsteps, dt):
+    def linearized_map(self, v, p, nsteps, dt, budget_s=None):
+        """nsteps of the direct perturbation stepper from (v, p), order ramp restarted (core/matvec.f:216).  budget_s: stop
+        after that many seconds of wall time (at a step boundary, at least one step); self.steps_done / self.step_seconds
+        report what ran -- used by bench.py to bound the CPU baseline."""
+        import time as _time
+        t_start = _time.perf_counter()
+        self.steps_done, self.step_seconds = 0, []
         cp, lib = self.cp, self.cp.lib
         n, n2 = cp.n, cp.n2
         u = _c(v).reshape(3, n).copy()
@@ -233,6 +239,9 @@ class CStepper:
         plag = np.zeros(n2)
         b, r, w3 = np.zeros((3, n)), np.zeros((3, n)), np.zeros((3, n))
         for istep in range(1, nsteps + 1):
+            t_step = _time.perf_counter()
+            if budget_s is not None and istep > 1 and t_step - t_start > budget_s:
+                break
             k = min(istep, 3)
             bd, ab = np.array(BD[k] + [0.0] * 3), np.array(AB[k] + [0.0] * 3)
             h2 = BD[k][0] / dt
@@ -266,4 +275,6 @@ class CStepper:
             flag = [f, flag[0]]
             plag = pr
             u, pr = unew, pnew
+            self.steps_done += 1
+            self.step_seconds.append(_time.perf_counter() - t_step)
         return u, pr

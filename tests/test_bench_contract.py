@@ -6,6 +6,8 @@ import os
 import subprocess
 import sys
 
+import pytest
+
 from util import ROOT
 
 
@@ -30,8 +32,29 @@ def test_reference_arm_prints_one_json_line():
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "hexahedra" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "DOF*steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+    # the CPU arm runs to tolerance and reports its own measured iteration counts (no forced counts)
+    assert d["config"]["pres_iters_per_step"] > 0 and d["config"]["helm_iters_per_comp_per_step"] > 0
+    assert "forced" not in cb["sample"] and "solvers run to tol" in cb["sample"]
+    assert d["config"]["workload"] == "cyl3d_1996x10_lx8" and d["config"]["elements"] == 19960      # = the GPU arm's workload name
 
 
 def test_reference_arm_other_ranks_stay_silent():
     out = _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
     assert out.strip() == ""
+
+
+@pytest.mark.gpu
+def test_gpu_and_cpu_arms_do_the_same_work_on_the_small_mesh():
+    """on the same (small) mesh, seed, dt, tolerances and steps the CPU arm's measured iteration counts must
+    agree with the GPU arm's (same algorithm, same preconditioner): within 10 %."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--small", "--steps", "3", "--warmup", "2", "--arnoldi", "0",
+                        "--cpu-seconds", "150"], capture_output=True, text=True, timeout=1500, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-3000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.strip()][-1])
+    cb = d["cpu_baseline"]
+    assert cb["value"] and cb["steps_done"] == 3, cb
+    gp, cp = d["config"]["pres_iters_per_step"], cb["pres_iters_per_step"]
+    gh, ch = d["config"]["helm_iters_per_comp_per_step"], cb["helm_iters_per_comp_per_step"]
+    assert abs(gp - cp) <= 0.10 * cp, (gp, cp)
+    assert abs(gh - ch) <= 0.10 * ch, (gh, ch)
+    assert d["gpu_launches"] > 0 and d["e2e"]["value"] > 0 and d["roofline"]["frac"] > 0

@@ -1,7 +1,8 @@
 """Size-independent properties at BASELINE.json's full single-GPU size (config 5: 19 960 hexahedra, lx1 = 8, 1.02e7 points
 per field), where the oracle is too slow to serve as the checker: averaging projector of the gather-scatter, symmetry and
 positivity of E and of the pressure preconditioner, the converged pressure solve, linearity of the matvec, orthonormality
-of the Gram-Schmidt step.  Everything goes through the C ABI."""
+of the Gram-Schmidt step.  Everything goes through the C ABI.  (The oracle comparison of the cfg-5 matvec itself lives in
+tests/test_gpu_cfg5_oracle.py.)"""
 import sys
 
 import numpy as np
@@ -17,7 +18,7 @@ def full():
     sys.path.insert(0, ROOT)
     import bench
     from nekstab_b200 import lib
-    case, n_glob = bench.build_workload(1, 0, small=False)
+    case, n_glob = bench.build_workload(10)
     assert case.nel == 19960 and n_glob == 19960 * 512
     g = lib.NekStabB200(case)
     g.set_params(1.0 / case.re, 1.0, 1e-10, 1e-10, 2000, 100000)
@@ -99,3 +100,4 @@ def test_matvec_is_linear_and_gram_schmidt_orthonormal(full):
         for j in range(i + 1):
             ip = g.inner_product(i, j)
             assert abs(ip - (1.0 if i == j else 0.0)) < 1e-12, (i, j, ip)
+

@@ -52,8 +52,14 @@ def test_linearized_maps(name):
         g.matvec(lib.NEWTON, 0, 1)
         v, p = g.vec_download(1)
         assert energy_rel(s, v.reshape(v1.shape), v1 - v0) < 1e-9
+        # ts_force_sensitivity_map: f = (I - exp(TL+)) q   (core/matvec.f:357-373, uparam(1) = 4.3)
+        g.matvec(lib.FORCE_SENS, 0, 1)
+        v, p = g.vec_download(1)
+        va, pa = st.linearized_map(v0, p0, nsteps, dt, adjoint=True)
+        assert energy_rel(s, v.reshape(va.shape), v0 - va) < 1e-9
+        assert rel(p, p0 - pa) < 1e-6
         st_ = g.stats()
-        assert st_["steps"] == 5 * nsteps and st_["kernel_launches"] > 0
+        assert st_["steps"] == 6 * nsteps and st_["kernel_launches"] > 0
     finally:
         g.close()
 

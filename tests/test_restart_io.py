@@ -3,6 +3,7 @@
 import os
 
 import numpy as np
+import pytest
 
 from nekstab_b200 import restart
 from util import GOLD, small_cases
@@ -75,3 +76,47 @@ def test_krylov_vector_file_round_trip(tmp_path):
         restart.write_krylov_vector(path, c, v, p, wdsize=4)
         v4, _ = restart.read_krylov_vector(path, c)
         assert np.abs(v4 - v).max() < 1e-6 * np.abs(v).max()
+
+
+def test_log_transform_negative_real_ritz_value_has_zero_imaginary_part():
+    """core/eigensolvers.f:908-915: `if (aimag(x) .eq. 0) log_transform = real(log_transform)` -- not pi/tau."""
+    lam = restart.log_transform(np.array([-0.5 + 0j, 0.5 + 0j, -0.5 + 1e-30j, 0.3 - 0.4j]), 2.0)
+    assert lam[0].imag == 0.0 and abs(lam[0].real - np.log(0.5) / 2.0) < 1e-15
+    assert lam[1].imag == 0.0
+    assert abs(lam[2].imag - np.pi / 2.0) < 1e-12            # a (tiny) non-zero imaginary part keeps the principal value
+    assert abs(lam[3] - np.log(0.3 - 0.4j) / 2.0) < 1e-15
+
+
+def test_partial_case_needs_a_communicator(tmp_path):
+    """a rank's share must not be written as if it were the whole mesh (the last writer used to win)."""
+    c = small_cases()["box2d_n6_outflow"]
+    part = c.local_part(0, 2)
+    v = np.zeros((c.ldim, part.nel, c.npts)); p = np.zeros((part.nel, c.lx2 ** c.ldim))
+    with pytest.raises(ValueError, match="comm="):
+        restart.write_krylov_vector(str(tmp_path / "KRYx0.f00001"), part, v, p)
+
+
+def test_multirank_checkpoint_gathers_one_global_file(tmp_path):
+    """Two ranks' shares gathered through restart.GatherComm into ONE file with nelg = the global count, rank-major element
+    order (the reference's `outpost` layout); each share and the global case read their elements back."""
+    c = small_cases()["box3d_n8_outflow"]
+    rng = np.random.default_rng(7)
+    v = rng.standard_normal((c.ldim, c.nel, c.npts))
+    p = rng.standard_normal((c.nel, c.lx2 ** c.ldim))
+    parts = [c.local_part(r, 2) for r in range(2)]
+    sels = [q.lglel - 1 for q in parts]
+    box = []                                                     # in-process stand-in for gather_object: rank 1 calls first
+    path = str(tmp_path / restart.kry_filename("box", 2))
+    for r in (1, 0):
+        def gather(obj, r=r):
+            box.append((r, obj))
+            return [o for _, o in sorted(box, key=lambda t: t[0])] if r == 0 else None
+        restart.write_krylov_vector(path, parts[r], v[:, sels[r]], p[sels[r]], comm=restart.GatherComm(r, 2, gather))
+    from nekstab_b200 import nekio
+    ff = nekio.read_field(path)
+    assert ff.nel == c.nel and list(ff.elmap) == list(np.concatenate([q.lglel for q in parts]))
+    v2, p2 = restart.read_krylov_vector(path, c)
+    assert np.array_equal(v2, v) and np.abs(p2 - p).max() < 1e-12
+    for r in range(2):
+        v3, p3 = restart.read_krylov_vector(path, parts[r])
+        assert np.array_equal(v3, v[:, sels[r]])

@@ -26,6 +26,10 @@ def main():
     precond = sys.argv[4] if len(sys.argv) > 4 else "pmg"
     mxprev = int(sys.argv[5]) if len(sys.argv) > 5 else 0
     which = sys.argv[6] if len(sys.argv) > 6 else "direct"
+    print(json.dumps(run(k_dim, tol_p, tol_v, precond, mxprev, which), indent=1))
+
+
+def run(k_dim=200, tol_p=1e-7, tol_v=1e-9, precond="pmg", mxprev=0, which="direct", tag_suffix=""):
     mode = lib.ADJOINT if which == "adjoint" else lib.DIRECT
     tag = "a" if which == "adjoint" else "d"
     g = np.load(os.path.join(ROOT, "tests", "golden", "cyl.npz"))
@@ -52,9 +56,9 @@ def main():
     out = os.path.join(ROOT, "gpurun_out")
     os.makedirs(out, exist_ok=True)
     from nekstab_b200 import restart
-    restart.write_spectrum(os.path.join(out, f"Spectre_H{tag}.dat"), vals, res)          # '(3E15.7)', core/eigensolvers.f:590-604
-    restart.write_spectrum(os.path.join(out, f"Spectre_NS{tag}.dat"), lam, res)
-    with open(os.path.join(out, f"Spectre_NS{tag}_conv.dat"), "w") as f3:
+    restart.write_spectrum(os.path.join(out, f"Spectre_H{tag}{tag_suffix}.dat"), vals, res)          # '(3E15.7)', core/eigensolvers.f:590-604
+    restart.write_spectrum(os.path.join(out, f"Spectre_NS{tag}{tag_suffix}.dat"), lam, res)
+    with open(os.path.join(out, f"Spectre_NS{tag}{tag_suffix}_conv.dat"), "w") as f3:
         for i in range(k_dim):
             if res[i] < 1e-6:
                 f3.write(restart.fortran_e(lam[i].real) + restart.fortran_e(lam[i].imag) + "\n")
@@ -78,10 +82,11 @@ def main():
                "rel_err_leading_lambda": float(abs(lam[jl] - ref_lam) / abs(ref_lam)),
                "rel_err_first_converged_ritz_values": errs, "leading_residual": float(res[0]),
                "dof_steps_per_s": c.n * st["steps"] / (st["step_ms"] * 1e-3)}
-    with open(os.path.join(out, f"arnoldi_cfg1_{which}_summary.json"), "w") as f:
+    summary["ritz_values_first_24"] = [[float(v.real), float(v.imag), float(r)] for v, r in zip(vals[:24], res[:24])]
+    with open(os.path.join(out, f"arnoldi_cfg1_{which}{tag_suffix}_summary.json"), "w") as f:
         json.dump(summary, f, indent=1)
-    print(json.dumps(summary, indent=1))
     ctx.close()
+    return summary
 
 
 if __name__ == "__main__":

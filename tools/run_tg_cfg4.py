@@ -20,6 +20,10 @@ def main():
     k_dim = int(sys.argv[1]) if len(sys.argv) > 1 else 64
     schur_tgt = int(sys.argv[2]) if len(sys.argv) > 2 else 2
     precond = sys.argv[3] if len(sys.argv) > 3 else "pmg"
+    print(json.dumps(run(k_dim, schur_tgt, precond), indent=1))
+
+
+def run(k_dim=64, schur_tgt=2, precond="pmg"):
     g = np.load(os.path.join(ROOT, "tests", "golden", "bfs.npz"))
     c = cases.bfs_case(g)
     t0 = time.time()
@@ -57,8 +61,8 @@ def main():
                "cos(optimal perturbation, shipped pRe)": cosang}
     with open(os.path.join(out, "tg_cfg4_summary.json"), "w") as f:
         json.dump(summary, f, indent=1)
-    print(json.dumps(summary, indent=1))
     ctx.close()
+    return summary
 
 
 if __name__ == "__main__":

@@ -107,6 +107,13 @@ int nsb_orthonormalize(int k, int first_slot, int slot_f, double* hcol);
  * sum_i (yre(i), yim(i)) * Q(first+i) */
 int nsb_basis_gemv_complex(int k, int first_slot, const double* yre, const double* yim, int slot_re, int slot_im);
 
+/* ------------------------------------------------------------------ direct / adjoint mode post-processing (BASELINE config 3)
+ * biorthogonalize (core/sensitivity.f:428-504): direct mode (slots dre, dim) scaled to unit norm, adjoint mode (are, aim)
+ * rotated / scaled so that <a, d> = 1 in the bm1s inner product; in place on the device-resident modes.
+ * wave_maker (core/sensitivity.f:7-81): bi-orthonormalise, then wavemaker(x) = |u_direct(x)| |u_adjoint(x)| (n values, host). */
+int nsb_biorthogonalize(int slot_dre, int slot_dim, int slot_are, int slot_aim);
+int nsb_wave_maker(int slot_dre, int slot_dim, int slot_are, int slot_aim, double* wavemaker);
+
 /* ------------------------------------------------------------------ matvec (core/matvec.f:64-159) */
 enum {
   NSB_DIRECT = 1,          /* forward_linearized_map   uparam(1) in [3.0,3.2)  core/matvec.f:163 */

@@ -402,6 +402,23 @@ def bfs_case(g: dict, sponge: bool = True) -> Case:
     return case
 
 
+def cavity_case(g: dict) -> Case:
+    """Config 3: examples/lid_driven (Re = 3600 `viscosity = -3600` cav.par:28, endTime 0.5 cav.par:4, tol 1e-9/1e-9, k_dim 90 cav.par:8,
+    schur_tgt 4 cav.usr:22; lid 'v' at the top face, walls 'W' elsewhere => all-Dirichlet velocity, singular E).  `g` =
+    tests/golden/cav.npz.  The coordinates are those of the shipped base flow (y in [0, 1.2]; cav.par:9 / cav.usr:107-109 would
+    rescale to 1.5 -- SURVEY.md cfg-3 caveat: the fixture is kept as shipped so that U is a solution ON ITS OWN mesh).  No sponge."""
+    lx1 = int(g["lx1"])
+    X = g["X"].reshape(-1, 2, lx1 * lx1).transpose(1, 0, 2).astype(np.float64)
+    U = g["U"].reshape(-1, 2, lx1 * lx1).transpose(1, 0, 2).astype(np.float64)
+    glo = global_numbering_2d(g["vert"], lx1)
+    codes = {c: i for i, c in enumerate([s.decode() if isinstance(s, bytes) else str(s) for s in g["bc_names"]])}
+    dirf = (g["bc"] == codes["v  "]) | (g["bc"] == codes["W  "])
+    case = Case("cavity_re3600", 2, lx1, X.shape[1], X, glo, _mask_from_faces(dirf, glo, lx1, 2), g["key"].astype(np.int64),
+                int(g["d2"]), U, re=3600.0, end_time=0.5, tol_p=1e-9, tol_v=1e-9)
+    case.ifvcor = case.ifvcor_adjoint = True
+    return case
+
+
 def extrude(c2: Case, nz: int, lz: float, name: Optional[str] = None, compress_ids: bool = True) -> Case:
     """Config 5 recipe (SURVEY 8d): extrude a 2-D case into nz uniform periodic layers over [0,lz];
     element eg3 = layer*nel2 + eg2, key3 = key2, z-invariant base flow with W=0."""

@@ -509,6 +509,38 @@ extern "C" int nsb_orthonormalize(int k, int first, int slot_f, double* hcol) {
   return nsb_vec_normalize(slot_f, &hcol[k]);
 }
 
+// ------------------------------------------------------------------------------------------ direct / adjoint mode post-processing
+// biorthogonalize (core/sensitivity.f:428-504) on four device-resident modes: the direct mode is scaled to unit norm, the adjoint
+// mode rotated / scaled so that <a, d> = 1 under the bm1s inner product (core/eigensolvers.f:7-58).
+extern "C" int nsb_biorthogonalize(int dre, int dim, int are, int aim) {
+  REQUIRE_CTX(); CHECK_SLOT(dre); CHECK_SLOT(dim); CHECK_SLOT(are); CHECK_SLOT(aim);
+  if (dre == dim || are == aim || dre == are || dre == aim || dim == are || dim == aim) { nsb_set_error("biorthogonalize: the four slots must differ"); return 1; }
+  double alpha = 0, beta = 0;
+  NSB_TRY(nsb_vec_inner_product(dre, dre, &alpha));                    // :463-467
+  NSB_TRY(nsb_vec_inner_product(dim, dim, &beta));
+  if (!(alpha + beta > 0)) { nsb_set_error("biorthogonalize: zero direct mode"); return 1; }
+  double gamma = 1.0 / std::sqrt(alpha + beta);
+  NSB_TRY(nsb_vec_cmult(dre, gamma));                                  // :471-472 (the reference's opcmult leaves the pressure as is;
+  NSB_TRY(nsb_vec_cmult(dim, gamma));                                  //  the pressure part is not used downstream)
+  NSB_TRY(nsb_vec_inner_product(are, dre, &alpha));                    // :475-477
+  NSB_TRY(nsb_vec_inner_product(aim, dim, &beta));
+  gamma = alpha + beta;
+  NSB_TRY(nsb_vec_inner_product(are, dim, &alpha));                    // :479-481
+  NSB_TRY(nsb_vec_inner_product(aim, dre, &beta));
+  const double delta = alpha - beta;
+  if (!(gamma * gamma + delta * delta > 0)) { nsb_set_error("biorthogonalize: direct and adjoint modes are orthogonal"); return 1; }
+  return vk_rotate_pair(c, slot_ptr(c, are), slot_ptr(c, aim), gamma, delta, c->vlen);      // :484-501
+}
+// wave_maker (core/sensitivity.f:7-81): bi-orthonormalise, then |u_direct| |u_adjoint| pointwise; the field (n values, the array the
+// reference outposts as temperature in wm_<session>0.f00001) is returned to the host.
+extern "C" int nsb_wave_maker(int dre, int dim, int are, int aim, double* wavemaker) {
+  NSB_TRY(nsb_biorthogonalize(dre, dim, are, aim));
+  Ctx* c = g_ctx;
+  if (!wavemaker) { nsb_set_error("wave_maker: output array is NULL"); return 1; }
+  NSB_TRY(vk_wavemaker(c, slot_ptr(c, dre), slot_ptr(c, dim), slot_ptr(c, are), slot_ptr(c, aim), c->wk[0]));
+  return d2h(c, wavemaker, c->wk[0], c->n);
+}
+
 // ------------------------------------------------------------------------------------------ matvec
 extern "C" int nsb_matvec(int mode, int sin, int sout) {
   REQUIRE_CTX(); CHECK_SLOT(sin); CHECK_SLOT(sout);

@@ -328,6 +328,8 @@ int vk_multidot_raw(Ctx* c, int k, const double* Q, long long vlen, const double
 int vk_multiaxpy_raw(Ctx* c, int k, const double* Q, long long vlen, const double* f, double a, const double* h_dev, double sign,
                      double* out);
 int vk_rotate(Ctx* c, int k, int first_slot, const double* S_dev, int lds);
+int vk_rotate_pair(Ctx* c, double* are, double* aim, double g, double d, long long n);
+int vk_wavemaker(Ctx* c, const double* dre, const double* dim, const double* are, const double* aim, double* wm);
 
 // ---- pressure preconditioner (pmg.cu)
 int pm_setup(Ctx* c, int set, int nagg_req);

@@ -530,3 +530,34 @@ int vk_rotate(Ctx* c, int k, int first_slot, const double* S_dev, int lds) {
   NSB_CUDA(cudaGetLastError());
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------- direct / adjoint mode post-processing
+// biorthogonalize (core/sensitivity.f:486-501): (a_re, a_im) <- ((g a_re - d a_im), (g a_im + d a_re)) / (g^2 + d^2), whole vectors
+__global__ void k_rotate_pair(double* __restrict__ are, double* __restrict__ aim, double g, double d, double inv_den, long long n) {
+  GSTRIDE(i, n) {
+    const double r = are[i], m = aim[i];
+    are[i] = (g * r - d * m) * inv_den;
+    aim[i] = (g * m + d * r) * inv_den;
+  }
+}
+// wave_maker (core/sensitivity.f:69-71): |u_direct| * |u_adjoint| pointwise over the velocity components
+__global__ void k_wavemaker(const double* __restrict__ dre, const double* __restrict__ dim, const double* __restrict__ are,
+                            const double* __restrict__ aim, double* __restrict__ wm, long long n, int D) {
+  GSTRIDE(i, n) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int c = 0; c < D; ++c) {
+      const long long j = (long long)c * n + i;
+      s1 += dre[j] * dre[j] + dim[j] * dim[j];
+      s2 += are[j] * are[j] + aim[j] * aim[j];
+    }
+    wm[i] = sqrt(s1) * sqrt(s2);
+  }
+}
+int vk_rotate_pair(Ctx* c, double* are, double* aim, double g, double d, long long n) {
+  LAUNCH1(k_rotate_pair, n, are, aim, g, d, 1.0 / (g * g + d * d), n);
+  return 0;
+}
+int vk_wavemaker(Ctx* c, const double* dre, const double* dim, const double* are, const double* aim, double* wm) {
+  LAUNCH1(k_wavemaker, c->n, dre, dim, are, aim, wm, c->n, c->ldim);
+  return 0;
+}

@@ -82,6 +82,8 @@ _SIGS = {
     "nsb_basis_gemv": [C.c_int, C.c_int, _dp, C.c_int],
     "nsb_basis_gemv_complex": [C.c_int, C.c_int, _dp, _dp, C.c_int, C.c_int],
     "nsb_basis_rotate": [C.c_int, C.c_int, _dp, C.c_int],
+    "nsb_biorthogonalize": [C.c_int] * 4,
+    "nsb_wave_maker": [C.c_int] * 4 + [_dp],
     "nsb_orthonormalize": [C.c_int, C.c_int, C.c_int, _dp],
     "nsb_matvec": [C.c_int] * 3,
     "nsb_nonlinear_forward_map": [C.c_int, C.c_int],
@@ -307,6 +309,20 @@ class NekStabB200:
     def basis_gemv(self, k, first, y, out):
         y = _arr(y)
         _ck(self.lib.nsb_basis_gemv(k, first, _p(y), out))
+
+    def basis_gemv_complex(self, k, first, y, slot_re, slot_im):
+        """mode = sum_i y_i Q_i for a complex coefficient vector (outpost_ks, core/eigensolvers.f:554-564)."""
+        y = np.asarray(y, dtype=complex)
+        yr, yi = np.ascontiguousarray(y.real), np.ascontiguousarray(y.imag)
+        _ck(self.lib.nsb_basis_gemv_complex(k, first, _p(yr), _p(yi), slot_re, slot_im))
+
+    def biorthogonalize(self, dre, dim, are, aim):
+        _ck(self.lib.nsb_biorthogonalize(dre, dim, are, aim))
+
+    def wave_maker(self, dre, dim, are, aim):
+        wm = np.empty(self.n)
+        _ck(self.lib.nsb_wave_maker(dre, dim, are, aim, _p(wm)))
+        return wm.reshape(self.nel, -1)
 
     def basis_rotate(self, k, first, S):
         S = np.asfortranarray(S, dtype=np.float64)

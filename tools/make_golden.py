@@ -7,6 +7,9 @@ What is extracted (SURVEY.md 8c "golden vectors"):
             .../adjoint/Spectre_*.dat, .../postproc/sensitivity_budget_wavemaker/{dRe,dIm}1cyl0.f00001,
             element->rank maps of the field files (partition KAT)
   bfs.npz : examples/back_fstep/transient_growth/{BF_bfs0,pRebfs0,orebfs0}.f00001, bfs.ma2, bfs.re2
+  cav.npz : examples/lid_driven/{BF_cav0.f00001, cav.ma2, cav.re2} (config 3; the shipped base flow lives on y in [0, 1.2]
+            although cav.par:9 sets the aspect ratio 1.5 that cav.usr:107-109 rescales the mesh to: the fixture's own
+            coordinates are kept, SURVEY.md 8 cfg-3 caveat)
 All element data are re-ordered to ascending global element id.
 """
 import os
@@ -93,6 +96,24 @@ def bfs():
     print("bfs.npz", os.path.getsize(f"{OUT}/bfs.npz") / 1e6, "MB")
 
 
+def cav():
+    d = f"{REF}/examples/lid_driven"
+    bf_raw = nekio.read_field(f"{d}/BF_cav0.f00001")
+    bf = bf_raw.sort_global()
+    re2 = nekio.read_re2(f"{d}/cav.re2")
+    ma2 = nekio.read_ma2(f"{d}/cav.ma2")
+    names = np.array(["E  ", "P  ", "v  ", "O  ", "W  "])
+    codes = re2.bc_codes()
+    bc = np.zeros(codes.shape, dtype=np.uint8)
+    for i, nme in enumerate(names):
+        bc[codes == nme] = i
+    out = dict(lx1=bf.nx, X=bf.data["X"][:, :, 0], U=bf.data["U"][:, :, 0], P=bf.data["P"][:, 0], time=bf.time, istep=bf.istep,
+               vert=ma2.vert.astype(np.int32), key=ma2.key.astype(np.int32), d2=ma2.d2, bc=bc, bc_names=names.astype("S3"),
+               re2_xyz=re2.xyz, rank_file=runs_to_rank(bf_raw))
+    np.savez_compressed(f"{OUT}/cav.npz", **out)
+    print("cav.npz", os.path.getsize(f"{OUT}/cav.npz") / 1e6, "MB")
+
+
 def spectrum_text():
     """First lines of the shipped spectrum files as TEXT: pins the '(3E15.7)' writer of nekstab_b200/restart.py byte for byte."""
     d = f"{REF}/examples/cylinder/stability/direct"
@@ -103,7 +124,11 @@ def spectrum_text():
 
 
 if __name__ == "__main__":
+    if "--cav-only" in sys.argv:
+        cav()
+        sys.exit(0)
     if "--spectrum-only" not in sys.argv:
         cyl()
         bfs()
+        cav()
     spectrum_text()

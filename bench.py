@@ -56,6 +56,10 @@ WORDS = {
     "pcg_pc_restrict": 1.0 * R2,
     "pcg_pc_coarse": 0.0,
     "pcg_pc_apply": (2 + 126.0 / 216.0) * R2,
+    # fused CG tail (k_pcg_fused): r, Ep, p, x, 1/bm2 read, r, x, zloc written + the FDM factors; the direction kernel then reads
+    # zloc and pdir (no separate z, no vector of ones)
+    "pcg_fused": (5 + 3 + 126.0 / 216.0) * R2,
+    "pcg_gradt_fused": (2 + 9) * R2 + R2 + 3.0,
     # Helmholtz-CG iteration pieces (3 components batched)
     "hcg_axhelm": 3 * (1 + 1 + 1 + 1) + 6 + 1 + 1,   # per comp r,p read, p,w write; 6 G + bm1 + dinv once
     "hcg_dssum": 3 * 2 * FS + 0.5 * FS,
@@ -85,19 +89,46 @@ def build_workload(nz: int, world: int = 1, rank: int = 0, name: str = ""):
 
 
 class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md).  In-process NVML (the library nvidia-smi itself
+    queries) every 50 ms; falls back to spawning nvidia-smi when pynvml is missing.  Spawning a process per sample steals host time
+    from the thread that polls the CG loops, NVML does not."""
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
     def __init__(self, device):
         super().__init__(daemon=True)
-        self.device, self.stop_flag, self.rows = device, False, []
+        self.device, self.stop_flag, self.rows, self.how = device, False, [], "nvidia-smi"
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[device]) if vis and vis.split(",")[device].strip().isdigit() else device
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nv, self.how = pynvml, "nvml"
+        except Exception:
+            self.nv = None
+
+    def _nvml_row(self):
+        nv = self.nv
+        sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+        mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+        r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        bits = [getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8), getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20), getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)]
+        return [str(sm), str(mx)] + ["Active" if (r & b) else "Not Active" for b in bits]
 
     def run(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.device}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([t.strip() for t in out.split(",")])
+                if self.nv is not None:
+                    self.rows.append(self._nvml_row())
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--id={self.device}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                         capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.rows.append([t.strip() for t in out.split(",")])
             except Exception:
                 pass
             time.sleep(0.05)
@@ -106,10 +137,9 @@ class ClockSampler(threading.Thread):
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
         sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        reasons = [n for i, n in enumerate(self.NAMES) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
-                "reasons": reasons, "samples": len(self.rows)}
+                "reasons": reasons, "samples": len(self.rows), "how": self.how}
 
 
 def kernel_source_hash():
@@ -311,7 +341,7 @@ def sampled_kernels(ctx, dt, nsteps):
     from nekstab_b200 import lib
     ctx.set_timestep(dt, nsteps)
     ctx.profile(1)
-    ctx.matvec(lib.DIRECT, 2, 1)
+    ctx.matvec(lib.DIRECT, 2, 3)                  # slot 3 is scratch: slot 1 stays the input of the timed and the end-to-end calls
     return ctx.profile(0)
 
 
@@ -325,16 +355,24 @@ def roofline_block(prof, st, K, n_loc, precond, world):
             kern[kname] = {"avg_ms": ms / cnt, "samples": cnt, "alg_GBs": gbs, "frac": gbs / peak}
         elif cnt > 0:
             kern[kname] = {"avg_ms": ms / cnt, "samples": cnt}
-    pc = [k for k in ("pcg_gradt", "dssum", "pcg_div", "pcg_update", "pcg_pc_restrict", "pcg_pc_coarse", "pcg_pc_apply") if k in kern]
+    fused = "pcg_fused" in kern
+    if fused and "pcg_gradt" in kern:                      # the direction kernel no longer reads a vector of ones
+        t = kern["pcg_gradt"]["avg_ms"] * 1e-3
+        gbs = WORDS["pcg_gradt_fused"] * 8.0 * n_loc / t / 1e9
+        kern["pcg_gradt"].update({"alg_GBs": gbs, "frac": gbs / peak})
+    names = ("pcg_gradt", "dssum", "pcg_div", "pcg_fused", "pcg_pc_coarse") if fused else \
+        ("pcg_gradt", "dssum", "pcg_div", "pcg_update", "pcg_pc_restrict", "pcg_pc_coarse", "pcg_pc_apply")
+    wname = lambda k: "pcg_gradt_fused" if (fused and k == "pcg_gradt") else k
+    pc = [k for k in names if k in kern]
     cands = [k for k in pc if "frac" in kern[k]]
     if not cands:
         return None
     dom = max(cands, key=lambda k: kern[k]["avg_ms"])
     iter_ms = sum(kern[k]["avg_ms"] for k in pc)
-    iter_words = sum(WORDS.get(k, 0.0) for k in pc)
+    iter_words = sum(WORDS.get(wname(k), 0.0) for k in pc)
     traffic, tsrc = ncu_traffic(dom) if world == 1 else (None, None)
     roof = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["alg_GBs"], "peak": peak, "unit": "GB/s", "frac": kern[dom]["frac"],
-            "traffic": traffic, "traffic_source": tsrc, "peak_source": peak_src, "alg_bytes_per_launch": WORDS[dom] * 8.0 * n_loc,
+            "traffic": traffic, "traffic_source": tsrc, "peak_source": peak_src, "alg_bytes_per_launch": WORDS[wname(dom)] * 8.0 * n_loc,
             "pressure_iteration": {"alg_GBs": iter_words * 8.0 * n_loc / (iter_ms * 1e-3) / 1e9,
                                    "frac": iter_words * 8.0 * n_loc / (iter_ms * 1e-3) / 1e9 / peak, "ms": iter_ms,
                                    "note": "sampled (profiler on, graphs off)"},
@@ -342,7 +380,7 @@ def roofline_block(prof, st, K, n_loc, precond, world):
     # whole-step roofline: algorithmic bytes of everything a step executes (SURVEY 8d W_step with the measured iteration counts;
     # the advection's HBM traffic = the fine-mesh metrics + fields) over the measured device time per step of the TIMED call
     ip, ih = st["pres_iters"] / K, st["helm_iters"] / K / 3
-    iter_w = sum(WORDS[k] for k in ("pcg_gradt", "dssum", "pcg_div", "pcg_update")) + \
+    iter_w = iter_words if fused else sum(WORDS[k] for k in ("pcg_gradt", "dssum", "pcg_div", "pcg_update")) + \
         (sum(WORDS[k] for k in ("pcg_pc_restrict", "pcg_pc_coarse", "pcg_pc_apply")) if precond == "pmg" else 0.0)
     helm_w = WORDS["hcg_axhelm"] + WORDS["hcg_dssum"] + WORDS["hcg_update"]
     other_w = SURVEY_WORDS["ADV"] + SURVEY_WORDS["RHS"] + SURVEY_WORDS["RES"] + SURVEY_WORDS["PCOR"]
@@ -533,7 +571,7 @@ def main():
     if world > 1 and args.scaling in ("strong", "both") and not args.small:
         cs, ng = build_workload(10, world, rank)
         ctx, dt, _ = open_context(pl, cs, args)
-        seed_slot0(ctx, cs, 3)
+        seed_slot0(ctx, cs, 4)
         tm = timed_matvec(pl, ctx, dt, K, W)
         prof = sampled_kernels(ctx, dt, min(K, 2))
         slow = sorted(((k, ms / cnt) for k, (ms, cnt) in prof.items() if cnt > 0 and k != "advab"), key=lambda t: -t[1])[:4]
@@ -551,7 +589,7 @@ def main():
     ctx, dt, nsteps_full = open_context(pl, case, args)
     k_dim = min(args.k_dim, 20) if args.small else args.k_dim
     do_arn = args.arnoldi > 0
-    seed_slot0(ctx, case, (k_dim + 2) if do_arn else 3)
+    seed_slot0(ctx, case, (k_dim + 2) if do_arn else 4)
     if plane is None and world > 1:
         plane = "p2p" if ctx.get_field("p2p")[0] > 0 else "nccl"
     t_setup = time.time() - t_setup

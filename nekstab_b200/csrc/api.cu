@@ -240,6 +240,8 @@ extern "C" int nsb_init(int ldim, int lx1, int lxd, int lx2, int nelv, long long
   const char* np_ = getenv("NSB_PERSISTENT");
   c->persistent_pcg = !(np_ && np_[0] == '0');
   c->persistent_gradt = (np_ && np_[0] == '2');
+  const char* nt = getenv("NSB_PCG_FUSED");
+  c->pcg_fused = !(nt && nt[0] == '0');
   const char* nf = getenv("NSB_FUSED_GS");
   c->fused_gs = (c->ldim == 3 && c->nranks == 1 && c->gs.nb_off != nullptr && nf && nf[0] == '1');
   NSB_CUDA(cudaStreamSynchronize(c->stream));

@@ -46,6 +46,7 @@ struct ConstMats {
   double Jd[216], Jdt[216], Dd[216], Ddt[216];          // lxd x lx1 (t: lx1 x lxd)
   double w1[12], w2[12], wd[18];
   double z1[12];
+  double hat1[12];                                       // Q1 hat function (1+z)/2 at the GL(lx2) points (pressure preconditioner)
 };
 
 // Device-resident state of one conjugate-gradient recurrence (one per solved component).
@@ -112,7 +113,8 @@ struct PMG {
   int* agg = nullptr;               // [nel] aggregate of every element (global aggregate id)
   int *aoff = nullptr, *aent = nullptr;   // CSR local aggregate -> elements
   double* A2inv = nullptr;          // [nagg][nagg] (Pa^T E Pa)^-1
-  double *rc = nullptr, *xv = nullptr, *ra = nullptr, *x2 = nullptr;   // work: corner sums, vertex values, aggregate sums/values
+  double *rc = nullptr, *xv = nullptr, *ra = nullptr, *x2 = nullptr;   // work: corner sums, vertex values, aggregate sums (+3 CG scalars)/values
+  double* rc0 = nullptr;            // un-assembled copy of rc (multi-rank: rc is summed across ranks in place)
   std::vector<int> h_agg;
   std::vector<double> h_d1, h_A2inv;
   // EXPERIMENTAL (kind 2, single rank, not yet validated on a GPU): Q1 level as a V-cycle on the assembled A_c = P^T E P
@@ -185,6 +187,7 @@ struct Ctx {
   bool persistent_gradt = false;
   bool persistent_pcg = true; // 3-D: persistent, TMA-pipelined k_gradt3p / k_div3p in the pressure-CG loop (NSB_PERSISTENT=0 disables)
   bool fused_gs = false;      // 3-D, single rank: k_div3 gathers the surface sums itself (no dssum in the pressure loop)
+  bool pcg_fused = true;      // 3-D, pc_kind 1: fused CG tail (pm_pcg_tail) + coarse levels added in the direction kernel (NSB_PCG_FUSED=0 disables)
 
   double* adv_scratch = nullptr;   // per-CTA fine-mesh work arrays of the advection kernel (L2-resident)
   size_t adv_scratch_words = 0;
@@ -335,6 +338,7 @@ int vk_wavemaker(Ctx* c, const double* dre, const double* dim, const double* are
 int pm_setup(Ctx* c, int set, int nagg_req);
 int pm_setup_vcycle(Ctx* c, int set);
 int pm_apply(Ctx* c, int set, const double* r, double* z, int mode, int prof_slot = 0);
+int pm_pcg_tail(Ctx* c, int set, int init, int prof_slot);   // fused CG update + restriction + element blocks + coarse levels + scalars (3-D)
 void pm_free(PMG& m);
 int vk_cg_finalize_multi(Ctx* c, CGState* s, int ncomp, int kind);
 

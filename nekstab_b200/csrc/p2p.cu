@@ -16,7 +16,7 @@
 
 #include "nsb_internal.h"
 
-static constexpr int RSLOT = 512;                 // doubles per rank slot of the all-reduce buffer
+static constexpr int RSLOT = 640;                 // doubles per rank slot of the all-reduce buffer (>= 512 aggregate sums + 3 CG scalars)
 static constexpr long long SPIN_TIMEOUT_NS = 30000000000LL;   // 30 s: host-side skew between ranks (setup, numpy work) is seconds at most
 
 __device__ __forceinline__ unsigned long long ld_flag(const unsigned long long* p) {

@@ -88,11 +88,15 @@ __device__ __forceinline__ void apply2_store(const double* __restrict__ M1, cons
 }
 
 // ------------------------------------------------------------------------------------------------ gradt
+// MODE 0: w = D^T p.  MODE 1: CG direction with a pointwise preconditioner, p = dinvE*r + beta*pdir.  MODE 2: CG direction with the
+// three-level preconditioner of pmg.cu in its fused form: `p` holds the element-block part zloc of z = M^-1 r (k_pcg_fused); the Q1
+// vertex-mesh part (trilinear interpolation of the 8 corner values xv[vid]) and the aggregate value x2[agg] are added here.
 template <int N, int MODE>
 __global__ void __launch_bounds__(PK_TPB, 3)
 k_gradt3(const double* __restrict__ p, double* __restrict__ w, const double* __restrict__ RW2,
          const double* __restrict__ dinvE, double* __restrict__ pdir, const CGState* __restrict__ cgs, long long n,
-         long long n2) {
+         long long n2, const double* __restrict__ xv, const int* __restrict__ vid, const double* __restrict__ x2,
+         const int* __restrict__ agg) {
   constexpr int N2 = N - 2, TPB = PK_TPB;
   constexpr int NP1 = N * N * N, NP2 = N2 * N2 * N2;
   using S2 = Shp<N2, N2, N2>;
@@ -103,15 +107,43 @@ k_gradt3(const double* __restrict__ p, double* __restrict__ w, const double* __r
   using C2 = ColIn<2, N2, N, N>;
   __shared__ double sa[9][SA::size];
   __shared__ double sb[6][SB::size];
+  __shared__ double sxc[9], sh1[8];
   // products RW2[i][c]*p, one array per (i,c); consumed by the r stage before the s stage overwrites sb
   double* sq = &sb[0][0];
   static_assert(9 * S2::size <= 6 * SB::size, "sq alias");
   const int tid = threadIdx.x;
-  if (MODE == 1 && cgs->done) return;
+  if (MODE >= 1 && cgs->done) return;
   const long long e2 = (long long)blockIdx.x * NP2;
   const long long e1 = (long long)blockIdx.x * NP1;
   static_assert(NP2 <= TPB, "one mesh-2 point per thread");
-  if (tid < NP2) {
+  if (MODE == 2) {
+    // two dependent L2 hits (vid -> xv) that hide behind the DRAM latency of the metric loads below
+    if (tid >= TPB - 8) sxc[tid - (TPB - 8)] = xv[vid[(long long)blockIdx.x * 8 + (tid - (TPB - 8))]];
+    else if (tid == TPB - 9) sxc[8] = x2[agg[blockIdx.x]];
+    else if (tid >= TPB - 32 && tid < TPB - 32 + N2) sh1[tid - (TPB - 32)] = cm.hat1[tid - (TPB - 32)];
+    double zl = 0.0, pd = 0.0, m9[9];
+    if (tid < NP2) {
+      zl = p[e2 + tid];
+      pd = pdir[e2 + tid];
+#pragma unroll
+      for (int g = 0; g < 9; ++g) m9[g] = RW2[(long long)g * n2 + e2 + tid];   // coalesced
+    }
+    __syncthreads();
+    if (tid < NP2) {
+      const int q = tid;
+      const int i0 = q % N2, i1 = (q / N2) % N2, i2 = q / (N2 * N2);
+      const double a0 = sh1[i0], a1 = sh1[i1], a2 = sh1[i2];
+      const double c0 = fma(sxc[1] - sxc[0], a0, sxc[0]), c1 = fma(sxc[3] - sxc[2], a0, sxc[2]);
+      const double d0 = fma(sxc[5] - sxc[4], a0, sxc[4]), d1 = fma(sxc[7] - sxc[6], a0, sxc[6]);
+      const double q0 = fma(c1 - c0, a1, c0), q1 = fma(d1 - d0, a1, d0);
+      const double z = (zl + fma(q1 - q0, a2, q0)) + sxc[8];
+      const double v = fma(cgs->beta, pd, z);
+      pdir[e2 + q] = v;
+      const int o = S2::lin(q);
+#pragma unroll
+      for (int g = 0; g < 9; ++g) sq[g * S2::size + o] = m9[g] * v;
+    }
+  } else if (tid < NP2) {
     const int q = tid;
     double v;
     if (MODE == 1) {
@@ -747,6 +779,182 @@ k_axhelm3(const double* __restrict__ u, double* __restrict__ w, const double* __
   }
 }
 
+// ------------------------------------------------------------------------------------------------ persistent, TMA-pipelined axhelm (Helmholtz-CG head)
+// r1d ncu on k_axhelm3<8,2>: 45 % of the HBM roofline, stalls = load latency at the kernel head (one element per CTA, 2 CTAs/SM, nothing
+// in flight while the four tensor phases run).  Here one CTA per SM slot (2 per SM) walks over elements; the 14 input arrays of an
+// element live in ONE staging buffer whose two halves are refilled by bulk TMA copies as soon as they have been consumed:
+//   head half (r x3, pdir x3, dinv) is consumed by the first phase  -> element e+1's head is requested right after the first barrier
+//   G half (g1..g6, bm1) is consumed by the geometric-factor phase  -> element e+1's factors are requested right after that barrier
+// so the loads of element e+1 are in flight during three of the four phases of element e.  Shared memory: 14 + 12*1.125 element
+// arrays = 112 KB per CTA, two CTAs per SM.
+struct AxPArgs {
+  const double* r; const double* dinv; const double* G; const double* bm1;
+  double* pdir; double* w;
+  long long n;
+  double h1, h2;
+};
+template <int N>
+struct AxP {
+  static constexpr int NP1 = N * N * N;
+  using S1 = Shp<N, N, N>;
+  static constexpr int TPB = AxCfg<N>::TPB;
+  static constexpr int stage = 14 * NP1;
+  static constexpr size_t smem = sizeof(double) * (stage + 12 * S1::size) + 2 * sizeof(uint64_t) + sizeof(AxPArgs);
+};
+struct Rho3 { double a, b, c; };
+
+template <int N>
+__device__ __forceinline__ void ax3p_issue_head(const AxPArgs* A, double* stg, uint64_t* bar, int e) {
+  constexpr int NP1 = N * N * N;
+  const long long e0 = (long long)e * NP1;
+  mbar_expect_tx(bar, 7 * NP1 * (uint32_t)sizeof(double));
+#pragma unroll
+  for (int f = 0; f < 3; ++f) {
+    tma_bulk_g2s(stg + f * NP1, A->r + (long long)f * A->n + e0, NP1 * sizeof(double), bar);
+    tma_bulk_g2s(stg + (3 + f) * NP1, A->pdir + (long long)f * A->n + e0, NP1 * sizeof(double), bar);
+  }
+  tma_bulk_g2s(stg + 6 * NP1, A->dinv + e0, NP1 * sizeof(double), bar);
+}
+template <int N>
+__device__ __forceinline__ void ax3p_issue_g(const AxPArgs* A, double* stg, uint64_t* bar, int e) {
+  constexpr int NP1 = N * N * N;
+  const long long e0 = (long long)e * NP1;
+  mbar_expect_tx(bar, 7 * NP1 * (uint32_t)sizeof(double));
+#pragma unroll
+  for (int q = 0; q < 6; ++q) tma_bulk_g2s(stg + (7 + q) * NP1, A->G + (long long)q * A->n + e0, NP1 * sizeof(double), bar);
+  tma_bulk_g2s(stg + 13 * NP1, A->bm1 + e0, NP1 * sizeof(double), bar);
+}
+
+// One element (not inlined: inside the element loop nvcc would hoist the constant-bank operator matrices into registers, see
+// gradt3_element).  actmask: bit f = component f still iterating.
+template <int N>
+__device__ __noinline__ Rho3 ax3p_element(const AxPArgs* __restrict__ A, double* __restrict__ stg, double* __restrict__ su,
+                                          double* __restrict__ sr, uint64_t* bar, int e, int e_next, uint32_t parity, int actmask,
+                                          double b0, double b1, double b2, int tid) {
+  constexpr int NP1 = N * N * N, NC = N * N;
+  using S1 = Shp<N, N, N>;
+  constexpr int PI = S1::PI;
+  const long long e0 = (long long)e * NP1;
+  const double beta[3] = {b0, b1, b2};
+  double uo[3] = {0.0, 0.0, 0.0};
+  mbar_wait(&bar[0], parity);
+  if (tid < NP1) {
+    const int o = S1::lin(tid);
+    const double di = stg[6 * NP1 + tid];
+#pragma unroll
+    for (int f = 0; f < 3; ++f)
+      if (actmask & (1 << f)) {
+        const double v = di * stg[f * NP1 + tid] + beta[f] * stg[(3 + f) * NP1 + tid];
+        A->pdir[(long long)f * A->n + e0 + tid] = v;
+        uo[f] = v;
+        su[f * S1::size + o] = v;
+      }
+  }
+  __syncthreads();                                   // head half consumed
+  if (tid == 0 && e_next >= 0) ax3p_issue_head<N>(A, stg, &bar[0], e_next);
+  const int tf = tid / (3 * NC), tdir = (tid / NC) % 3, tcol = tid % NC;
+  const bool task = tid < 9 * NC && ((actmask >> (tf < 3 ? tf : 0)) & 1);
+  const int cbase = (tdir == 0) ? tcol * PI : ((tdir == 1) ? (tcol / N) * N * PI + (tcol % N) : (tcol / N) * PI + (tcol % N));
+  const int cstr = (tdir == 0) ? 1 : ((tdir == 1) ? PI : N * PI);
+  if (task) {
+    const double* pin = su + tf * S1::size + cbase;
+    double v[N];
+#pragma unroll
+    for (int l = 0; l < N; ++l) v[l] = pin[l * cstr];
+    apply_store<N, N>(cm.D, v, sr + (tf * 3 + tdir) * S1::size + cbase, cstr);
+  }
+  mbar_wait(&bar[1], parity);
+  __syncthreads();
+  double bm = 0.0;
+  if (tid < NP1) {
+    const int o = S1::lin(tid);
+    double g[6];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) g[q] = stg[(7 + q) * NP1 + tid];
+    bm = stg[13 * NP1 + tid];
+#pragma unroll
+    for (int f = 0; f < 3; ++f)
+      if (actmask & (1 << f)) {
+        double* p0 = sr + (f * 3) * S1::size + o;
+        const double d0 = p0[0], d1 = p0[S1::size], d2 = p0[2 * S1::size];
+        p0[0] = g[0] * d0 + g[3] * d1 + g[4] * d2;
+        p0[S1::size] = g[3] * d0 + g[1] * d1 + g[5] * d2;
+        p0[2 * S1::size] = g[4] * d0 + g[5] * d1 + g[2] * d2;
+      }
+  }
+  __syncthreads();                                   // factor half consumed
+  if (tid == 0 && e_next >= 0) ax3p_issue_g<N>(A, stg, &bar[1], e_next);
+  if (task) {
+    double* pc = sr + (tf * 3 + tdir) * S1::size + cbase;
+    double v[N];
+#pragma unroll
+    for (int l = 0; l < N; ++l) v[l] = pc[l * cstr];
+    apply_store<N, N>(cm.Dt, v, pc, cstr);
+  }
+  __syncthreads();
+  Rho3 rho = {0.0, 0.0, 0.0};
+  if (tid < NP1) {
+    const int o = S1::lin(tid);
+    double rr[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int f = 0; f < 3; ++f)
+      if (actmask & (1 << f)) {
+        const double* p0 = sr + (f * 3) * S1::size + o;
+        const double hv = A->h1 * ((p0[0] + p0[S1::size]) + p0[2 * S1::size]) + A->h2 * bm * uo[f];
+        A->w[(long long)f * A->n + e0 + tid] = hv;
+        rr[f] = uo[f] * hv;
+      }
+    rho.a = rr[0]; rho.b = rr[1]; rho.c = rr[2];
+  }
+  return rho;
+}
+
+template <int N>
+__global__ void __launch_bounds__(AxCfg<N>::TPB, 2)
+k_axhelm3p(AxPArgs args, CGState* __restrict__ cgs, double* __restrict__ part, unsigned* counter, double* __restrict__ red_out,
+           int finalize, int nel) {
+  using P = AxP<N>;
+  using S1 = typename P::S1;
+  extern __shared__ __align__(128) double dsm[];
+  double* stg = dsm;                                 // [14][NP1]
+  double* su = dsm + P::stage;                       // [3][S1::size]
+  double* sr = su + 3 * S1::size;                    // [9][S1::size]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sr + 9 * S1::size);
+  AxPArgs* sargs = reinterpret_cast<AxPArgs*>(bar + 2);
+  __shared__ double sred[3 * 32];
+  const int tid = threadIdx.x;
+  int actmask = 0;
+#pragma unroll
+  for (int f = 0; f < 3; ++f) actmask |= cgs[f].done ? 0 : (1 << f);
+  if (!actmask) return;
+  const double b0 = cgs[0].beta, b1 = cgs[1].beta, b2 = cgs[2].beta;
+  if (tid == 0) {
+    *sargs = args;
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (tid == 0 && (int)blockIdx.x < nel) {
+    ax3p_issue_head<N>(sargs, stg, &bar[0], blockIdx.x);
+    ax3p_issue_g<N>(sargs, stg, &bar[1], blockIdx.x);
+  }
+  double rho[3] = {0.0, 0.0, 0.0};
+  int it = 0;
+  for (int e = blockIdx.x; e < nel; e += gridDim.x, ++it) {
+    const int en = (e + (int)gridDim.x < nel) ? e + (int)gridDim.x : -1;
+    const Rho3 q = ax3p_element<N>(sargs, stg, su, sr, bar, e, en, (uint32_t)(it & 1), actmask, b0, b1, b2, tid);
+    rho[0] += q.a; rho[1] += q.b; rho[2] += q.c;
+  }
+  if (grid_sum_finish<3>(rho, part, counter, red_out, sred) && finalize && tid == 0) {
+    for (int f = 0; f < 3; ++f)
+      if (!cgs[f].done) {
+        cgs[f].rho = red_out[f];
+        cgs[f].alpha = cgs[f].rtz1 / red_out[f];
+      }
+  }
+}
+
 }  // namespace
 
 int pk_upload_constants(const ConstMats& h) {
@@ -765,7 +973,7 @@ int pk_upload_constants(const ConstMats& h) {
   } while (0)
 
 int pk_gradt(Ctx* c, const double* p, double* w) {
-  DISPATCH_N(c, k_gradt3<N, 0><<<c->nel, PK_TPB, 0, c->stream>>>(p, w, c->RW2, nullptr, nullptr, nullptr, c->n, c->n2));
+  DISPATCH_N(c, k_gradt3<N, 0><<<c->nel, PK_TPB, 0, c->stream>>>(p, w, c->RW2, nullptr, nullptr, nullptr, c->n, c->n2, nullptr, nullptr, nullptr, nullptr));
   nsb_count_launch();
   NSB_CUDA(cudaGetLastError());
   return 0;
@@ -791,8 +999,16 @@ int pk_pcg_dir_gradt(Ctx* c, int adj) {
     NSB_CUDA(cudaGetLastError());
     return 0;
   }
+  if (c->pc_kind == 1 && c->pcg_fused) {          // fused preconditioner: pz holds the element-block part, the coarse parts are added here
+    const PMG& m = c->pmg[(adj && c->has_adj_masks) ? 1 : 0];
+    DISPATCH_N(c, k_gradt3<N, 2><<<c->nel, PK_TPB, 0, c->stream>>>(c->pz, c->wk[2], c->RW2, nullptr, c->pk[2], c->cgs + 3, c->n, c->n2,
+                                                                m.xv, m.vid, m.x2, m.agg));
+    nsb_count_launch();
+    NSB_CUDA(cudaGetLastError());
+    return 0;
+  }
   DISPATCH_N(c, k_gradt3<N, 1><<<c->nel, PK_TPB, 0, c->stream>>>(zsrc, c->wk[2], c->RW2, zscale, c->pk[2], c->cgs + 3,
-                                                              c->n, c->n2));
+                                                              c->n, c->n2, nullptr, nullptr, nullptr, nullptr));
   nsb_count_launch();
   NSB_CUDA(cudaGetLastError());
   return 0;
@@ -871,6 +1087,17 @@ static int launch_axhelm3(Ctx* c, int mode, const double* u, double* w, const do
 
 int pk_axhelm(Ctx* c, int mode, const double* u, double* w, const double* b, int nfields, double h1, double h2) {
   static const bool pf = [] { const char* e = getenv("NSB_AX_PREFETCH"); return !(e && e[0] == '0'); }();
+  static const bool pers = [] { const char* e = getenv("NSB_AX_PERSISTENT"); return !(e && e[0] == '0'); }();
+  if (mode == 2 && nfields == 3 && pers && c->lx1 == 8) {      // Helmholtz-CG head: persistent, TMA-pipelined (lx1 = 8: 112 KB per CTA)
+    constexpr int N = 8;
+    AxPArgs a{c->rk, c->dinvH, c->G, c->bm1, c->wk[1], c->wk[2], c->n, h1, h2};
+    NSB_TRY(set_smem(k_axhelm3p<N>, AxP<N>::smem));
+    k_axhelm3p<N><<<persistent_grid(c), AxCfg<N>::TPB, AxP<N>::smem, c->stream>>>(a, c->cgs, c->red_part, c->red_count, c->red_out,
+                                                                                c->nranks == 1, c->nel);
+    nsb_count_launch();
+    NSB_CUDA(cudaGetLastError());
+    return 0;
+  }
   if (pf) DISPATCH_N(c, NSB_TRY((launch_axhelm3<N, true>(c, mode, u, w, b, nfields, h1, h2))));
   else DISPATCH_N(c, NSB_TRY((launch_axhelm3<N, false>(c, mode, u, w, b, nfields, h1, h2))));
   nsb_count_launch();

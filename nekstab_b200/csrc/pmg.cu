@@ -450,6 +450,268 @@ __global__ void __launch_bounds__(Pm2<D, L>::NT) k_pm_apply2(const double* __res
   }
 }
 
+// ---------------------------------------------------------------------------------------------- fused pressure-CG tail (3-D)
+// One kernel for everything of a CG iteration that touches the mesh-2 vectors between the E application and the next direction:
+//   x += alpha p ; r -= alpha Ep ; |r|^2 (Nek norm: r^2/bm2) ; rc = P^T r (Q1 restriction) ; zloc = FDM_e(r) ; zloc . r
+// (r1d: k_pcg_update 0.058 + k_pm_restrict 0.019 + k_pm_apply2 0.074 ms, r streamed three times).  The coarse-level parts of
+// z = M^-1 r are NOT added here: they need the vertex / aggregate sums of ALL elements, so the direction kernel (k_gradt3 MODE 2,
+// pcg_kernels.cu) adds the trilinear interpolation of the vertex values and the aggregate value while it forms p = z + beta p,
+// and z.r is assembled from the level contributions: zloc.r (here) + sum_v xv rv + ra^T A2^-1 ra (k_pm_coarse_dot, k_pm_gemv_fin).
+// init = 1: start of a solve (x = 0, p = 0, r given).  The two sums go to out[0..1] (deterministic two-stage reduction).
+template <int D, int L>
+__global__ void __launch_bounds__(Pm2<D, L>::NT) k_pcg_fused(double* __restrict__ r, double* __restrict__ x, double* __restrict__ pdir,
+                                                            const double* __restrict__ ep, const double* __restrict__ bm2inv,
+                                                            double* __restrict__ zloc, double* __restrict__ rc, double* __restrict__ rc0,
+                                                            int nel, const double* __restrict__ Sg, const double* __restrict__ lamg,
+                                                            const CGState* __restrict__ cgs, int init, double* part, unsigned* counter,
+                                                            double* out) {
+  using P = Pm2<D, L>;
+  constexpr int NP = P::NP, NK = P::NK, LL = L * L, PI = P::PI, ESZ = P::ESZ, EPB = P::EPB, NT = P::NT, NCOL = P::NCOL;
+  constexpr int PER = (EPB * NP + NT - 1) / NT;
+  if (!init && cgs->done) return;
+  __shared__ __align__(16) double sS[EPB * D * LL];
+  __shared__ double sA[EPB * ESZ], sB[EPB * ESZ], sL[EPB * D * L], sMx[EPB], sl0[8], sl1[8], sred[2 * 32];
+  __shared__ double sP[EPB * NCOL * 2], sQ[(D == 3) ? EPB * L * 4 : 1];
+  const int tid = threadIdx.x;
+  const int e0 = blockIdx.x * EPB;
+  const int ne = min(EPB, nel - e0);
+  const double alpha = init ? 0.0 : cgs->alpha;
+  // ---- load phase (coalesced): CG update, residual -> sA (padded rows), FDM factors
+  double rr[PER];
+  double sums[2] = {0.0, 0.0};
+#pragma unroll
+  for (int q = 0; q < PER; ++q) {
+    const int t = tid + q * NT;
+    rr[q] = 0.0;
+    if (t < ne * NP) {
+      const long long gi = (long long)e0 * NP + t;
+      double v = r[gi];
+      if (init) {
+        x[gi] = 0.0;
+        pdir[gi] = 0.0;
+      } else {
+        v = fma(-alpha, ep[gi], v);
+        r[gi] = v;
+        x[gi] = fma(alpha, pdir[gi], x[gi]);
+      }
+      rr[q] = v;
+      sums[0] = fma(v * v, bm2inv[gi], sums[0]);
+      const int el = t / NP, p = t - el * NP;
+      sA[el * ESZ + (p / L) * PI + (p % L)] = v;
+    }
+  }
+  for (int t = tid; t < ne * D * LL; t += NT) sS[t] = Sg[(long long)e0 * D * LL + t];
+  for (int t = tid; t < ne * D * L; t += NT) sL[t] = lamg[(long long)e0 * D * L + t];
+  if (tid < L) { sl0[tid] = pm_l[0][tid]; sl1[tid] = pm_l[1][tid]; }
+  __syncthreads();
+  if (tid < ne) {                                   // threshold scale of the element: sum_d max_i lam_d[i]
+    double mx = 0.0;
+    for (int d = 0; d < D; ++d) {
+      double m = sL[(tid * D + d) * L];
+      for (int i = 1; i < L; ++i) m = fmax(m, sL[(tid * D + d) * L + i]);
+      mx += m;
+    }
+    sMx[tid] = mx;
+  }
+  __syncthreads();
+  const int el = tid / NCOL, c = tid - el * NCOL;
+  const bool act = el < ne;
+  double* in = sA + el * ESZ;
+  double* ou = sB + el * ESZ;
+  const int ca = c % L, cb = c / L;
+#pragma unroll
+  for (int pass = 0; pass < 2 * D; ++pass) {
+    const int d = (pass < D) ? pass : (2 * D - 1 - pass);
+    const bool fwd = pass < D;
+    if (act) {
+      int base, str;
+      if (D == 3) {
+        if (d == 0) { base = (cb * L + ca) * PI; str = 1; }
+        else if (d == 1) { base = cb * L * PI + ca; str = PI; }
+        else { base = cb * PI + ca; str = L * PI; }
+      } else {
+        if (d == 0) { base = c * PI; str = 1; }
+        else { base = c; str = PI; }
+      }
+      const double* Sd = sS + (el * D + d) * LL;
+      double v[L], o[L];
+#pragma unroll
+      for (int a = 0; a < L; ++a) v[a] = in[base + a * str];
+      if (pass == 0) {                              // Q1 restriction, first level: the row's two sums along r
+        double s1 = 0.0, s0 = 0.0;
+#pragma unroll
+        for (int a = 0; a < L; ++a) { s1 = fma(sl1[a], v[a], s1); s0 = fma(sl0[a], v[a], s0); }
+        sP[(el * NCOL + c) * 2] = s0;
+        sP[(el * NCOL + c) * 2 + 1] = s1;
+      }
+      if (fwd) {
+#pragma unroll
+        for (int i = 0; i < L; ++i) o[i] = 0.0;
+#pragma unroll
+        for (int a = 0; a < L; ++a) {
+          const double2* row = reinterpret_cast<const double2*>(Sd + a * L);
+#pragma unroll
+          for (int i2 = 0; i2 < L / 2; ++i2) {
+            const double2 s2 = row[i2];
+            o[2 * i2] = fma(s2.x, v[a], o[2 * i2]);
+            o[2 * i2 + 1] = fma(s2.y, v[a], o[2 * i2 + 1]);
+          }
+        }
+        if (d == D - 1) {
+          const double* lam = sL + el * D * L;
+          const double mx = sMx[el];
+          const double l01 = (D == 3) ? lam[ca] + lam[L + cb] : lam[c];
+#pragma unroll
+          for (int i = 0; i < L; ++i) {
+            const double den = l01 + lam[(D - 1) * L + i];
+            o[i] = (den > 1e-12 * mx) ? o[i] / den : 0.0;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int a = 0; a < L; ++a) {
+          const double2* row = reinterpret_cast<const double2*>(Sd + a * L);
+          double sacc = 0.0;
+#pragma unroll
+          for (int i2 = 0; i2 < L / 2; ++i2) {
+            const double2 s2 = row[i2];
+            sacc = fma(s2.x, v[2 * i2], sacc);
+            sacc = fma(s2.y, v[2 * i2 + 1], sacc);
+          }
+          o[a] = sacc;
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < L; ++a) ou[base + a * str] = o[a];
+    }
+    __syncthreads();
+    // ---- Q1 restriction, remaining levels, in the shadow of the tensor passes (fixed summation order => deterministic)
+    if (D == 3) {
+      if (pass == 0 && tid < ne * L * 4) {          // sum over s (ca) for every (element, t-plane cb, b0, b1)
+        const int e1 = tid / (L * 4), rem = tid - e1 * (L * 4);
+        const int kb = rem >> 2, b0 = rem & 1, b1 = (rem >> 1) & 1;
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < L; ++j) acc = fma(b1 ? sl1[j] : sl0[j], sP[(e1 * NCOL + kb * L + j) * 2 + b0], acc);
+        sQ[tid] = acc;
+      }
+      if (pass == 1 && tid < ne * NK) {             // sum over t (cb) for every (element, corner)
+        const int e1 = tid / NK, k = tid - e1 * NK;
+        const int b0 = k & 1, b1 = (k >> 1) & 1, b2 = (k >> 2) & 1;
+        double acc = 0.0;
+#pragma unroll
+        for (int kb = 0; kb < L; ++kb) acc = fma(b2 ? sl1[kb] : sl0[kb], sQ[e1 * L * 4 + kb * 4 + b1 * 2 + b0], acc);
+        rc[(long long)(e0 + e1) * NK + k] = acc;
+        if (rc0) rc0[(long long)(e0 + e1) * NK + k] = acc;
+      }
+    } else {
+      if (pass == 0 && tid < ne * NK) {             // 2-D: sum over s (row index c) for every (element, corner)
+        const int e1 = tid / NK, k = tid - e1 * NK;
+        const int b0 = k & 1, b1 = (k >> 1) & 1;
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < L; ++j) acc = fma(b1 ? sl1[j] : sl0[j], sP[(e1 * NCOL + j) * 2 + b0], acc);
+        rc[(long long)(e0 + e1) * NK + k] = acc;
+        if (rc0) rc0[(long long)(e0 + e1) * NK + k] = acc;
+      }
+    }
+    double* tmp = in; in = ou; ou = tmp;
+  }
+  // ---- zloc = block solve (an even number of passes ends in the buffer it started from); partial zloc . r
+#pragma unroll
+  for (int q = 0; q < PER; ++q) {
+    const int t = tid + q * NT;
+    if (t < ne * NP) {
+      const int e1 = t / NP, p = t - e1 * NP;
+      const double val = sA[e1 * ESZ + (p / L) * PI + (p % L)];
+      zloc[(long long)e0 * NP + t] = val;
+      sums[1] = fma(val, rr[q], sums[1]);
+    }
+  }
+  grid_sum_finish<2>(sums, part, counter, out, sred);
+}
+
+// Coarse levels with their share of z.r.  Threads [0, vthreads): one vertex each, xv = d1inv * rv with rv = the sum of the corner
+// sums over ALL (element, corner) entries of the vertex on ALL ranks (`assembled`: rc already holds that total in every copy after the
+// vertex gather-scatter; otherwise it is summed here from the local entries); contribution to z.r: xv * (sum of the LOCAL entries
+// rc0), which adds up to sum_v xv rv over the ranks.  Then one warp per local aggregate: ra = sum of its elements' corner sums
+// (sum_k phi_k = 1); entries of ra owned by other ranks are zeroed (filled by the all-reduce).  out[0] receives sum xv rv_local.
+__global__ void __launch_bounds__(128) k_pm_coarse_dot(int nv, const int* __restrict__ voff, const int* __restrict__ vent,
+                                                       const double* __restrict__ d1inv, const double* __restrict__ rc,
+                                                       const double* __restrict__ rc0, double* __restrict__ xv, int nagg, int nagg_loc,
+                                                       int agg_first, const int* __restrict__ aoff, const int* __restrict__ aent, int nk,
+                                                       double* __restrict__ ra, int assembled, const CGState* skip, int init,
+                                                       double* part, unsigned* counter, double* out) {
+  if (!init && skip && skip->done) return;
+  __shared__ double sred[32];
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int vthreads = ((max(nv, nagg) + 31) / 32) * 32;
+  double contrib[1] = {0.0};
+  if (t < vthreads) {
+    if (t < nv) {
+      double sl = 0.0;
+      for (int j = voff[t]; j < voff[t + 1]; ++j) sl += rc0[vent[j]];
+      const double st = assembled ? rc[vent[voff[t]]] : sl;
+      const double xx = d1inv[t] * st;
+      xv[t] = xx;
+      contrib[0] = xx * sl;
+    }
+    if (t < nagg && (t < agg_first || t >= agg_first + nagg_loc)) ra[t] = 0.0;
+  } else {
+    const int a = (t - vthreads) >> 5, lane = t & 31;
+    if (a < nagg_loc) {
+      double s = 0.0;
+      for (int j = aoff[a] + lane; j < aoff[a + 1]; j += 32) {
+        const double* q = rc0 + (long long)aent[j] * nk;
+        double se = 0.0;
+        for (int k = 0; k < nk; ++k) se += q[k];
+        s += se;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+      if (lane == 0) ra[agg_first + a] = s;
+    }
+  }
+  grid_sum_finish<1>(contrib, part, counter, out, sred);
+}
+
+// x2 = A2inv ra (one warp per row) + the aggregate level's share ra^T x2 of z.r; the last block then updates the CG scalars from
+// sc[0] = |r|^2 (Nek norm), sc[1] = zloc.r, sc[2] = sum xv rv, and its own sum: what k_pcg_update + k_pm_apply2 used to do.
+__global__ void __launch_bounds__(128) k_pm_gemv_fin(int nagg, const double* __restrict__ A, const double* __restrict__ ra,
+                                                     double* __restrict__ x2, const double* __restrict__ sc, CGState* cgs, int init,
+                                                     double* part, unsigned* counter, double* out) {
+  if (!init && cgs->done) return;
+  __shared__ double sred[32];
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  double contrib[1] = {0.0};
+  if (row < nagg) {
+    double s = 0.0;
+    for (int j = lane; j < nagg; j += 32) s = fma(A[(long long)row * nagg + j], ra[j], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane == 0) { x2[row] = s; contrib[0] = s * ra[row]; }
+  }
+  if (grid_sum_finish<1>(contrib, part, counter, out, sred) && threadIdx.x == 0) {
+    CGState* s = cgs;
+    const double rn = sqrt(fmax(sc[0], 0.0) / s->vol);
+    if (init) {
+      s->rtz1 = 1.0; s->rtz2 = 1.0; s->beta = 0.0; s->alpha = 0.0;
+      s->rnorm = rn; s->iter = 0;
+      s->done = (rn <= s->tol) || (s->maxit <= 0);
+    } else {
+      s->rtz2 = s->rtz1;
+      s->rnorm = rn;
+      s->iter += 1;
+      s->done = (rn <= s->tol) || (s->iter >= s->maxit) || !(rn == rn);
+    }
+    if (!s->done) {
+      const double rtz = (sc[1] + sc[2]) + out[0];
+      s->rtz1 = rtz;
+      s->beta = (s->iter == 0) ? 0.0 : rtz / s->rtz2;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- host helpers
 // symmetric eigen-decomposition by cyclic Jacobi rotations (n <= 8): A = V diag(w) V^T, A destroyed
 static void jacobi_eig(int n, double* A, double* V, double* w) {
@@ -714,7 +976,7 @@ static int pm_download(Ctx* c, std::vector<double>& h, const double* d, long lon
 
 void pm_free(PMG& m) {
   cudaFree(m.S); cudaFree(m.lam); cudaFree(m.vid); cudaFree(m.voff); cudaFree(m.vent); cudaFree(m.d1inv); cudaFree(m.agg);
-  cudaFree(m.aoff); cudaFree(m.aent); cudaFree(m.A2inv); cudaFree(m.rc); cudaFree(m.xv); cudaFree(m.ra); cudaFree(m.x2);
+  cudaFree(m.aoff); cudaFree(m.aent); cudaFree(m.A2inv); cudaFree(m.rc); cudaFree(m.rc0); cudaFree(m.xv); cudaFree(m.ra); cudaFree(m.x2);
   cudaFree(m.vc_off); cudaFree(m.vc_col); cudaFree(m.vc_val); cudaFree(m.vc_odinv); cudaFree(m.vc_vagg); cudaFree(m.vc_aoff);
   cudaFree(m.vc_aent); cudaFree(m.vc_A2inv); cudaFree(m.vc_rv); cudaFree(m.vc_x); cudaFree(m.vc_r1);
   m = PMG();
@@ -822,6 +1084,15 @@ static int pm_vcycle(Ctx* c, PMG& m, const CGState* skip) {
 int pm_apply(Ctx* c, int set, const double* r, double* z, int mode, int prof_slot) {
   PMG& m = c->pmg[(set && c->has_adj_masks) ? 1 : 0];      // without separate adjoint masks both problems share one E
   if (!m.ready) { nsb_set_error("pmg: preconditioner not set up"); return 1; }
+  if (mode == 0 && c->pc_kind == 1 && c->pcg_fused && c->ldim == 3) {
+    // operator-level entry (nsb_op_pc_apply) through the kernels of the fused CG tail: the init form of pm_pcg_tail gives the
+    // element-block part in pz and the coarse-level values xv, x2; their interpolation is added with the set-up's prolongation.
+    NSB_TRY(vk_copy(c, c->pk[0], r, c->n2));
+    NSB_TRY(pm_pcg_tail(c, set, 1, 0));
+    NSB_TRY(pm_prolong(c, m, m.xv, m.x2, c->pk[4]));
+    if (z != c->pz) NSB_TRY(vk_copy(c, z, c->pz, c->n2));
+    return vk_axpy(c, z, 1.0, c->pk[4], c->n2);
+  }
   CGState* sp = c->cgs + 3;
   const CGState* skip = mode ? sp : nullptr;
   NSB_TRY(pm_restrict(c, m, r, skip));
@@ -846,6 +1117,36 @@ int pm_apply(Ctx* c, int set, const double* r, double* z, int mode, int prof_slo
                        r, z, c->nel, m.S, m.lam, m.xv, m.vid, x2p, m.agg, sp, kmode, c->red_part, c->red_count, c->red_out)));
   }
   if (mode && c->nranks > 1) NSB_TRY(vk_cg_finalize_multi(c, sp, 1, 5));
+  return 0;
+}
+
+// The fused tail of one pressure-CG iteration (3-D): CG update + norm + restriction + element-block solves (k_pcg_fused), the vertex
+// and aggregate levels with their shares of z.r (k_pm_coarse_dot), the dense aggregate solve and the CG scalar update
+// (k_pm_gemv_fin).  Multi-rank: ONE vertex halo exchange (assembles rc) and ONE all-reduce (aggregate sums + the three scalars)
+// instead of the former norm / vertex halo / aggregate / z.r sequence.  The three scalars live behind the aggregate sums: ra[nagg..nagg+2].
+int pm_pcg_tail(Ctx* c, int set, int init, int prof_slot) {
+  PMG& m = c->pmg[(set && c->has_adj_masks) ? 1 : 0];
+  if (!m.ready) { nsb_set_error("pmg: preconditioner not set up"); return 1; }
+  CGState* sp = c->cgs + 3;
+  double* sc = m.ra + m.nagg;
+  const bool multi = c->nranks > 1;
+  PM_DISPATCH(c, (k_pcg_fused<D, L><<<(c->nel + Pm2<D, L>::EPB - 1) / Pm2<D, L>::EPB, Pm2<D, L>::NT, 0, c->stream>>>(
+                     c->pk[0], c->pk[1], c->pk[2], c->pk[3], c->bm2inv, c->pz, m.rc, multi ? m.rc0 : nullptr, c->nel, m.S, m.lam, sp, init,
+                     c->red_part, c->red_count, sc)));
+  if (prof_slot > 0) cudaEventRecord(c->prof_ev[prof_slot], c->stream);
+  if (multi) NSB_TRY(gs_dssum_map(c, c->gsv, c->p2pv, m.rc, 1, 0, sp));                 // vertex sums across elements and ranks
+  const int vthreads = ((std::max(m.nv, m.nagg) + 31) / 32) * 32;
+  const long long nthr = vthreads + 32LL * m.nagg_loc;
+  k_pm_coarse_dot<<<(int)((nthr + 127) / 128), 128, 0, c->stream>>>(m.nv, m.voff, m.vent, m.d1inv, m.rc, multi ? m.rc0 : m.rc, m.xv, m.nagg,
+                                                                   m.nagg_loc, m.agg_first, m.aoff, m.aent, (c->ldim == 3) ? 8 : 4, m.ra,
+                                                                   multi ? 1 : 0, sp, init, c->red_part, c->red_count, sc + 2);
+  nsb_count_launch();
+  if (multi) NSB_TRY(vk_allreduce_sum(c, m.ra, m.nagg + 3));
+  k_pm_gemv_fin<<<(m.nagg * 32 + 127) / 128, 128, 0, c->stream>>>(m.nagg, m.A2inv, m.ra, m.x2, sc, sp, init, c->red_part, c->red_count,
+                                                                c->red_out);
+  nsb_count_launch();
+  NSB_CUDA(cudaGetLastError());
+  if (prof_slot > 0) cudaEventRecord(c->prof_ev[prof_slot + 1], c->stream);
   return 0;
 }
 
@@ -993,7 +1294,8 @@ int pm_setup(Ctx* c, int set, int nagg_req) {
   NSB_TRY(pm_upload(&m.aent, aent));
   NSB_TRY(pm_upload(&m.rc, std::vector<double>((size_t)nel * NK, 0.0)));
   NSB_TRY(pm_upload(&m.xv, std::vector<double>(m.nv, 0.0)));
-  NSB_TRY(pm_upload(&m.ra, std::vector<double>(m.nagg, 0.0)));
+  NSB_TRY(pm_upload(&m.ra, std::vector<double>(m.nagg + 3, 0.0)));      // + |r|^2, zloc.r, sum xv rv (pm_pcg_tail)
+  NSB_TRY(pm_upload(&m.rc0, std::vector<double>((size_t)nel * NK, 0.0)));
   NSB_TRY(pm_upload(&m.x2, std::vector<double>(m.nagg, 0.0)));
   // ---- distance-2 colouring of the GLOBAL vertex graph (adjacent = share an element): every rank gathers the corner ids
   //      of all elements and runs the same greedy colouring, so that the probing below is consistent across ranks

@@ -132,6 +132,7 @@ void sem_build_constmats(int lx1, int lx2, int lxd, ConstMats* cm) {
   double z2[12], zd[18];
   sem_zwgll(lx1, cm->z1, cm->w1);
   sem_zwgl(lx2, z2, cm->w2);
+  for (int i = 0; i < lx2; ++i) cm->hat1[i] = 0.5 * (1.0 + z2[i]);
   sem_zwgl(lxd, zd, cm->wd);
   sem_deriv(lx1, cm->z1, cm->D);
   transpose(lx1, lx1, cm->D, cm->Dt);

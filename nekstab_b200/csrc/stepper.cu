@@ -67,7 +67,8 @@ static int cg_state_poll(Ctx* c, int first, int count, bool* all_done) {
 }
 
 // ---- sampling profiler: kinds 0 pcg_gradt, 1 dssum(3 fields), 2 pcg_div, 3 pcg_update, 4 hcg_axhelm, 5 hcg_update,
-//      6 advab, 7 helmholtz dssum.  Events bracket ONE launch each; elapsed times are read after the next host poll.
+//      6 advab, 7 helmholtz dssum, 8-10 preconditioner pieces, 11-12 Gram-Schmidt, 13 fused pressure-CG tail.  Events bracket ONE
+//      launch each; elapsed times are read after the next host poll.
 static inline void prof_mark(Ctx* c, bool on, int slot) {
   if (on) cudaEventRecord(c->prof_ev[slot], c->stream);
 }
@@ -230,9 +231,16 @@ int st_pressure(Ctx* c, int adj, int* iters) {
   const bool proj = c->proj_max > 0;
   if (proj) NSB_TRY(proj_pre(c, adj));
   NSB_TRY(cg_state_setup(c, 3, 1, c->tol_p, c->vol2, c->maxit_p));
-  NSB_TRY(vk_pcg_init(c, adj));
   const bool pc = c->pc_kind != 0;
-  if (pc) NSB_TRY(pm_apply(c, adj, c->pk[0], c->pz, 1));
+  // 3-D + three-level preconditioner: everything between the E application and the next direction is one fused tail
+  // (pm_pcg_tail, csrc/pmg.cu); otherwise the separate update / preconditioner kernels
+  const bool fused = c->pc_kind == 1 && c->pcg_fused && c->ldim == 3;
+  if (fused) {
+    NSB_TRY(pm_pcg_tail(c, adj, 1, 0));
+  } else {
+    NSB_TRY(vk_pcg_init(c, adj));
+    if (pc) NSB_TRY(pm_apply(c, adj, c->pk[0], c->pz, 1));
+  }
   bool done = false;
   int issued = 0;
   Ctx::GraphEntry* ge = graphs_ok(c) ? &c->graph_p[adj] : nullptr;
@@ -247,10 +255,14 @@ int st_pressure(Ctx* c, int adj, int* iters) {
       NSB_TRY(ek_pcg_div(c, adj));
       if (c->nranks > 1) NSB_TRY(vk_cg_finalize_multi(c, sp, 1, 2));
       prof_mark(c, sm, 7);
-      NSB_TRY(vk_pcg_update(c, adj));
-      prof_mark(c, sm, 8);
-      if (pc) NSB_TRY(pm_apply(c, adj, c->pk[0], c->pz, 1, sm ? 9 : 0));
-      prof_mark(c, sm, 11);
+      if (fused) {
+        NSB_TRY(pm_pcg_tail(c, adj, 0, sm ? 8 : 0));        // records events 8 (after k_pcg_fused) and 9 (after the coarse levels)
+      } else {
+        NSB_TRY(vk_pcg_update(c, adj));
+        prof_mark(c, sm, 8);
+        if (pc) NSB_TRY(pm_apply(c, adj, c->pk[0], c->pz, 1, sm ? 9 : 0));
+        prof_mark(c, sm, 11);
+      }
     }
     return 0;
   };
@@ -260,7 +272,10 @@ int st_pressure(Ctx* c, int adj, int* iters) {
     else NSB_TRY(batch(sample));
     issued += c->check_every_p;
     NSB_TRY(cg_state_poll(c, 3, 1, &done));
-    if (sample) { const int kinds[7] = {0, 1, 2, 3, 8, 9, 10}; prof_collect(c, kinds, pc ? 7 : 4, 4); }
+    if (sample) {
+      if (fused) { const int kinds[5] = {0, 1, 2, 13, 9}; prof_collect(c, kinds, 5, 4); }
+      else { const int kinds[7] = {0, 1, 2, 3, 8, 9, 10}; prof_collect(c, kinds, pc ? 7 : 4, 4); }
+    }
     if (issued > c->maxit_p + c->check_every_p) break;
   }
   NSB_TRY(p2p_check_error(c));

@@ -256,7 +256,7 @@ class NekStabB200:
         return {k: getattr(s, k) for k, _ in Stats._fields_}
 
     PROFILE_KINDS = ["pcg_gradt", "dssum", "pcg_div", "pcg_update", "hcg_axhelm", "hcg_update", "advab", "hcg_dssum",
-                     "pcg_pc_restrict", "pcg_pc_coarse", "pcg_pc_apply", "orth_multidot", "orth_multiaxpy"]
+                     "pcg_pc_restrict", "pcg_pc_coarse", "pcg_pc_apply", "orth_multidot", "orth_multiaxpy", "pcg_fused"]
 
     def profile(self, enable=-1):
         ms = np.zeros(16); cnt = np.zeros(16, dtype=np.int64)

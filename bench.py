@@ -397,14 +397,6 @@ def roofline_block(prof, st, K, n_loc, precond, world):
     return roof
 
 
-def fp64_peak():
-    try:
-        with open(os.path.join(ROOT, "profiles", "fp64_peak.json")) as f:
-            return json.load(f)
-    except Exception:
-        return None
-
-
 def arnoldi_leg(pl: Plumbing, ctx, case, n_glob, nsteps_full, dt, m_iters, k_dim):
     """M iterations of arnoldi_factorization (core/krylov_decomposition.f:73-99) on the resident basis: wall time per iteration
     ("Time per iteration", :92-99), matvec / orthogonalisation split, then the CGS2/DGKS pass against k_dim resident vectors."""
@@ -615,6 +607,7 @@ def main():
     e2e_value = n_glob * K / e2e_s
     vec_bytes = (vin.size + pin.size) * 8
 
+    fp64_tf = ctx.fp64_peak()                 # FP64 FMA throughput measured live (register-resident DFMA loop, csrc/vec_kernels.cu)
     arn = None
     if do_arn:
         arn = arnoldi_leg(pl, ctx, case, n_glob, nsteps_full, dt, args.arnoldi, k_dim)
@@ -623,13 +616,11 @@ def main():
     if rank == 0:
         roof = roofline_block(prof, tm, K, case.n, args.precond, world)
         if roof and "advab" in roof["kernels"]:
-            fp = fp64_peak()
             adv = roof["kernels"]["advab"]
             adv["flops_per_point"] = 2.7e3
             adv["TFLOPs"] = 2.7e3 * case.n / (adv["avg_ms"] * 1e-3) / 1e12
-            if fp:
-                adv["fp64_peak_TFLOPs_measured"] = fp.get("fp64_fma_tflops")
-                adv["frac_of_measured_fp64_peak"] = adv["TFLOPs"] / fp["fp64_fma_tflops"] if fp.get("fp64_fma_tflops") else None
+            adv["fp64_fma_peak_TFLOPs_measured"] = fp64_tf
+            adv["frac_of_measured_fp64_peak"] = adv["TFLOPs"] / fp64_tf if fp64_tf else None
         cfg = workload_config(world, args.precond, args.tol, args.small)
         cfg.update({"dt": dt, "nsteps_per_matvec_T1": nsteps_full, "residual_projection_mxprev": args.mxprev,
                     "pres_iters_per_step": tm["pres_iters"] / K, "helm_iters_per_comp_per_step": tm["helm_iters"] / K / 3,

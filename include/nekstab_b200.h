@@ -25,6 +25,11 @@
 extern "C" {
 #endif
 
+/* Marks a pointer parameter that addresses ONE value (an output or in/out scalar), as opposed to an array: the Fortran binding
+ * (nekstab_b200/fortran/nekstab_b200_c.f90, generated from this header by tools/gen_fortran_bindings.py) declares it as a scalar
+ * passed by reference, every other pointer as an assumed-size array. */
+#define NSB_SCALAR
+
 /* ------------------------------------------------------------------ communicator (NCCL over NVLink)
  * Replaces Nek5000's MPI wrappers reached from the path: gop/glsc3 (core/krylov_subspace.f:37-43),
  * gslib gs_op under dssum, bcast/nekgsync (core/matvec.f:7,18).  Rank 0 creates the id, the host
@@ -58,7 +63,7 @@ int nsb_set_baseflow(const double* ubase, const double* vbase, const double* wba
 int nsb_set_sponge(const double* spng_fun);
 /* prepare_linearized_solver (core/matvec.f:1-52): ctarg = compute_cfl(base flow, dt=1);
  * dt = cfl_target/ctarg; nsteps = ceiling(end_time/dt); dt = end_time/nsteps. Stores dt, nsteps. */
-int nsb_prepare_linearized_solver(double end_time, double cfl_target, double* dt, int* nsteps, double* ctarg);
+int nsb_prepare_linearized_solver(double end_time, double cfl_target, double* NSB_SCALAR dt, int* NSB_SCALAR nsteps, double* NSB_SCALAR ctarg);
 int nsb_set_timestep(double dt, int nsteps);
 /* Nek5000's `ifvcor` (no outflow-type boundary => E = D B^-1 D^T has the constant null vector => `ortho` on the
  * pressure right-hand side and solution) for the direct and the adjoint mask set: 1 / 0, or -1 to decide
@@ -91,9 +96,9 @@ int nsb_vec_zero(int slot);                                      /* krylov_zero 
 int nsb_vec_cmult(int slot, double alpha);                       /* krylov_cmult :90  */
 int nsb_vec_add2(int p, int q);                                  /* krylov_add2  :116 */
 int nsb_vec_sub2(int p, int q);                                  /* krylov_sub2  :142 */
-int nsb_vec_inner_product(int p, int q, double* alpha);          /* krylov_inner_product :24 (NaN -> error) */
-int nsb_vec_norm(int p, double* alpha);                          /* krylov_norm :58 */
-int nsb_vec_normalize(int p, double* alpha);                     /* krylov_normalize :71 */
+int nsb_vec_inner_product(int p, int q, double* NSB_SCALAR alpha);          /* krylov_inner_product :24 (NaN -> error) */
+int nsb_vec_norm(int p, double* NSB_SCALAR alpha);                          /* krylov_norm :58 */
+int nsb_vec_normalize(int p, double* NSB_SCALAR alpha);                     /* krylov_normalize :71 */
 /* krylov_matmul (core/krylov_subspace.f:214-258): slot_out = sum_i y(i) * Q(first+i), i<k */
 int nsb_basis_gemv(int k, int first_slot, const double* y, int slot_out);
 /* basis rotation of schur_condensation (core/eigensolvers.f:466-474): Q(:,1:k) <- Q(:,1:k) * S(k,k),
@@ -125,9 +130,17 @@ enum {
 int nsb_matvec(int mode, int slot_in, int slot_out);
 /* nonlinear_forward_map (core/newton_krylov.f:336-378): slot_f = phi_T(slot_q) - slot_q with the FULL Navier-Stokes
  * stepper (same kernels, advection term C(u)u; the Dirichlet data are the boundary values of slot_q), then ubase <- slot_q. */
+/* Per-step host hook.  The reference calls the user's `nekstab_usrchk()` on the host before EVERY `nek_advance` of a matvec
+ * (core/matvec.f:221,304; core/newton_krylov.f:358).  nsb_matvec keeps all `nsteps` steps on the device; a registered callback is
+ * invoked on the calling host thread before step `istep` (1-based, restarted by every matvec like Nek's istep, core/matvec.f:216)
+ * is enqueued, with the physical time at the start of the step.  The hook may call the nsb_set_* entry points (e.g. a time-dependent
+ * base flow or sponge); it must not call nsb_matvec.  Device work of the previous step may still be in flight: use nsb_vec_download
+ * to synchronise.  NULL (the default) removes the hook; the shipped cases use nekstab_usrchk only at istep == 0 (1cyl.usr:11-31). */
+typedef void (*nsb_step_callback)(int istep, double time, void* user);
+int nsb_set_step_callback(nsb_step_callback cb, void* user);
 int nsb_nonlinear_forward_map(int slot_q, int slot_f);
 /* prepare_linearized_solver evaluated on the velocity in `slot` (newton_krylov re-prepares on every iterate, :69). */
-int nsb_prepare_solver_from_slot(int slot, double end_time, double cfl_target, double* dt, int* nsteps, double* ctarg);
+int nsb_prepare_solver_from_slot(int slot, double end_time, double cfl_target, double* NSB_SCALAR dt, int* NSB_SCALAR nsteps, double* NSB_SCALAR ctarg);
 /* Adjoint problems may use different Dirichlet masks (outflow 'O' -> 'v', 1cyl.usr:126-132). NULL = same. */
 int nsb_set_adjoint_masks(const double* v1mask, const double* v2mask, const double* v3mask);
 
@@ -146,6 +159,8 @@ int nsb_get_stats(nsb_stats* out, int reset);
  * 4 Helmholtz-CG axhelm, 5 Helmholtz-CG vector update, 6 advection, 7 Helmholtz dssum, 8-10 pressure preconditioner
  * (8 restriction to the element corners, 9 vertex / aggregate levels, 10 element blocks + prolongation + z.r), 11 unused. */
 int nsb_profile(int enable, double* ms_sum, long long* count);
+/* measurement aid: FP64 FMA throughput of the device in TFLOP/s (register-resident DFMA loop, best of 4 after a warm-up launch) */
+int nsb_fp64_peak(double* NSB_SCALAR tflops);
 
 /* ------------------------------------------------------------------ operator-level entry points
  * Mirrors of the Nek5000 routines on the path, taking HOST arrays (copied in and out) so that every
@@ -154,24 +169,24 @@ int nsb_profile(int enable, double* ms_sum, long long* count);
  * perturb.f advabp/advabp_adjoint; hmholtz.f hmholtz (Jacobi-PCG); navier1.f esolver (here Jacobi-PCG). */
 int nsb_op_axhelm(const double* u, double h1, double h2, double* w);
 int nsb_op_dssum(double* u);
-int nsb_op_glsc3(const double* a, const double* b, const double* c, double* out);
+int nsb_op_glsc3(const double* a, const double* b, const double* c, double* NSB_SCALAR out);
 int nsb_op_opgradt(const double* p, double* wx, double* wy, double* wz);
 int nsb_op_opdiv(const double* ux, const double* uy, const double* uz, double* q);
 int nsb_op_cdabdtp(const double* p, double* ep);
 int nsb_op_advab(int adjoint, const double* upx, const double* upy, const double* upz,
                  double* fx, double* fy, double* fz);            /* mass-weighted, un-assembled */
 int nsb_op_hmholtz(double* ux, double* uy, double* uz, const double* rx, const double* ry, const double* rz,
-                   double h1, double h2, int* iters);            /* rhs un-assembled; returns du */
-int nsb_op_esolver(const double* g, double* phi, int* iters);
+                   double h1, double h2, int* NSB_SCALAR iters);            /* rhs un-assembled; returns du */
+int nsb_op_esolver(const double* g, double* phi, int* NSB_SCALAR iters);
 /* z = M^-1 r, the preconditioner selected with nsb_set_pressure_preconditioner(1, ..), on mesh-2 arrays */
 int nsb_op_pc_apply(int adjoint, const double* r, double* z);
 /* set-up data of that preconditioner (direct mask set) as doubles: which 0: local aggregate of every element [nelv];
  * 1: diag(P^T E P) per local vertex (ascending global corner id); 2: (Pa^T E Pa)^-1 [nagg*nagg];
  * 3: {local vertices, aggregates (all ranks), colours used for probing, local aggregates, first global aggregate id} */
-int nsb_pc_get(int which, double* out, long long* count);
-int nsb_op_cfl(const double* ux, const double* uy, const double* uz, double dt, double* cfl);
+int nsb_pc_get(int which, double* out, long long* NSB_SCALAR count);
+int nsb_op_cfl(const double* ux, const double* uy, const double* uz, double dt, double* NSB_SCALAR cfl);
 /* named geometry arrays for parity checks: "bm1","binvm1","jacm1","g1".."g6","bm2","ediag","hdiagA","vmult" */
-int nsb_get_field(const char* name, double* out, long long* count);
+int nsb_get_field(const char* name, double* out, long long* NSB_SCALAR count);
 /* Host-only views of the gather-scatter plan (no CUDA/NCCL needed): the multi-rank map construction of gs_setup
  * (replaces gslib gs_setup's discovery of shared nodes) exposed for CPU tests with any transport.
  * 1) nsb_gs_host_candidates: this rank's element-surface global ids (ascending) -- what ranks all-gather;
@@ -179,7 +194,7 @@ int nsb_get_field(const char* name, double* out, long long* count);
  *    sizes_out = {nseg, len(seg_idx), nneighbours, nshared, len(rseg_pos), 0,0,0};
  * 3) nsb_gs_host_get(which): 0 seg_off 1 seg_idx 2 nbr_rank 3 nbr_off 4 send_seg 5 send_base 6 send_cnt 7 rseg_off
  *    8 rseg_pos 9 rseg_cnt 10 rseg_nbefore. */
-int nsb_gs_host_candidates(int ldim, int lx1, int nelv, const long long* glo_num, long long* ids_out, long long* count);
+int nsb_gs_host_candidates(int ldim, int lx1, int nelv, const long long* glo_num, long long* ids_out, long long* NSB_SCALAR count);
 int nsb_gs_host_plan(int rank, int nranks, const long long* counts, const long long* ids, int sizes_out[8]);
 int nsb_gs_host_get(int which, int* out);
 /* Host-only pieces of the pressure-preconditioner set-up (no CUDA needed; CPU tests):
@@ -189,7 +204,7 @@ int nsb_gs_host_get(int which, int* out);
  * the 1-D FDM factors for given end weights: S[lx2*lx2] (row = node, column = mode, S^T M S = I), lam[lx2];
  * dense SPD inverse in place (row-major n x n). */
 int nsb_pm_host_aggregates(int ldim, int nel, const double* cent, int nagg, int* agg_out);
-int nsb_pm_host_colouring(int nel, int nk, const long long* vglo, int* colour_out, int* ncolours);
+int nsb_pm_host_colouring(int nel, int nk, const long long* vglo, int* colour_out, int* NSB_SCALAR ncolours);
 int nsb_pm_host_fdm_1d(int lx1, double w_first, double w_last, double* S, double* lam);
 int nsb_pm_host_spd_inverse(int n, double* A);
 long long nsb_n(void);   /* nelv*lx1^ldim */
@@ -202,19 +217,19 @@ int nsb_arnoldi_factorization(int mode, int first_slot, double* H, int ldh, int 
 /* krylov_schur (core/eigensolvers.f:141-388): returns Ritz values (sorted by decreasing magnitude),
  * residuals, eigenvectors of H (column-major complex interleaved, k x k) and the count of converged. */
 int nsb_krylov_schur(int mode, int k_dim, int schur_tgt, double eigen_tol, double schur_del, int seed_slot,
-                     double* vals_re, double* vals_im, double* residual, double* vecs_reim, int* n_converged,
-                     int* schur_cnt, int max_restarts);
-int nsb_schur_condensation(int* mstart, double* H, int ldh, int first_slot, int ksize, int schur_tgt, double schur_del); /* :395 */
-int nsb_select_eigenvalues(int* selected, int* cnt, const double* vals_re, const double* vals_im, double delta, int nev, int n); /* :729 */
+                     double* vals_re, double* vals_im, double* residual, double* vecs_reim, int* NSB_SCALAR n_converged,
+                     int* NSB_SCALAR schur_cnt, int max_restarts);
+int nsb_schur_condensation(int* NSB_SCALAR mstart, double* H, int ldh, int first_slot, int ksize, int schur_tgt, double schur_del); /* :395 */
+int nsb_select_eigenvalues(int* selected, int* NSB_SCALAR cnt, const double* vals_re, const double* vals_im, double delta, int nev, int n); /* :729 */
 /* ts_gmres (core/newton_krylov.f:175-297): solves matvec(mode) * sol = rhs; slots first..first+ksize hold the basis */
 int nsb_ts_gmres(int mode, int rhs_slot, int sol_slot, int first_slot, int work_slot, int maxiter, int ksize, double tol,
-                 int* calls, double* final_res);
+                 int* NSB_SCALAR calls, double* NSB_SCALAR final_res);
 /* newton_krylov (core/newton_krylov.f:5-168), fixed-point branch (uparam(1) = 2): Newton iterations on phi_T(q) - q = 0
  * with ts_gmres on newton_linearized_map; squared residual norms against tol as in the reference.  Returns 0 when
  * converged, 3 when maxiter_newton was reached. */
 int nsb_newton_krylov(int q_slot, int f_slot, int dq_slot, int work_slot, int first_slot, int k_dim, double end_time,
-                      double cfl_target, double tol, int maxiter_newton, int maxiter_gmres, int* newton_iters,
-                      double* residual_out, double* hist, long long* calls_out);
+                      double cfl_target, double tol, int maxiter_newton, int maxiter_gmres, int* NSB_SCALAR newton_iters,
+                      double* NSB_SCALAR residual_out, double* hist, long long* NSB_SCALAR calls_out);
 /* LAPACK wrappers exactly as core/lapack_wrapper.f (schur:7, ordschur:70, eig:129, lstsq:287). */
 int nsb_lapack_eig(const double* A, int n, double* vals_re, double* vals_im, double* vecs_reim);
 int nsb_lapack_schur(double* A, int n, double* vecs, double* vals_re, double* vals_im);

@@ -319,6 +319,12 @@ extern "C" int nsb_set_timestep(double dt, int nsteps) {
   c->dt = dt; c->nsteps = nsteps;
   return 0;
 }
+extern "C" int nsb_set_step_callback(nsb_step_callback cb, void* user) {
+  REQUIRE_CTX();
+  c->step_cb = cb;
+  c->step_cb_user = user;
+  return 0;
+}
 extern "C" int nsb_set_projection(int mxprev) {
   REQUIRE_CTX();
   if (mxprev < 0 || mxprev > 200) { nsb_set_error("nsb_set_projection: mxprev out of range"); return 1; }
@@ -621,6 +627,12 @@ extern "C" int nsb_profile(int enable, double* ms_sum, long long* count) {
     for (int i = 0; i < 16; ++i) { c->prof_ms[i] = 0; c->prof_cnt[i] = 0; }
   }
   return 0;
+}
+// FP64 FMA throughput of this GPU (TFLOP/s), measured with a register-resident DFMA loop: the roofline denominator of the advection kernel
+extern "C" int nsb_fp64_peak(double* tflops) {
+  REQUIRE_CTX();
+  if (!tflops) { nsb_set_error("nsb_fp64_peak: NULL output"); return 1; }
+  return vk_fp64_peak(c, tflops);
 }
 extern "C" long long nsb_n(void) { return g_ctx ? g_ctx->n : 0; }
 extern "C" long long nsb_n2(void) { return g_ctx ? g_ctx->n2 : 0; }

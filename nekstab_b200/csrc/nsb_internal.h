@@ -243,6 +243,10 @@ struct Ctx {
   double prof_ms[16] = {0};
   long long prof_cnt[16] = {0};
 
+  // per-step host hook (the reference's nekstab_usrchk before every nek_advance, core/matvec.f:221)
+  nsb_step_callback step_cb = nullptr;
+  void* step_cb_user = nullptr;
+
   // stats
   nsb_stats stats = {0, 0, 0, 0, 0.0};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -331,6 +335,7 @@ int vk_multidot_raw(Ctx* c, int k, const double* Q, long long vlen, const double
 int vk_multiaxpy_raw(Ctx* c, int k, const double* Q, long long vlen, const double* f, double a, const double* h_dev, double sign,
                      double* out);
 int vk_rotate(Ctx* c, int k, int first_slot, const double* S_dev, int lds);
+int vk_fp64_peak(Ctx* c, double* tflops);
 int vk_rotate_pair(Ctx* c, double* are, double* aim, double g, double d, long long n);
 int vk_wavemaker(Ctx* c, const double* dre, const double* dim, const double* are, const double* aim, double* wm);
 

@@ -346,6 +346,7 @@ int st_linearized_map(Ctx* c, int adjoint, const double* vin, double* vout) {
   NSB_TRY(vk_copy(c, c->u, vin, dn));            // nopcopy(vxp,..,prp <- q)   core/matvec.f:212
   NSB_TRY(vk_copy(c, c->pr, vin + dn, c->n2));
   for (int istep = 1; istep <= c->nsteps; ++istep) {
+    if (c->step_cb) c->step_cb(istep, (istep - 1) * c->dt, c->step_cb_user);     // nekstab_usrchk(), core/matvec.f:221,304
     int rc = one_step(c, istep, adjoint);
     if (rc) return rc;
     (void)adj;

@@ -561,3 +561,39 @@ int vk_wavemaker(Ctx* c, const double* dre, const double* dim, const double* are
   LAUNCH1(k_wavemaker, c->n, dre, dim, are, aim, wm, c->n, c->ldim);
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------- FP64 FMA peak (measurement aid)
+// Dependent-chain-free DFMA loop: 8 independent accumulators per thread, 2 flops per DFMA.  Gives the denominator for the FP64-pipe
+// utilisation of the dealiased advection kernel ("measure with an FMA microbenchmark before quoting utilisation").
+__global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x * 1e-3, x1 = x0 + 1.0, x2 = x0 + 2.0, x3 = x0 + 3.0, x4 = x0 + 4.0, x5 = x0 + 5.0, x6 = x0 + 6.0, x7 = x0 + 7.0;
+  for (int i = 0; i < iters; ++i) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  const double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+  if (s == 123.456) out[0] = s;                  // never true: keeps the loop alive
+}
+int vk_fp64_peak(Ctx* c, double* tflops) {
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+  const int blocks = sms * 8, iters = 1 << 16;
+  cudaEvent_t e0, e1;
+  NSB_CUDA(cudaEventCreate(&e0));
+  NSB_CUDA(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    NSB_CUDA(cudaEventRecord(e0, c->stream));
+    k_fp64_peak<<<blocks, 256, 0, c->stream>>>(c->red_out + 12, iters, 0.999999, 1e-9);
+    NSB_CUDA(cudaEventRecord(e1, c->stream));
+    NSB_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    NSB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    const double tf = 2.0 * 8.0 * iters * 256.0 * blocks / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;         // rep 0 = warm-up
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  nsb_count_launch(5);
+  *tflops = best;
+  return 0;
+}

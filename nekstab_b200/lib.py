@@ -64,6 +64,7 @@ _SIGS = {
     "nsb_set_timestep": [C.c_double, C.c_int],
     "nsb_set_ifvcor": [C.c_int, C.c_int],
     "nsb_set_projection": [C.c_int],
+    "nsb_set_step_callback": [C.c_void_p, C.c_void_p],
     "nsb_set_pressure_preconditioner": [C.c_int, C.c_int],
     "nsb_op_pc_apply": [C.c_int, _dp, _dp],
     "nsb_pc_get": [C.c_int, _dp, _lp],
@@ -91,6 +92,7 @@ _SIGS = {
     "nsb_newton_krylov": [C.c_int] * 6 + [C.c_double] * 3 + [C.c_int, C.c_int, _ip, _dp, _dp, _lp],
     "nsb_get_stats": [C.POINTER(Stats), C.c_int],
     "nsb_profile": [C.c_int, _dp, _lp],
+    "nsb_fp64_peak": [_dp],
     "nsb_op_axhelm": [_dp, C.c_double, C.c_double, _dp],
     "nsb_op_dssum": [_dp],
     "nsb_op_glsc3": [_dp] * 4,
@@ -237,6 +239,17 @@ class NekStabB200:
         _ck(self.lib.nsb_pc_get(which, _p(out), C.byref(cnt)))
         return out
 
+    STEP_CB = C.CFUNCTYPE(None, C.c_int, C.c_double, C.c_void_p)
+
+    def set_step_callback(self, fn):
+        """fn(istep, time) is called on the host before every step of a matvec (nekstab_usrchk, core/matvec.f:221); None removes it."""
+        if fn is None:
+            self._step_cb = None
+            _ck(self.lib.nsb_set_step_callback(None, None))
+            return
+        self._step_cb = self.STEP_CB(lambda istep, t, _u: fn(istep, t))        # keep a reference: ctypes callbacks must outlive the call
+        _ck(self.lib.nsb_set_step_callback(C.cast(self._step_cb, C.c_void_p), None))
+
     def set_projection(self, mxprev):
         _ck(self.lib.nsb_set_projection(int(mxprev)))
 
@@ -262,6 +275,11 @@ class NekStabB200:
         ms = np.zeros(16); cnt = np.zeros(16, dtype=np.int64)
         _ck(self.lib.nsb_profile(enable, _p(ms), _p(cnt)))
         return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.PROFILE_KINDS)}
+
+    def fp64_peak(self):
+        t = C.c_double()
+        _ck(self.lib.nsb_fp64_peak(C.byref(t)))
+        return t.value
 
     # ---- krylov vectors
     def vec_alloc(self, nslots):

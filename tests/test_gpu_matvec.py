@@ -157,3 +157,44 @@ def test_pressure_residual_projection_same_answer_fewer_iterations():
         assert np.array_equal(v2, ref)       # projection off => a pure, bit-reproducible function of the input
     finally:
         g.close()
+
+
+def test_step_callback():
+    """nsb_set_step_callback = the reference's `call nekstab_usrchk()` before every nek_advance (core/matvec.f:221): called once per
+    step with (istep, time); a hook that switches the sponge off half-way reproduces the oracle run that does the same."""
+    from nekstab_b200 import lib
+    from oracle.stepper import LinearizedStepper
+    c = CASES["box3d_n8_outflow"]
+    s = make_oracle(c)
+    g = lib.NekStabB200(c)
+    try:
+        nsteps, dt, half = 6, 2.0e-3, 3
+        g.set_params(1.0 / c.re, 1.0, 1e-13, 1e-13, 3000, 100000)
+        g.set_timestep(dt, nsteps)
+        g.vec_alloc(2)
+        v0 = smooth_field(c, 4).reshape((c.ldim,) + s.eshape)
+        p0 = np.zeros(s.eshape2)
+        g.vec_upload(0, v0, p0)
+        calls = []
+
+        def hook(istep, t):
+            calls.append((istep, t))
+            if istep == half + 1:
+                g.lib.nsb_set_sponge(None)
+        g.set_step_callback(hook)
+        g.matvec(lib.DIRECT, 0, 1)
+        g.set_step_callback(None)
+        v, _ = g.vec_download(1)
+        assert [i for i, _ in calls] == list(range(1, nsteps + 1))
+        assert all(abs(t - (i - 1) * dt) < 1e-15 for i, t in calls)
+        st = LinearizedStepper(s, c.ubase, c.re, c.spng_fun, solver="direct", ifvcor=c.ifvcor)
+        vo, _ = st.linearized_map(v0, p0, nsteps, dt, record=lambda i, u, p: setattr(st, "spng", None) if i == half else None)
+        assert energy_rel(s, v.reshape(vo.shape), vo) < 1e-10
+        # and it differs from the run that keeps the sponge (the hook really acted)
+        st2 = LinearizedStepper(s, c.ubase, c.re, c.spng_fun, solver="direct", ifvcor=c.ifvcor)
+        v2, _ = st2.linearized_map(v0, p0, nsteps, dt)
+        assert energy_rel(s, v.reshape(v2.shape), v2) > 1e-6
+        g.matvec(lib.DIRECT, 0, 1)                     # no hook any more
+        assert len(calls) == nsteps
+    finally:
+        g.close()

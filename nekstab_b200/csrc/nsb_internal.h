@@ -114,6 +114,8 @@ struct PMG {
   int *aoff = nullptr, *aent = nullptr;   // CSR local aggregate -> elements
   double* A2inv = nullptr;          // [nagg][nagg] (Pa^T E Pa)^-1
   double *rc = nullptr, *xv = nullptr, *ra = nullptr, *x2 = nullptr;   // work: corner sums, vertex values, aggregate sums (+3 CG scalars)/values
+  double* xc = nullptr;             // [nel][9] corner values of the vertex level + aggregate value per element (fused CG tail)
+  double* hat = nullptr;            // [lx2] hat function (1+z)/2 at the GL points
   double* rc0 = nullptr;            // un-assembled copy of rc (multi-rank: rc is summed across ranks in place)
   std::vector<int> h_agg;
   std::vector<double> h_d1, h_A2inv;

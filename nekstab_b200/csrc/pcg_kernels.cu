@@ -90,7 +90,8 @@ __device__ __forceinline__ void apply2_store(const double* __restrict__ M1, cons
 // ------------------------------------------------------------------------------------------------ gradt
 // MODE 0: w = D^T p.  MODE 1: CG direction with a pointwise preconditioner, p = dinvE*r + beta*pdir.  MODE 2: CG direction with the
 // three-level preconditioner of pmg.cu in its fused form: `p` holds the element-block part zloc of z = M^-1 r (k_pcg_fused); the Q1
-// vertex-mesh part (trilinear interpolation of the 8 corner values xv[vid]) and the aggregate value x2[agg] are added here.
+// vertex-mesh part (trilinear interpolation of the element's 8 corner values) and the aggregate value are added here; in this mode the
+// argument `xv` is the per-element table xc[nel][9] (k_pm_corner_values) and `x2` the table of hat-function values at the GL points.
 template <int N, int MODE>
 __global__ void __launch_bounds__(PK_TPB, 3)
 k_gradt3(const double* __restrict__ p, double* __restrict__ w, const double* __restrict__ RW2,
@@ -107,7 +108,6 @@ k_gradt3(const double* __restrict__ p, double* __restrict__ w, const double* __r
   using C2 = ColIn<2, N2, N, N>;
   __shared__ double sa[9][SA::size];
   __shared__ double sb[6][SB::size];
-  __shared__ double sxc[9], sh1[8];
   // products RW2[i][c]*p, one array per (i,c); consumed by the r stage before the s stage overwrites sb
   double* sq = &sb[0][0];
   static_assert(9 * S2::size <= 6 * SB::size, "sq alias");
@@ -117,26 +117,24 @@ k_gradt3(const double* __restrict__ p, double* __restrict__ w, const double* __r
   const long long e1 = (long long)blockIdx.x * NP1;
   static_assert(NP2 <= TPB, "one mesh-2 point per thread");
   if (MODE == 2) {
-    // two dependent L2 hits (vid -> xv) that hide behind the DRAM latency of the metric loads below
-    if (tid >= TPB - 8) sxc[tid - (TPB - 8)] = xv[vid[(long long)blockIdx.x * 8 + (tid - (TPB - 8))]];
-    else if (tid == TPB - 9) sxc[8] = x2[agg[blockIdx.x]];
-    else if (tid >= TPB - 32 && tid < TPB - 32 + N2) sh1[tid - (TPB - 32)] = cm.hat1[tid - (TPB - 32)];
-    double zl = 0.0, pd = 0.0, m9[9];
-    if (tid < NP2) {
-      zl = p[e2 + tid];
-      pd = pdir[e2 + tid];
-#pragma unroll
-      for (int g = 0; g < 9; ++g) m9[g] = RW2[(long long)g * n2 + e2 + tid];   // coalesced
-    }
-    __syncthreads();
+    // xc = the element's 8 corner values of the vertex level + its aggregate value (k_pm_corner_values): 9 doubles per element read by
+    // every thread as warp-uniform (broadcast) loads, no shared-memory staging and no extra barrier.  (First version: xv[vid[..]]
+    // gathered here through shared memory: two dependent, L2-evicted loads + a barrier on the critical path, 0.150 -> 0.183 ms.)
     if (tid < NP2) {
       const int q = tid;
+      const double* xc = xv + (long long)blockIdx.x * 9;
       const int i0 = q % N2, i1 = (q / N2) % N2, i2 = q / (N2 * N2);
-      const double a0 = sh1[i0], a1 = sh1[i1], a2 = sh1[i2];
-      const double c0 = fma(sxc[1] - sxc[0], a0, sxc[0]), c1 = fma(sxc[3] - sxc[2], a0, sxc[2]);
-      const double d0 = fma(sxc[5] - sxc[4], a0, sxc[4]), d1 = fma(sxc[7] - sxc[6], a0, sxc[6]);
+      const double a0 = __ldg(&x2[i0]), a1 = __ldg(&x2[i1]), a2 = __ldg(&x2[i2]);      // x2 = hat-function table (device copy of cm.hat1)
+      const double zl = p[e2 + q], pd = pdir[e2 + q];
+      double m9[9];
+#pragma unroll
+      for (int g = 0; g < 9; ++g) m9[g] = RW2[(long long)g * n2 + e2 + q];   // coalesced
+      const double x0 = __ldg(&xc[0]), x1 = __ldg(&xc[1]), x2v = __ldg(&xc[2]), x3 = __ldg(&xc[3]);
+      const double x4 = __ldg(&xc[4]), x5 = __ldg(&xc[5]), x6 = __ldg(&xc[6]), x7 = __ldg(&xc[7]), x8 = __ldg(&xc[8]);
+      const double c0 = fma(x1 - x0, a0, x0), c1 = fma(x3 - x2v, a0, x2v);
+      const double d0 = fma(x5 - x4, a0, x4), d1 = fma(x7 - x6, a0, x6);
       const double q0 = fma(c1 - c0, a1, c0), q1 = fma(d1 - d0, a1, d0);
-      const double z = (zl + fma(q1 - q0, a2, q0)) + sxc[8];
+      const double z = (zl + fma(q1 - q0, a2, q0)) + x8;
       const double v = fma(cgs->beta, pd, z);
       pdir[e2 + q] = v;
       const int o = S2::lin(q);
@@ -642,6 +640,147 @@ k_div3p(const double* __restrict__ u, const double* __restrict__ mbinv, double* 
   }
 }
 
+// ------------------------------------------------------------------------------------------------ k_div3q: single staging buffer, early refill
+// r1d ncu on k_div3p: 59 % of the HBM roofline, 15 % of the stall samples in the mbarrier wait -- two stages at 2 CTAs/SM (111 KB per
+// CTA) do not keep enough bytes in flight.  Here the element's inputs live in ONE staging buffer whose two halves are refilled as
+// soon as they have been consumed (the scheme of k_axhelm3p):
+//   half A (w x3, mask*binv)   consumed by the t stage      -> element e+1 requested right after the t-stage barrier
+//   half B (9 metric arrays)   consumed by the final stage  -> element e+1 requested right after the final stage
+// pdir is read straight from global memory into a register at the start of the element.  74.5 KB per CTA => THREE CTAs per SM.
+template <int N>
+struct DivQ {
+  static constexpr int N2 = N - 2, NP1 = N * N * N, NP2 = N2 * N2 * N2;
+  using SA = Shp<N2, N, N>;
+  using SB = Shp<N2, N2, N>;
+  static constexpr int halfA = 4 * NP1, halfB = 9 * NP2;
+  static constexpr size_t smem = sizeof(double) * (halfA + halfB + 6 * SA::size + 9 * SB::size) + 2 * sizeof(uint64_t);
+};
+struct DivQArgs {
+  const double* u; const double* mbinv; const double* RW2; const double* pdir; double* qout;
+  long long n, n2;
+};
+template <int N>
+__device__ __forceinline__ void div3q_issue_a(const DivQArgs* A, double* stg, uint64_t* bar, int e) {
+  constexpr int NP1 = N * N * N;
+  const long long e1 = (long long)e * NP1;
+  mbar_expect_tx(bar, 4 * NP1 * (uint32_t)sizeof(double));
+#pragma unroll
+  for (int c = 0; c < 3; ++c) tma_bulk_g2s(stg + c * NP1, A->u + (long long)c * A->n + e1, NP1 * sizeof(double), bar);
+  tma_bulk_g2s(stg + 3 * NP1, A->mbinv + e1, NP1 * sizeof(double), bar);
+}
+template <int N>
+__device__ __forceinline__ void div3q_issue_b(const DivQArgs* A, double* stg, uint64_t* bar, int e) {
+  constexpr int NP1 = N * N * N, NP2 = (N - 2) * (N - 2) * (N - 2);
+  const long long e2 = (long long)e * NP2;
+  mbar_expect_tx(bar, 9 * NP2 * (uint32_t)sizeof(double));
+#pragma unroll
+  for (int g = 0; g < 9; ++g) tma_bulk_g2s(stg + 4 * NP1 + g * NP2, A->RW2 + (long long)g * A->n2 + e2, NP2 * sizeof(double), bar);
+}
+
+template <int N>
+__device__ __noinline__ double div3q_element(const DivQArgs* __restrict__ A, double* __restrict__ stg, double* __restrict__ sa,
+                                             double* __restrict__ sbuf, uint64_t* bar, int e, int e_next, uint32_t parity, int tid) {
+  using P = DivQ<N>;
+  constexpr int N2 = P::N2, NP1 = P::NP1, NP2 = P::NP2;
+  using SA = typename P::SA;
+  using SB = typename P::SB;
+  using C2 = ColIn<2, N, N, N>;
+  using C1 = ColIn<1, N2, N, N>;
+  using C0 = ColIn<0, N2, N2, N>;
+  double* spart = sa;
+  const double* inmb = stg + 3 * NP1;
+  const double* inrw = stg + 4 * NP1;
+  const double pd = (tid < NP2) ? A->pdir[(long long)e * NP2 + tid] : 0.0;      // needed in the final stage only: latency hidden
+  mbar_wait(&bar[0], parity);
+  if (tid < 3 * C2::ncol) {
+    const int c = tid / C2::ncol, col = tid - c * C2::ncol;
+    double v[N];
+#pragma unroll
+    for (int l = 0; l < N; ++l) v[l] = stg[c * NP1 + l * N * N + col] * inmb[l * N * N + col];
+    apply_store<N2, N>(cm.J12, v, sa + (c * 2) * SA::size + C2::base(col), C2::stride);
+    apply_store<N2, N>(cm.D12, v, sa + (c * 2 + 1) * SA::size + C2::base(col), C2::stride);
+  }
+  __syncthreads();                                   // half A consumed
+  if (tid == 0 && e_next >= 0) div3q_issue_a<N>(A, stg, &bar[0], e_next);
+  if (tid < 6 * C1::ncol) {
+    const int grp = tid / C1::ncol, col = tid - grp * C1::ncol;
+    const int which = grp / 3, c = grp - which * 3;
+    const int bi = C1::base(col);
+    const int bo = (col / N) * N2 * SB::PI + (col % N);
+    double v[N];
+#pragma unroll
+    for (int l = 0; l < N; ++l) v[l] = sa[(c * 2 + which) * SA::size + bi + l * C1::stride];
+    apply_store<N2, N>(cm.J12, v, sbuf + (c * 3 + (which == 0 ? 0 : 2)) * SB::size + bo, SB::PI);
+    if (which == 0) apply_store<N2, N>(cm.D12, v, sbuf + (c * 3 + 1) * SB::size + bo, SB::PI);
+  }
+  __syncthreads();
+  if (tid < 9 * C0::ncol) {
+    const int grp = tid / C0::ncol, col = tid - grp * C0::ncol;
+    const int dir = grp / 3, c = grp - dir * 3;
+    const double* b0 = sbuf + (c * 3 + dir) * SB::size + C0::base(col);
+    double v[N];
+#pragma unroll
+    for (int l = 0; l < N; ++l) v[l] = b0[l];
+    double* po = spart + grp * NP2 + col * N2;
+    if (dir == 0) apply_store<N2, N>(cm.D12, v, po, 1);
+    else apply_store<N2, N>(cm.J12, v, po, 1);
+  }
+  mbar_wait(&bar[1], parity);
+  __syncthreads();
+  double rho = 0.0;
+  if (tid < NP2) {
+    const int q = tid;
+    double acc = 0.0;
+#pragma unroll
+    for (int g = 0; g < 9; ++g) acc = fma(inrw[g * NP2 + q], spart[g * NP2 + q], acc);
+    A->qout[(long long)e * NP2 + q] = acc;
+    rho = pd * acc;
+  }
+  __syncthreads();                                   // half B consumed (and spart free for the next element's t stage)
+  if (tid == 0 && e_next >= 0) div3q_issue_b<N>(A, stg, &bar[1], e_next);
+  return rho;
+}
+
+template <int N>
+__global__ void __launch_bounds__(PK_TPB, 3)
+k_div3q(DivQArgs args, CGState* __restrict__ cgs, double* __restrict__ part, unsigned* counter, double* __restrict__ red_out,
+        int finalize, int nel) {
+  using P = DivQ<N>;
+  using SA = typename P::SA;
+  using SB = typename P::SB;
+  extern __shared__ __align__(128) double dsm[];
+  double* stg = dsm;                                   // [halfA | halfB]
+  double* sa = dsm + P::halfA + P::halfB;              // [6][SA::size], reused for the 9 partial arrays
+  double* sbuf = sa + 6 * SA::size;                    // [9][SB::size]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sbuf + 9 * SB::size);
+  __shared__ double sred[32];
+  __shared__ DivQArgs sargs;
+  static_assert(9 * P::NP2 <= 6 * SA::size, "spart alias");
+  const int tid = threadIdx.x;
+  if (cgs->done) return;
+  if (tid == 0) {
+    sargs = args;
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (tid == 0 && (int)blockIdx.x < nel) {
+    div3q_issue_a<N>(&sargs, stg, &bar[0], blockIdx.x);
+    div3q_issue_b<N>(&sargs, stg, &bar[1], blockIdx.x);
+  }
+  double rho[1] = {0.0};
+  int it = 0;
+  for (int e = blockIdx.x; e < nel; e += gridDim.x, ++it) {
+    const int en = (e + (int)gridDim.x < nel) ? e + (int)gridDim.x : -1;
+    rho[0] += div3q_element<N>(&sargs, stg, sa, sbuf, bar, e, en, (uint32_t)(it & 1), tid);
+  }
+  if (grid_sum_finish<1>(rho, part, counter, red_out, sred) && finalize && tid == 0) {
+    cgs->rho = red_out[0];
+    cgs->alpha = cgs->rtz1 / red_out[0];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ axhelm
 // w_f = (h1 A + h2 B) u_f for up to 3 fields at once [UPSTREAM hmholtz.f axhelm = local_grad3 -> G -> local_grad3_t]:
 // every (field, direction) pair is one column task per thread in both tensor stages; the stiffness factors are read
@@ -1002,7 +1141,7 @@ int pk_pcg_dir_gradt(Ctx* c, int adj) {
   if (c->pc_kind == 1 && c->pcg_fused) {          // fused preconditioner: pz holds the element-block part, the coarse parts are added here
     const PMG& m = c->pmg[(adj && c->has_adj_masks) ? 1 : 0];
     DISPATCH_N(c, k_gradt3<N, 2><<<c->nel, PK_TPB, 0, c->stream>>>(c->pz, c->wk[2], c->RW2, nullptr, c->pk[2], c->cgs + 3, c->n, c->n2,
-                                                                m.xv, m.vid, m.x2, m.agg));
+                                                                m.xc, nullptr, m.hat, nullptr));
     nsb_count_launch();
     NSB_CUDA(cudaGetLastError());
     return 0;
@@ -1024,6 +1163,8 @@ static constexpr size_t div3_smem() {
 template <class K>
 static int set_smem(K kernel, size_t bytes) {
   NSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  // the persistent kernels size their staging buffers for 2-3 CTAs per SM: ask for the largest shared-memory carve-out
+  if (bytes > 64 * 1024) NSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
   return 0;
 }
 
@@ -1039,6 +1180,18 @@ int pk_pcg_div(Ctx* c, int adj, int fused) {
   const double* s1 = c->mask_same[adj] ? nullptr : c->mbinv[adj][1];
   const double* s2 = c->mask_same[adj] ? nullptr : c->mbinv[adj][2];
   const GSMap& m = c->gs;
+  static const bool divq = [] { const char* e = getenv("NSB_DIVQ"); return !(e && e[0] == '0'); }();
+  if (c->persistent_pcg && !fused && c->mask_same[adj] && divq) {      // single staging buffer with early refill, 3 CTAs per SM
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    DISPATCH_N(c, DivQArgs a{c->wk[2], s0, c->RW2, c->pk[2], c->pk[3], c->n, c->n2};
+               NSB_TRY(set_smem(k_div3q<N>, DivQ<N>::smem));
+               k_div3q<N><<<std::min(c->nel, 3 * sms), PK_TPB, DivQ<N>::smem, c->stream>>>(a, c->cgs + 3, c->red_part, c->red_count, c->red_out,
+                                                                                         c->nranks == 1, c->nel));
+    nsb_count_launch();
+    NSB_CUDA(cudaGetLastError());
+    return 0;
+  }
   if (c->persistent_pcg && !fused && c->mask_same[adj]) {
     DISPATCH_N(c, NSB_TRY(set_smem(k_div3p<N>, DivP<N>::smem));
                k_div3p<N><<<persistent_grid(c), PK_TPB, DivP<N>::smem, c->stream>>>(c->wk[2], s0, c->pk[3], c->RW2, c->pk[2], c->cgs + 3,

@@ -712,6 +712,17 @@ __global__ void __launch_bounds__(128) k_pm_gemv_fin(int nagg, const double* __r
   }
 }
 
+// xc[e][k] = xv[vid[e][k]] (k < 2^D), xc[e][2^D] = x2[agg[e]]: the coarse-level values of an element in one contiguous record, so that
+// the direction kernel reads them with one hop (the vid -> xv chain does not survive in L2 between iterations: 2 GB stream through it)
+__global__ void k_pm_corner_values(int nel, int nk, const double* __restrict__ xv, const int* __restrict__ vid, const double* __restrict__ x2,
+                                   const int* __restrict__ agg, double* __restrict__ xc, const CGState* skip) {
+  if (skip && skip->done) return;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nel * (nk + 1)) return;
+  const int e = t / (nk + 1), k = t - e * (nk + 1);
+  xc[t] = (k < nk) ? xv[vid[e * nk + k]] : x2[agg[e]];
+}
+
 // ---------------------------------------------------------------------------------------------- host helpers
 // symmetric eigen-decomposition by cyclic Jacobi rotations (n <= 8): A = V diag(w) V^T, A destroyed
 static void jacobi_eig(int n, double* A, double* V, double* w) {
@@ -976,7 +987,7 @@ static int pm_download(Ctx* c, std::vector<double>& h, const double* d, long lon
 
 void pm_free(PMG& m) {
   cudaFree(m.S); cudaFree(m.lam); cudaFree(m.vid); cudaFree(m.voff); cudaFree(m.vent); cudaFree(m.d1inv); cudaFree(m.agg);
-  cudaFree(m.aoff); cudaFree(m.aent); cudaFree(m.A2inv); cudaFree(m.rc); cudaFree(m.rc0); cudaFree(m.xv); cudaFree(m.ra); cudaFree(m.x2);
+  cudaFree(m.aoff); cudaFree(m.aent); cudaFree(m.A2inv); cudaFree(m.rc); cudaFree(m.rc0); cudaFree(m.xc); cudaFree(m.hat); cudaFree(m.xv); cudaFree(m.ra); cudaFree(m.x2);
   cudaFree(m.vc_off); cudaFree(m.vc_col); cudaFree(m.vc_val); cudaFree(m.vc_odinv); cudaFree(m.vc_vagg); cudaFree(m.vc_aoff);
   cudaFree(m.vc_aent); cudaFree(m.vc_A2inv); cudaFree(m.vc_rv); cudaFree(m.vc_x); cudaFree(m.vc_r1);
   m = PMG();
@@ -1144,7 +1155,11 @@ int pm_pcg_tail(Ctx* c, int set, int init, int prof_slot) {
   if (multi) NSB_TRY(vk_allreduce_sum(c, m.ra, m.nagg + 3));
   k_pm_gemv_fin<<<(m.nagg * 32 + 127) / 128, 128, 0, c->stream>>>(m.nagg, m.A2inv, m.ra, m.x2, sc, sp, init, c->red_part, c->red_count,
                                                                 c->red_out);
-  nsb_count_launch();
+  {
+    const int nk = (c->ldim == 3) ? 8 : 4, tot = c->nel * (nk + 1);
+    k_pm_corner_values<<<(tot + 255) / 256, 256, 0, c->stream>>>(c->nel, nk, m.xv, m.vid, m.x2, m.agg, m.xc, init ? nullptr : sp);
+  }
+  nsb_count_launch(2);
   NSB_CUDA(cudaGetLastError());
   if (prof_slot > 0) cudaEventRecord(c->prof_ev[prof_slot + 1], c->stream);
   return 0;
@@ -1296,6 +1311,8 @@ int pm_setup(Ctx* c, int set, int nagg_req) {
   NSB_TRY(pm_upload(&m.xv, std::vector<double>(m.nv, 0.0)));
   NSB_TRY(pm_upload(&m.ra, std::vector<double>(m.nagg + 3, 0.0)));      // + |r|^2, zloc.r, sum xv rv (pm_pcg_tail)
   NSB_TRY(pm_upload(&m.rc0, std::vector<double>((size_t)nel * NK, 0.0)));
+  NSB_TRY(pm_upload(&m.xc, std::vector<double>((size_t)nel * (NK + 1), 0.0)));
+  NSB_TRY(pm_upload(&m.hat, std::vector<double>(c->cm.hat1, c->cm.hat1 + 12)));
   NSB_TRY(pm_upload(&m.x2, std::vector<double>(m.nagg, 0.0)));
   // ---- distance-2 colouring of the GLOBAL vertex graph (adjacent = share an element): every rank gathers the corner ids
   //      of all elements and runs the same greedy colouring, so that the probing below is consistent across ranks

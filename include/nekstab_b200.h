@@ -78,7 +78,9 @@ int nsb_set_projection(int mxprev);
 /* Preconditioner of the pressure CG on E = D (mask B^-1 QQ^T) D^T.  kind 0: Jacobi (the default; the north-star's solver).
  * kind 1: three-level additive operator of the class the reference runs (`[PRESSURE] preconditioner = semg_xxt`,
  * 1cyl.par:28; [UPSTREAM] hsmg.f): element blocks by fast diagonalisation + Jacobi on the Q1 space of the element-vertex
- * mesh + an exactly solved problem on `nagg` element aggregates (0 = automatic: nelv/32, at most 512).  Changes the
+ * mesh + an exactly solved problem on `nagg` element aggregates (total over all ranks; 0 = automatic:
+ * nelv/32 per rank, at most 512 per rank and 4096 in total -- the aggregate size, hence the iteration count, then stays the same under
+ * weak scaling).  Changes the
  * iteration count (measured 2 787 -> 206 on the cylinder mesh), not the converged pressure.  Rebuilt automatically when
  * nsb_set_adjoint_masks changes the adjoint operator.  Environment NSB_PRECOND=1 selects kind 1 at nsb_init.
  * kind 2 (EXPERIMENTAL, single GPU, not yet validated on hardware): as kind 1 with the vertex-mesh level replaced by a V-cycle on

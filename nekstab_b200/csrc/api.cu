@@ -339,7 +339,7 @@ extern "C" int nsb_set_projection(int mxprev) {
 extern "C" int nsb_set_pressure_preconditioner(int kind, int nagg) {
   REQUIRE_CTX();
   if (kind < 0 || kind > 2) { nsb_set_error("nsb_set_pressure_preconditioner: kind must be 0 (Jacobi), 1 (pmg) or 2 (experimental)"); return 1; }
-  if (nagg < 0 || nagg > 512) { nsb_set_error("nsb_set_pressure_preconditioner: nagg must be in [0, 512]"); return 1; }
+  if (nagg < 0 || nagg > 4096) { nsb_set_error("nsb_set_pressure_preconditioner: nagg must be in [0, 4096]"); return 1; }
   drop_graphs(c);
   c->pc_kind = 0;
   if (kind == 0) return 0;

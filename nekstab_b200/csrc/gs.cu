@@ -43,7 +43,7 @@ __global__ void k_gs_sum(int nseg, const int* __restrict__ seg_off, const int* _
                          const double* __restrict__ recvbuf, double* __restrict__ u, long long stride,
                          const CGState* skip) {
   if (skip && skip->done) return;
-  int seg = blockIdx.x * blockDim.x + threadIdx.x;
+  int seg = blockIdx.x * blockDim.x + threadIdx.x;      // nseg may be a leading sub-range (the interior segments)
   if (seg >= nseg) return;
   int a = seg_off[seg], b = seg_off[seg + 1];
   double acc[NF], loc[NF];
@@ -114,6 +114,7 @@ struct HostPlan {
   std::vector<int> send_seg, send_base, send_cnt;
   std::vector<int> rseg_off, rseg_pos, rseg_cnt, nbefore;
   int nshared = 0;
+  int nseg_int = 0;                          // segments [0, nseg_int) have no copy on another rank
 };
 
 static bool is_surface(int p, int N, int D) {
@@ -169,7 +170,14 @@ static void plan_build(HostPlan& P, int rank, int nranks, const long long* count
     std::vector<int> segk;
     for (int k = 0; k < nu; ++k)
       if (P.ustart[k + 1] - P.ustart[k] > 1 || is_shared[k]) segk.push_back(k);
-    std::sort(segk.begin(), segk.end(), [&](int a, int b) { return P.order[P.ustart[a]] < P.order[P.ustart[b]]; });
+    // segments shared with another rank go LAST: the peer-memory path sums the interior range while the halo is in flight
+    // and only the short shared range waits for the neighbours' flags (r2: the flag wait cost 27 us per dssum at 2 GPUs)
+    std::sort(segk.begin(), segk.end(), [&](int a, int b) {
+      if (is_shared[a] != is_shared[b]) return is_shared[a] < is_shared[b];
+      return P.order[P.ustart[a]] < P.order[P.ustart[b]];
+    });
+    P.nseg_int = 0;
+    for (int k : segk) P.nseg_int += is_shared[k] ? 0 : 1;
     for (int k : segk) {
       seg_of_u[k] = (int)P.seg_off.size() - 1;
       for (int j = P.ustart[k]; j < P.ustart[k + 1]; ++j) P.seg_idx.push_back(P.order[j]);
@@ -222,7 +230,7 @@ extern "C" int nsb_gs_host_plan(int rank, int nranks, const long long* counts, c
   plan_build(g_host_plan, rank, nranks, counts, ids);
   const HostPlan& P = g_host_plan;
   const int v[8] = {(int)P.seg_off.size() - 1, (int)P.seg_idx.size(), (int)P.nbr_rank.size(), P.nshared,
-                    (int)P.rseg_pos.size(), 0, 0, 0};
+                    (int)P.rseg_pos.size(), P.nseg_int, 0, 0};
   for (int i = 0; i < 8; ++i) sizes_out[i] = v[i];
   return 0;
 }
@@ -273,6 +281,7 @@ int gs_build(Ctx* c, GSMap& m, P2P& p2p, long long n, int N1, int np_e, const lo
   }
   plan_build(P, c->rank, c->nranks, c->nranks > 1 ? cnts.data() : nullptr, all.data());
   m.nseg = (int)P.seg_off.size() - 1;
+  m.nseg_int = P.nseg_int;
   m.nbr_rank = P.nbr_rank; m.nbr_off = P.nbr_off;
   m.nnbr = (int)m.nbr_rank.size();
   m.nshared = P.nshared;

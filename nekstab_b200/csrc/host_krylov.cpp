@@ -27,6 +27,11 @@ typedef void (*dtrsen_t)(const char*, const char*, const llogical*, const lint*,
 typedef void (*dgels_t)(const char*, const lint*, const lint*, const lint*, double*, const lint*, double*, const lint*,
                         double*, const lint*, lint*, size_t);
 
+typedef void (*dpotrf_t)(const char*, const lint*, double*, const lint*, lint*, size_t);
+typedef void (*dpotri_t)(const char*, const lint*, double*, const lint*, lint*, size_t);
+static dpotrf_t p_dpotrf = nullptr;
+static dpotri_t p_dpotri = nullptr;
+
 static void* g_lapack = nullptr;
 static dgeev_t p_dgeev = nullptr;
 static dgees_t p_dgees = nullptr;
@@ -47,6 +52,8 @@ extern "C" int nsb_lapack_load(const char* path) {
   dgels_t l = (dgels_t)sym2(h, "dgels_", "scipy_dgels_");
   if (!a || !b || !t || !l) { nsb_set_error("nsb_lapack_load: %s lacks dgeev_/dgees_/dtrsen_/dgels_", path); dlclose(h); return 1; }
   g_lapack = h; p_dgeev = a; p_dgees = b; p_dtrsen = t; p_dgels = l;
+  p_dpotrf = (dpotrf_t)sym2(h, "dpotrf_", "scipy_dpotrf_");      // optional: large aggregate operators of the pressure preconditioner
+  p_dpotri = (dpotri_t)sym2(h, "dpotri_", "scipy_dpotri_");
   return 0;
 }
 
@@ -140,6 +147,20 @@ extern "C" int nsb_lapack_lstsq(const double* A, const double* b, double* x, int
   p_dgels("N", &mm, &nn, &nrhs, At.data(), &mm, bt.data(), &mm, work.data(), &lwork, &info, 1);
   if (info != 0) { nsb_set_error("dgels info=%d (Least-Squares solver UNsuccessful)", info); return 1; }
   for (int i = 0; i < n; ++i) x[i] = bt[i];
+  return 0;
+}
+
+// dense SPD inverse in place (column-major = row-major for a symmetric matrix): dpotrf + dpotri, lower triangle mirrored
+int nsb_lapack_spd_inverse(int n, double* A) {
+  NSB_TRY(need_lapack());
+  if (!p_dpotrf || !p_dpotri) { nsb_set_error("LAPACK library lacks dpotrf_/dpotri_"); return 1; }
+  lint nn = n, info = 0;
+  p_dpotrf("L", &nn, A, &nn, &info, 1);
+  if (info != 0) { nsb_set_error("dpotrf info=%d (matrix not positive definite)", info); return 2; }
+  p_dpotri("L", &nn, A, &nn, &info, 1);
+  if (info != 0) { nsb_set_error("dpotri info=%d", info); return 2; }
+  for (int j = 0; j < n; ++j)                  // column-major lower triangle: A(i,j), i >= j, at A[j*n+i]
+    for (int i = j + 1; i < n; ++i) A[(size_t)i * n + j] = A[(size_t)j * n + i];
   return 0;
 }
 

@@ -59,6 +59,7 @@ struct CGState {
 // Gather-scatter map (dssum): CSR segments of local copies of each shared node + halo lists.
 struct GSMap {
   int nseg = 0;              // segments written back (local multiplicity > 1 or shared with another rank)
+  int nseg_int = 0;          // the first nseg_int segments have no copy on another rank (summed while the halo is in flight)
   int* seg_off = nullptr;    // [nseg+1] into seg_idx
   int* seg_idx = nullptr;    // local dof indices
   // halo (multi-rank)
@@ -345,7 +346,8 @@ int vk_wavemaker(Ctx* c, const double* dre, const double* dim, const double* are
 int pm_setup(Ctx* c, int set, int nagg_req);
 int pm_setup_vcycle(Ctx* c, int set);
 int pm_apply(Ctx* c, int set, const double* r, double* z, int mode, int prof_slot = 0);
-int pm_pcg_tail(Ctx* c, int set, int init, int prof_slot);   // fused CG update + restriction + element blocks + coarse levels + scalars (3-D)
+int pm_pcg_tail(Ctx* c, int set, int init, int prof_slot);
+int pm_pcg_xfix(Ctx* c);                                     // x += alpha p of the last iteration (fused path)   // fused CG update + restriction + element blocks + coarse levels + scalars (3-D)
 void pm_free(PMG& m);
 int vk_cg_finalize_multi(Ctx* c, CGState* s, int ncomp, int kind);
 
@@ -356,4 +358,5 @@ int st_pressure(Ctx* c, int adj, int* iters);                          // solves
 int st_linearized_map(Ctx* c, int adjoint, const double* vin, double* vout);   // vin/vout device krylov vectors
 
 // ---- host krylov (host_krylov.cpp)
+int nsb_lapack_spd_inverse(int n, double* A);   // in place, dpotrf + dpotri; non-zero when not positive definite / LAPACK missing
 void nsb_count_launch(int n = 1);

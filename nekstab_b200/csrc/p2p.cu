@@ -16,7 +16,7 @@
 
 #include "nsb_internal.h"
 
-static constexpr int RSLOT = 640;                 // doubles per rank slot of the all-reduce buffer (>= 512 aggregate sums + 3 CG scalars)
+static constexpr int RSLOT = 4224;                // doubles per rank slot of the all-reduce buffer (>= 4096 aggregate sums + 3 CG scalars)
 static constexpr long long SPIN_TIMEOUT_NS = 30000000000LL;   // 30 s: host-side skew between ranks (setup, numpy work) is seconds at most
 
 __device__ __forceinline__ unsigned long long ld_flag(const unsigned long long* p) {
@@ -208,12 +208,35 @@ __global__ void k_gs_pack_p2p(int nshared, const int* __restrict__ send_seg, con
   }
 }
 
+// segments without remote copies: plain local segmented sum (same arithmetic as k_gs_sum<NF,false> of gs.cu)
+template <int NF>
+__global__ void k_gs_sum_local(int nseg, const int* __restrict__ seg_off, const int* __restrict__ seg_idx, double* __restrict__ u,
+                               long long stride, const CGState* skip) {
+  if (skip && skip->done) return;
+  const int seg = blockIdx.x * blockDim.x + threadIdx.x;
+  if (seg >= nseg) return;
+  const int a = seg_off[seg], b = seg_off[seg + 1];
+  double acc[NF];
+#pragma unroll
+  for (int f = 0; f < NF; ++f) acc[f] = 0.0;
+  for (int j = a; j < b; ++j) {
+    const int idx = seg_idx[j];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) acc[f] += u[(long long)f * stride + idx];
+  }
+  for (int j = a; j < b; ++j) {
+    const int idx = seg_idx[j];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) u[(long long)f * stride + idx] = acc[f];
+  }
+}
+
 template <int NF>
 __global__ void k_gs_sum_p2p(int nseg, const int* __restrict__ seg_off, const int* __restrict__ seg_idx,
                              const int* __restrict__ rseg_off, const int* __restrict__ rseg_pos, const int* __restrict__ rseg_cnt,
                              const int* __restrict__ rseg_nbefore, const double* __restrict__ recvbuf, double* __restrict__ u,
                              long long stride, const unsigned long long* __restrict__ flags, const int* __restrict__ nbr_rank,
-                             int nnbr, unsigned long long epoch, int* err, const CGState* skip) {
+                             int nnbr, unsigned long long epoch, int* err, const CGState* skip, int seg0) {
   if (skip && skip->done) return;
   __shared__ int ok;
   if (threadIdx.x == 0) ok = 1;
@@ -222,7 +245,7 @@ __global__ void k_gs_sum_p2p(int nseg, const int* __restrict__ seg_off, const in
     if (!p2p_wait(flags + nbr_rank[threadIdx.x], epoch, err)) ok = 0;
   __syncthreads();
   if (!ok) return;
-  const int seg = blockIdx.x * blockDim.x + threadIdx.x;
+  const int seg = seg0 + blockIdx.x * blockDim.x + threadIdx.x;      // only the segments shared with other ranks: [seg0, nseg)
   if (seg >= nseg) return;
   const int a = seg_off[seg], b = seg_off[seg + 1];
   double acc[NF], loc[NF];
@@ -264,12 +287,19 @@ static int dssum_p2p_nf(Ctx* c, P2P& p, GSMap& m, double* u, long long stride, c
                                                                    p.d_peer_flag + par * m.nnbr, m.nnbr, epoch, c->red_count + 2, skip);
     nsb_count_launch();
   }
-  if (m.nseg > 0) {
+  // interior segments (no copy on another rank) are summed while the partial sums travel over NVLink ...
+  if (m.nseg_int > 0) {
+    k_gs_sum_local<NF><<<(m.nseg_int + T - 1) / T, T, 0, c->stream>>>(m.nseg_int, m.seg_off, m.seg_idx, u, stride, skip);
+    nsb_count_launch();
+  }
+  // ... and only the shared segments wait for the neighbours' flags
+  if (m.nseg > m.nseg_int) {
     const double* recv = p.arena + off_halo(R) + par * p.halo_stride;
     const unsigned long long* flags = (const unsigned long long*)(p.arena + off_haloflag(par, 0, R));
-    k_gs_sum_p2p<NF><<<(m.nseg + T - 1) / T, T, 0, c->stream>>>(m.nseg, m.seg_off, m.seg_idx, m.rseg_off, m.rseg_pos, d_rseg_cnt,
-                                                               m.rseg_nbefore, recv, u, stride, flags, p.d_nbr_rank, m.nnbr, epoch,
-                                                               p.d_err, skip);
+    const int ns = m.nseg - m.nseg_int;
+    k_gs_sum_p2p<NF><<<(ns + T - 1) / T, T, 0, c->stream>>>(m.nseg, m.seg_off, m.seg_idx, m.rseg_off, m.rseg_pos, d_rseg_cnt,
+                                                           m.rseg_nbefore, recv, u, stride, flags, p.d_nbr_rank, m.nnbr, epoch,
+                                                           p.d_err, skip, m.nseg_int);
     nsb_count_launch();
   }
   NSB_CUDA(cudaGetLastError());

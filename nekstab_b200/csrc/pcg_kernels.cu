@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(PK_TPB, 3)
 k_gradt3(const double* __restrict__ p, double* __restrict__ w, const double* __restrict__ RW2,
          const double* __restrict__ dinvE, double* __restrict__ pdir, const CGState* __restrict__ cgs, long long n,
          long long n2, const double* __restrict__ xv, const int* __restrict__ vid, const double* __restrict__ x2,
-         const int* __restrict__ agg) {
+         const int* __restrict__ agg, double* __restrict__ xsol) {
   constexpr int N2 = N - 2, TPB = PK_TPB;
   constexpr int NP1 = N * N * N, NP2 = N2 * N2 * N2;
   using S2 = Shp<N2, N2, N2>;
@@ -126,6 +126,9 @@ k_gradt3(const double* __restrict__ p, double* __restrict__ w, const double* __r
       const int i0 = q % N2, i1 = (q / N2) % N2, i2 = q / (N2 * N2);
       const double a0 = __ldg(&x2[i0]), a1 = __ldg(&x2[i1]), a2 = __ldg(&x2[i2]);      // x2 = hat-function table (device copy of cm.hat1)
       const double zl = p[e2 + q], pd = pdir[e2 + q];
+      // the solution update of the PREVIOUS iteration rides along here (pd = p_k is in a register anyway): x_{k+1} = x_k + alpha_k p_k;
+      // the update of the last iteration is applied by k_pcg_xfix after the loop (this kernel is skipped once converged)
+      xsol[e2 + q] = fma(cgs->alpha, pd, xsol[e2 + q]);
       double m9[9];
 #pragma unroll
       for (int g = 0; g < 9; ++g) m9[g] = RW2[(long long)g * n2 + e2 + q];   // coalesced
@@ -1112,7 +1115,7 @@ int pk_upload_constants(const ConstMats& h) {
   } while (0)
 
 int pk_gradt(Ctx* c, const double* p, double* w) {
-  DISPATCH_N(c, k_gradt3<N, 0><<<c->nel, PK_TPB, 0, c->stream>>>(p, w, c->RW2, nullptr, nullptr, nullptr, c->n, c->n2, nullptr, nullptr, nullptr, nullptr));
+  DISPATCH_N(c, k_gradt3<N, 0><<<c->nel, PK_TPB, 0, c->stream>>>(p, w, c->RW2, nullptr, nullptr, nullptr, c->n, c->n2, nullptr, nullptr, nullptr, nullptr, nullptr));
   nsb_count_launch();
   NSB_CUDA(cudaGetLastError());
   return 0;
@@ -1141,13 +1144,13 @@ int pk_pcg_dir_gradt(Ctx* c, int adj) {
   if (c->pc_kind == 1 && c->pcg_fused) {          // fused preconditioner: pz holds the element-block part, the coarse parts are added here
     const PMG& m = c->pmg[(adj && c->has_adj_masks) ? 1 : 0];
     DISPATCH_N(c, k_gradt3<N, 2><<<c->nel, PK_TPB, 0, c->stream>>>(c->pz, c->wk[2], c->RW2, nullptr, c->pk[2], c->cgs + 3, c->n, c->n2,
-                                                                m.xc, nullptr, m.hat, nullptr));
+                                                                m.xc, nullptr, m.hat, nullptr, c->pk[1]));
     nsb_count_launch();
     NSB_CUDA(cudaGetLastError());
     return 0;
   }
   DISPATCH_N(c, k_gradt3<N, 1><<<c->nel, PK_TPB, 0, c->stream>>>(zsrc, c->wk[2], c->RW2, zscale, c->pk[2], c->cgs + 3,
-                                                              c->n, c->n2, nullptr, nullptr, nullptr, nullptr));
+                                                              c->n, c->n2, nullptr, nullptr, nullptr, nullptr, nullptr));
   nsb_count_launch();
   NSB_CUDA(cudaGetLastError());
   return 0;

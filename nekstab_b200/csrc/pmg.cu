@@ -19,6 +19,7 @@
 // CPU restatement: oracle/pmg.py (tests/test_gpu_pmg.py compares M^-1 r, solutions and iteration counts).
 #include <algorithm>
 #include <cmath>
+#include <cstdint>
 #include <numeric>
 
 #include "elem_common.cuh"
@@ -452,7 +453,8 @@ __global__ void __launch_bounds__(Pm2<D, L>::NT) k_pm_apply2(const double* __res
 
 // ---------------------------------------------------------------------------------------------- fused pressure-CG tail (3-D)
 // One kernel for everything of a CG iteration that touches the mesh-2 vectors between the E application and the next direction:
-//   x += alpha p ; r -= alpha Ep ; |r|^2 (Nek norm: r^2/bm2) ; rc = P^T r (Q1 restriction) ; zloc = FDM_e(r) ; zloc . r
+//   r -= alpha Ep ; |r|^2 (Nek norm: r^2/bm2) ; rc = P^T r (Q1 restriction) ; zloc = FDM_e(r) ; zloc . r
+// (the solution update x += alpha p rides along in the next direction kernel, which has p in registers anyway)
 // (r1d: k_pcg_update 0.058 + k_pm_restrict 0.019 + k_pm_apply2 0.074 ms, r streamed three times).  The coarse-level parts of
 // z = M^-1 r are NOT added here: they need the vertex / aggregate sums of ALL elements, so the direction kernel (k_gradt3 MODE 2,
 // pcg_kernels.cu) adds the trilinear interpolation of the vertex values and the aggregate value while it forms p = z + beta p,
@@ -489,10 +491,9 @@ __global__ void __launch_bounds__(Pm2<D, L>::NT) k_pcg_fused(double* __restrict_
       if (init) {
         x[gi] = 0.0;
         pdir[gi] = 0.0;
-      } else {
+      } else {                                    // x += alpha p is done by the next direction kernel (k_gradt3 MODE 2) / k_pcg_xfix
         v = fma(-alpha, ep[gi], v);
         r[gi] = v;
-        x[gi] = fma(alpha, pdir[gi], x[gi]);
       }
       rr[q] = v;
       sums[0] = fma(v * v, bm2inv[gi], sums[0]);
@@ -631,6 +632,255 @@ __global__ void __launch_bounds__(Pm2<D, L>::NT) k_pcg_fused(double* __restrict_
   grid_sum_finish<2>(sums, part, counter, out, sred);
 }
 
+// ---- persistent, TMA-pipelined form of k_pcg_fused (3-D).  r2 measurement of the one-group-per-CTA kernel above: 0.120 ms for 296 MB
+// (38 % of the HBM roofline): every CTA first waits for its loads, then runs ten barrier-separated phases with nothing in flight.
+// Here one CTA per SM slot walks over groups of EPB elements; the three streamed inputs of a group (r, Ep, 1/bm2) and its FDM factors
+// sit in ONE staging buffer that is refilled by bulk TMA copies as soon as it has been consumed (the scheme of k_axhelm3p / k_div3q):
+// the streamed half right after the load phase, the factor half right after the last tensor pass.
+__device__ __forceinline__ uint32_t pm_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void pm_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pm_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void pm_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pm_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void pm_tma_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(pm_smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(pm_smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void pm_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "PM_WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra PM_WAIT_DONE;\n"
+      "bra PM_WAIT_LOOP;\n"
+      "PM_WAIT_DONE:\n"
+      "}\n" ::"r"(pm_smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+template <int L>
+struct PfP {
+  static constexpr int D = 3, EPB = 8, NP = L * L * L, LL = L * L, NCOL = LL, NT = EPB * NCOL;
+  static constexpr int PI = (L % 2 == 0) ? L + 1 : L, ESZ = LL * PI, NK = 8;
+  static constexpr int PER = (EPB * NP + NT - 1) / NT;
+  static constexpr int stream = 3 * EPB * NP;                   // r | Ep | 1/bm2, EPB elements each
+  static constexpr int fac = EPB * (D * LL + D * L);            // S | lam
+  static constexpr int work = 2 * EPB * ESZ + EPB * NCOL * 2 + EPB * L * 4 + EPB + 16;
+  static constexpr size_t smem = sizeof(double) * (stream + fac + work) + 2 * sizeof(uint64_t);
+};
+struct PfArgs {
+  double* r; const double* ep; const double* bm2inv; const double* Sg; const double* lamg;
+  double *x, *pdir, *zloc, *rc, *rc0;
+  int nel, init;
+  double alpha;
+};
+template <int L>
+__device__ __forceinline__ void pfp_issue_stream(const PfArgs* A, double* stg, uint64_t* bar, int g) {
+  using P = PfP<L>;
+  const int e0 = g * P::EPB, ne = min(P::EPB, A->nel - e0);
+  const uint32_t bytes = (uint32_t)(ne * P::NP * sizeof(double));
+  const long long off = (long long)e0 * P::NP;
+  pm_mbar_expect_tx(bar, 3 * bytes);
+  pm_tma_g2s(stg, A->r + off, bytes, bar);
+  pm_tma_g2s(stg + P::EPB * P::NP, A->ep + off, bytes, bar);
+  pm_tma_g2s(stg + 2 * P::EPB * P::NP, A->bm2inv + off, bytes, bar);
+}
+template <int L>
+__device__ __forceinline__ void pfp_issue_fac(const PfArgs* A, double* fac, uint64_t* bar, int g) {
+  using P = PfP<L>;
+  const int e0 = g * P::EPB, ne = min(P::EPB, A->nel - e0);
+  const uint32_t bs = (uint32_t)(ne * P::D * P::LL * sizeof(double)), bl = (uint32_t)(ne * P::D * L * sizeof(double));
+  pm_mbar_expect_tx(bar, bs + bl);
+  pm_tma_g2s(fac, A->Sg + (long long)e0 * P::D * P::LL, bs, bar);
+  pm_tma_g2s(fac + P::EPB * P::D * P::LL, A->lamg + (long long)e0 * P::D * L, bl, bar);
+}
+
+template <int L>
+__global__ void __launch_bounds__(PfP<L>::NT, 2) k_pcg_fused_p(PfArgs args, const CGState* __restrict__ cgs, double* part,
+                                                              unsigned* counter, double* out) {
+  using P = PfP<L>;
+  constexpr int D = 3, NP = P::NP, NK = P::NK, LL = P::LL, PI = P::PI, ESZ = P::ESZ, EPB = P::EPB, NT = P::NT, NCOL = P::NCOL, PER = P::PER;
+  if (!args.init && cgs->done) return;
+  extern __shared__ __align__(128) double dsm[];
+  double* stg = dsm;                               // [3][EPB*NP]
+  double* sS = dsm + P::stream;                    // [EPB][D][LL]
+  double* sL = sS + EPB * D * LL;                  // [EPB][D][L]
+  double* sA = sL + EPB * D * L;
+  double* sB = sA + EPB * ESZ;
+  double* sP = sB + EPB * ESZ;                     // [EPB][NCOL][2]
+  double* sQ = sP + EPB * NCOL * 2;                // [EPB][L][4]
+  double* sMx = sQ + EPB * L * 4;                  // [EPB]
+  double* sl0 = sMx + EPB;                         // [8]
+  double* sl1 = sl0 + 8;                           // [8]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sl1 + 8);
+  __shared__ double sred[2 * 32];
+  __shared__ PfArgs sargs;
+  const int tid = threadIdx.x;
+  const int ngroups = (args.nel + EPB - 1) / EPB;
+  if (tid == 0) {
+    sargs = args;
+    if (!args.init) sargs.alpha = cgs->alpha;
+    pm_mbar_init(&bar[0], 1);
+    pm_mbar_init(&bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid < L) { sl0[tid] = pm_l[0][tid]; sl1[tid] = pm_l[1][tid]; }
+  __syncthreads();
+  const PfArgs* A = &sargs;
+  if (tid == 0 && (int)blockIdx.x < ngroups) {
+    pfp_issue_stream<L>(A, stg, &bar[0], blockIdx.x);
+    pfp_issue_fac<L>(A, sS, &bar[1], blockIdx.x);
+  }
+  const double alpha = args.init ? 0.0 : cgs->alpha;
+  const int init = args.init;
+  double sums[2] = {0.0, 0.0};
+  const int el = tid / NCOL, c = tid - el * NCOL;
+  const int ca = c % L, cb = c / L;
+  int it = 0;
+  for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++it) {
+    const uint32_t parity = (uint32_t)(it & 1);
+    const int gn = (g + (int)gridDim.x < ngroups) ? g + (int)gridDim.x : -1;
+    const int e0 = g * EPB;
+    const int ne = min(EPB, A->nel - e0);
+    // ---- load phase from the staged group: CG residual update, norm partial, residual -> sA (padded rows)
+    double rr[PER];
+    pm_mbar_wait(&bar[0], parity);
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+      const int t = tid + q * NT;
+      rr[q] = 0.0;
+      if (t < ne * NP) {
+        const long long gi = (long long)e0 * NP + t;
+        double v = stg[t];
+        if (init) {
+          A->x[gi] = 0.0;
+          A->pdir[gi] = 0.0;
+        } else {
+          v = fma(-alpha, stg[EPB * NP + t], v);
+          A->r[gi] = v;
+        }
+        rr[q] = v;
+        sums[0] = fma(v * v, stg[2 * EPB * NP + t], sums[0]);
+        const int e1 = t / NP, p = t - e1 * NP;
+        sA[e1 * ESZ + (p / L) * PI + (p % L)] = v;
+      }
+    }
+    pm_mbar_wait(&bar[1], parity);
+    if (tid < ne) {                                 // threshold scale of the element: sum_d max_i lam_d[i]
+      double mx = 0.0;
+      for (int d = 0; d < D; ++d) {
+        double m = sL[(tid * D + d) * L];
+        for (int i = 1; i < L; ++i) m = fmax(m, sL[(tid * D + d) * L + i]);
+        mx += m;
+      }
+      sMx[tid] = mx;
+    }
+    __syncthreads();                                // streamed half consumed
+    if (tid == 0 && gn >= 0) pfp_issue_stream<L>(A, stg, &bar[0], gn);
+    const bool act = el < ne;
+    double* in = sA + el * ESZ;
+    double* ou = sB + el * ESZ;
+#pragma unroll
+    for (int pass = 0; pass < 2 * D; ++pass) {
+      const int d = (pass < D) ? pass : (2 * D - 1 - pass);
+      const bool fwd = pass < D;
+      if (act) {
+        int base, str;
+        if (d == 0) { base = (cb * L + ca) * PI; str = 1; }
+        else if (d == 1) { base = cb * L * PI + ca; str = PI; }
+        else { base = cb * PI + ca; str = L * PI; }
+        const double* Sd = sS + (el * D + d) * LL;
+        double v[L], o[L];
+#pragma unroll
+        for (int a = 0; a < L; ++a) v[a] = in[base + a * str];
+        if (pass == 0) {
+          double s1 = 0.0, s0 = 0.0;
+#pragma unroll
+          for (int a = 0; a < L; ++a) { s1 = fma(sl1[a], v[a], s1); s0 = fma(sl0[a], v[a], s0); }
+          sP[(el * NCOL + c) * 2] = s0;
+          sP[(el * NCOL + c) * 2 + 1] = s1;
+        }
+        if (fwd) {
+#pragma unroll
+          for (int i = 0; i < L; ++i) o[i] = 0.0;
+#pragma unroll
+          for (int a = 0; a < L; ++a) {
+            const double2* row = reinterpret_cast<const double2*>(Sd + a * L);
+#pragma unroll
+            for (int i2 = 0; i2 < L / 2; ++i2) {
+              const double2 s2 = row[i2];
+              o[2 * i2] = fma(s2.x, v[a], o[2 * i2]);
+              o[2 * i2 + 1] = fma(s2.y, v[a], o[2 * i2 + 1]);
+            }
+          }
+          if (d == D - 1) {
+            const double* lam = sL + el * D * L;
+            const double mx = sMx[el];
+            const double l01 = lam[ca] + lam[L + cb];
+#pragma unroll
+            for (int i = 0; i < L; ++i) {
+              const double den = l01 + lam[(D - 1) * L + i];
+              o[i] = (den > 1e-12 * mx) ? o[i] / den : 0.0;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int a = 0; a < L; ++a) {
+            const double2* row = reinterpret_cast<const double2*>(Sd + a * L);
+            double sacc = 0.0;
+#pragma unroll
+            for (int i2 = 0; i2 < L / 2; ++i2) {
+              const double2 s2 = row[i2];
+              sacc = fma(s2.x, v[2 * i2], sacc);
+              sacc = fma(s2.y, v[2 * i2 + 1], sacc);
+            }
+            o[a] = sacc;
+          }
+        }
+#pragma unroll
+        for (int a = 0; a < L; ++a) ou[base + a * str] = o[a];
+      }
+      __syncthreads();
+      if (pass == 0 && tid < ne * L * 4) {
+        const int e1 = tid / (L * 4), rem = tid - e1 * (L * 4);
+        const int kb = rem >> 2, b0 = rem & 1, b1 = (rem >> 1) & 1;
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < L; ++j) acc = fma(b1 ? sl1[j] : sl0[j], sP[(e1 * NCOL + kb * L + j) * 2 + b0], acc);
+        sQ[tid] = acc;
+      }
+      if (pass == 1 && tid < ne * NK) {
+        const int e1 = tid / NK, k = tid - e1 * NK;
+        const int b0 = k & 1, b1 = (k >> 1) & 1, b2 = (k >> 2) & 1;
+        double acc = 0.0;
+#pragma unroll
+        for (int kb = 0; kb < L; ++kb) acc = fma(b2 ? sl1[kb] : sl0[kb], sQ[e1 * L * 4 + kb * 4 + b1 * 2 + b0], acc);
+        A->rc[(long long)(e0 + e1) * NK + k] = acc;
+        if (A->rc0) A->rc0[(long long)(e0 + e1) * NK + k] = acc;
+      }
+      if (pass == 2 * D - 1 && tid == 0 && gn >= 0) pfp_issue_fac<L>(A, sS, &bar[1], gn);      // factor half consumed
+      double* tmp = in; in = ou; ou = tmp;
+    }
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+      const int t = tid + q * NT;
+      if (t < ne * NP) {
+        const int e1 = t / NP, p = t - e1 * NP;
+        const double val = sA[e1 * ESZ + (p / L) * PI + (p % L)];
+        A->zloc[(long long)e0 * NP + t] = val;
+        sums[1] = fma(val, rr[q], sums[1]);
+      }
+    }
+    __syncthreads();                                // sA is rewritten by the next group's load phase
+  }
+  grid_sum_finish<2>(sums, part, counter, out, sred);
+}
+
 // Coarse levels with their share of z.r.  Threads [0, vthreads): one vertex each, xv = d1inv * rv with rv = the sum of the corner
 // sums over ALL (element, corner) entries of the vertex on ALL ranks (`assembled`: rc already holds that total in every copy after the
 // vertex gather-scatter; otherwise it is summed here from the local entries); contribution to z.r: xv * (sum of the LOCAL entries
@@ -723,6 +973,20 @@ __global__ void k_pm_corner_values(int nel, int nk, const double* __restrict__ x
   xc[t] = (k < nk) ? xv[vid[e * nk + k]] : x2[agg[e]];
 }
 
+// x += alpha p of the LAST iteration of a solve (the direction kernel that would have applied it is skipped once converged)
+__global__ void k_pcg_xfix(double* __restrict__ x, const double* __restrict__ p, const CGState* __restrict__ cgs, long long n2) {
+  const double a = cgs->alpha;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x)
+    x[i] = fma(a, p[i], x[i]);
+}
+int pm_pcg_xfix(Ctx* c) {
+  const long long nb = std::min<long long>((c->n2 + 1023) / 1024, 148 * 8);
+  k_pcg_xfix<<<(int)std::max<long long>(nb, 1), 256, 0, c->stream>>>(c->pk[1], c->pk[2], c->cgs + 3, c->n2);
+  nsb_count_launch();
+  NSB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------- host helpers
 // symmetric eigen-decomposition by cyclic Jacobi rotations (n <= 8): A = V diag(w) V^T, A destroyed
 static void jacobi_eig(int n, double* A, double* V, double* w) {
@@ -805,7 +1069,8 @@ static bool gen_eig(int n, const double* A, const double* M, double* S, double* 
   return true;
 }
 
-// dense SPD inverse by Cholesky (n <= 512), in place; false if not positive definite
+// dense SPD inverse by Cholesky, in place; false if not positive definite.  O(n^3) scalar code: used up to n = 512, larger
+// aggregate operators (multi-rank) go through LAPACK dpotrf/dpotri (host_krylov.cpp nsb_lapack_spd_inverse)
 static bool spd_inverse(int n, std::vector<double>& A) {
   std::vector<double> Lc((size_t)n * n, 0.0), Li((size_t)n * n, 0.0);
   for (int j = 0; j < n; ++j) {
@@ -1141,9 +1406,27 @@ int pm_pcg_tail(Ctx* c, int set, int init, int prof_slot) {
   CGState* sp = c->cgs + 3;
   double* sc = m.ra + m.nagg;
   const bool multi = c->nranks > 1;
-  PM_DISPATCH(c, (k_pcg_fused<D, L><<<(c->nel + Pm2<D, L>::EPB - 1) / Pm2<D, L>::EPB, Pm2<D, L>::NT, 0, c->stream>>>(
-                     c->pk[0], c->pk[1], c->pk[2], c->pk[3], c->bm2inv, c->pz, m.rc, multi ? m.rc0 : nullptr, c->nel, m.S, m.lam, sp, init,
-                     c->red_part, c->red_count, sc)));
+  static const bool pers = [] { const char* e = getenv("NSB_PCG_FUSED_P"); return !(e && e[0] == '0'); }();
+  if (pers && c->ldim == 3 && c->lx2 == 6) {               // persistent, TMA-pipelined (lx1 = 8)
+    constexpr int L = 6;
+    static bool attr = false;
+    if (!attr) {
+      NSB_CUDA(cudaFuncSetAttribute(k_pcg_fused_p<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PfP<L>::smem));
+      NSB_CUDA(cudaFuncSetAttribute(k_pcg_fused_p<L>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+      attr = true;
+    }
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    PfArgs a{c->pk[0], c->pk[3], c->bm2inv, m.S, m.lam, c->pk[1], c->pk[2], c->pz, m.rc, multi ? m.rc0 : nullptr, c->nel, init, 0.0};
+    const int ngroups = (c->nel + PfP<L>::EPB - 1) / PfP<L>::EPB;
+    k_pcg_fused_p<L><<<std::min(ngroups, 2 * sms), PfP<L>::NT, PfP<L>::smem, c->stream>>>(a, sp, c->red_part, c->red_count, sc);
+    nsb_count_launch();
+    NSB_CUDA(cudaGetLastError());
+  } else {
+    PM_DISPATCH(c, (k_pcg_fused<D, L><<<(c->nel + Pm2<D, L>::EPB - 1) / Pm2<D, L>::EPB, Pm2<D, L>::NT, 0, c->stream>>>(
+                       c->pk[0], c->pk[1], c->pk[2], c->pk[3], c->bm2inv, c->pz, m.rc, multi ? m.rc0 : nullptr, c->nel, m.S, m.lam, sp, init,
+                       c->red_part, c->red_count, sc)));
+  }
   if (prof_slot > 0) cudaEventRecord(c->prof_ev[prof_slot], c->stream);
   if (multi) NSB_TRY(gs_dssum_map(c, c->gsv, c->p2pv, m.rc, 1, 0, sp));                 // vertex sums across elements and ranks
   const int vthreads = ((std::max(m.nv, m.nagg) + 31) / 32) * 32;
@@ -1280,8 +1563,10 @@ int pm_setup(Ctx* c, int set, int nagg_req) {
   NSB_TRY(pm_upload(&m.voff, voff));
   NSB_TRY(pm_upload(&m.vent, vent));
   // ---- aggregates (recursive coordinate bisection of the local elements)
+  // aggregates per rank: nelv/32, at most 512 per rank and 4096 in total (r1: a fixed total of 512 made the aggregates grow with the
+  // rank count under weak scaling: 55 -> 61 iterations per step at 2-8 GPUs)
   int nagg = nagg_req > 0 ? std::max(1, nagg_req / c->nranks) : std::max(1, nel / 32);
-  nagg = std::max(1, std::min(std::min(nagg, nel), 512 / c->nranks));
+  nagg = std::max(1, std::min(std::min(nagg, nel), std::min(512, 4096 / c->nranks)));
   m.nagg_loc = nagg; m.nagg = nagg; m.agg_first = 0;
   if (c->nranks > 1) {      // global aggregate ids: rank-ordered blocks
     std::vector<double> cnt(c->nranks, 0.0);
@@ -1383,7 +1668,7 @@ int pm_setup(Ctx* c, int set, int nagg_req) {
   }
   if (c->ifvcor[set] && m.nagg == 1) {
     A2[0] = 0.0;
-  } else if (!spd_inverse(m.nagg, A2)) {
+  } else if (!(m.nagg > 512 ? nsb_lapack_spd_inverse(m.nagg, A2.data()) == 0 : spd_inverse(m.nagg, A2))) {
     nsb_set_error("pmg: aggregate operator not positive definite");
     return 1;
   }

@@ -278,6 +278,7 @@ int st_pressure(Ctx* c, int adj, int* iters) {
     }
     if (issued > c->maxit_p + c->check_every_p) break;
   }
+  if (fused && c->cgs_host[3].iter > 0) NSB_TRY(pm_pcg_xfix(c));       // the last x += alpha p (see k_gradt3 MODE 2)
   NSB_TRY(p2p_check_error(c));
   if (!(c->cgs_host[3].rnorm == c->cgs_host[3].rnorm)) { nsb_set_error("pressure CG produced NaN"); return 2; }
   if (proj) NSB_TRY(proj_post(c, adj));

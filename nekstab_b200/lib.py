@@ -151,6 +151,14 @@ def load_library(path: str = LIB_PATH):
         return _lib
     if not os.path.exists(path):
         raise NsbError(f"{path} not found: run `python -m nekstab_b200.build` (no CPU fallback exists)")
+    # Python hosts only: PyTorch bundles its own, newer libnccl.so.2.  The dynamic loader keeps ONE library per SONAME, so if this
+    # library pulled in the system NCCL first, a later `import torch` in the same process fails (undefined symbol ncclDevCommCreate).
+    # Importing torch first makes both use torch's NCCL (a superset of the API used here).  A Fortran host never loads torch.
+    if os.environ.get("NSB_NO_TORCH_PRELOAD") != "1":
+        try:
+            import torch  # noqa: F401
+        except Exception:
+            pass
     lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
     for name, args in _SIGS.items():
         fn = getattr(lib, name)

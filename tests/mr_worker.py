@@ -25,8 +25,10 @@ def main():
     failures = []
     for name in ("box3d_n8_outflow", "box2d_n6_outflow", "box3d_n6_dirichlet"):
         gc = small_cases()[name]
-        s = make_oracle(gc)
         part = cases.partition(gc.key, world, gc.d2)
+        if np.bincount(part, minlength=world).min() == 0:       # this small mesh leaves a rank without elements at this world size
+            continue
+        s = make_oracle(gc)
         sel = np.nonzero(part == rank)[0]
         c = gc.local_part(rank, world)
         g = lib.NekStabB200(c, device=lr, rank=rank, nranks=world, nccl_id=ids[0])

@@ -82,9 +82,7 @@ int nsb_set_projection(int mxprev);
  * nelv/32 per rank, at most 512 per rank and 4096 in total -- the aggregate size, hence the iteration count, then stays the same under
  * weak scaling).  Changes the
  * iteration count (measured 2 787 -> 206 on the cylinder mesh), not the converged pressure.  Rebuilt automatically when
- * nsb_set_adjoint_masks changes the adjoint operator.  Environment NSB_PRECOND=1 selects kind 1 at nsb_init.
- * kind 2 (EXPERIMENTAL, single GPU, not yet validated on hardware): as kind 1 with the vertex-mesh level replaced by a V-cycle on
- * the assembled P^T E P (CPU prototype: oracle/pmg.py `q1_cycle`; 201 -> 169 iterations on the cylinder mesh). */
+ * nsb_set_adjoint_masks changes the adjoint operator.  Environment NSB_PRECOND=1 selects kind 1 at nsb_init. */
 int nsb_set_pressure_preconditioner(int kind, int nagg);
 
 /* ------------------------------------------------------------------ krylov_vector algebra

@@ -233,17 +233,13 @@ extern "C" int nsb_init(int ldim, int lx1, int lxd, int lx2, int nelv, long long
   c->ifvcor[1] = c->ifvcor[0];
   c->mask_same[1] = c->mask_same[0];
   c->has_adj_masks = false;
-  // measured (r1b): the separate, segment-sorted dssum (0.115 ms) + k_div3 (0.318 ms) beats the fused gather (0.465 ms) on
-  // cfg 5, so the fused variant is opt-in
+  // (r1b, measured: a per-element gather fused into k_div3 lost to the separate segment-sorted dssum, 0.465 vs 0.115 + 0.238 ms; removed)
   const char* ng = getenv("NSB_GRAPHS");
   c->use_graphs = !(ng && ng[0] == '0');
   const char* np_ = getenv("NSB_PERSISTENT");
   c->persistent_pcg = !(np_ && np_[0] == '0');
-  c->persistent_gradt = (np_ && np_[0] == '2');
   const char* nt = getenv("NSB_PCG_FUSED");
   c->pcg_fused = !(nt && nt[0] == '0');
-  const char* nf = getenv("NSB_FUSED_GS");
-  c->fused_gs = (c->ldim == 3 && c->nranks == 1 && c->gs.nb_off != nullptr && nf && nf[0] == '1');
   NSB_CUDA(cudaStreamSynchronize(c->stream));
   const char* pcv = getenv("NSB_PRECOND");
   if (pcv && pcv[0] == '1') NSB_TRY(nsb_set_pressure_preconditioner(1, 0));
@@ -272,7 +268,6 @@ extern "C" int nsb_set_adjoint_masks(const double* m0, const double* m1, const d
   c->has_adj_masks = true;
   NSB_CUDA(cudaStreamSynchronize(c->stream));
   if (c->pc_kind) NSB_TRY(pm_setup(c, 1, c->pc_nagg));
-  if (c->pc_kind == 2) NSB_TRY(pm_setup_vcycle(c, 1));
   return 0;
 }
 
@@ -338,7 +333,7 @@ extern "C" int nsb_set_projection(int mxprev) {
 }
 extern "C" int nsb_set_pressure_preconditioner(int kind, int nagg) {
   REQUIRE_CTX();
-  if (kind < 0 || kind > 2) { nsb_set_error("nsb_set_pressure_preconditioner: kind must be 0 (Jacobi), 1 (pmg) or 2 (experimental)"); return 1; }
+  if (kind < 0 || kind > 1) { nsb_set_error("nsb_set_pressure_preconditioner: kind must be 0 (Jacobi) or 1 (three-level Schwarz/multilevel)"); return 1; }
   if (nagg < 0 || nagg > 4096) { nsb_set_error("nsb_set_pressure_preconditioner: nagg must be in [0, 4096]"); return 1; }
   drop_graphs(c);
   c->pc_kind = 0;
@@ -351,10 +346,6 @@ extern "C" int nsb_set_pressure_preconditioner(int kind, int nagg) {
   c->pc_nagg = nagg;
   NSB_TRY(pm_setup(c, 0, nagg));
   if (c->has_adj_masks) NSB_TRY(pm_setup(c, 1, nagg));     // separate adjoint masks => a different E => its own factors
-  if (kind == 2) {                                          // experimental Q1 V-cycle on top of the kind-1 set-up
-    NSB_TRY(pm_setup_vcycle(c, 0));
-    if (c->has_adj_masks) NSB_TRY(pm_setup_vcycle(c, 1));
-  }
   c->pc_kind = kind;
   return 0;
 }

@@ -1107,8 +1107,8 @@ int ek_div_mbinv(Ctx* c, const double* u, int adj, double* q, double sign) {
 }
 
 int ek_pcg_div(Ctx* c, int adj) {
-  // w = wk[2] (dssum'd, or raw when the gather is fused), Ep = pk[3], pdir = pk[2]
-  if (c->ldim == 3) return pk_pcg_div(c, adj, c->fused_gs ? 1 : 0);
+  // w = wk[2] (dssum'd), Ep = pk[3], pdir = pk[2]
+  if (c->ldim == 3) return pk_pcg_div(c, adj, 0);
   DISPATCH_DN(c, k_div<D, N, 1><<<c->nel, Cfg<D, N>::TPB, 0, c->stream>>>(
                      c->wk[2], c->mbinv[adj][0], c->mbinv[adj][1], c->mbinv[adj][c->ldim == 3 ? 2 : 1], c->pk[3], c->RW2, c->pk[2],
                      c->cgs + 3, c->red_part, c->red_count, c->red_out, c->nranks == 1, c->n, c->n2, 1.0));

@@ -94,7 +94,6 @@ int gs_free_map(Ctx* c, GSMap& m, P2P& p) {
   cudaFree(m.seg_off); cudaFree(m.seg_idx); cudaFree(m.send_seg); cudaFree(m.rseg_off); cudaFree(m.rseg_pos);
   cudaFree(m.rseg_nbefore); cudaFree(m.sendbuf); cudaFree(m.recvbuf);
   cudaFree(m.send_base); cudaFree(m.send_cnt); cudaFree(m.rseg_cnt);
-  cudaFree(m.surf_pts); cudaFree(m.nb_off); cudaFree(m.nb_idx);
   m = GSMap();
   return 0;
 }
@@ -244,11 +243,11 @@ extern "C" int nsb_gs_host_get(int which, int* out) {
   return 0;
 }
 
-int gs_setup(Ctx* c, const long long* glo) { return gs_build(c, c->gs, c->p2p, c->n, c->lx1, c->np1, glo, true); }
+int gs_setup(Ctx* c, const long long* glo) { return gs_build(c, c->gs, c->p2p, c->n, c->lx1, c->np1, glo); }
 
 // Build a gather-scatter map over `n` local dofs with global ids `glo` (np dofs per element on an N^ldim grid): the
 // velocity mesh (N = lx1) or the element-vertex mesh of the pressure preconditioner (N = 2).
-int gs_build(Ctx* c, GSMap& m, P2P& p2p, long long n, int N1, int np_e, const long long* glo, bool gather_table) {
+int gs_build(Ctx* c, GSMap& m, P2P& p2p, long long n, int N1, int np_e, const long long* glo) {
   if (n >= (1LL << 31)) { nsb_set_error("gs_setup: more than 2^31 local dofs"); return 1; }
   HostPlan P;
   plan_sort(P, n, glo);
@@ -285,37 +284,6 @@ int gs_build(Ctx* c, GSMap& m, P2P& p2p, long long n, int N1, int np_e, const lo
   m.nbr_rank = P.nbr_rank; m.nbr_off = P.nbr_off;
   m.nnbr = (int)m.nbr_rank.size();
   m.nshared = P.nshared;
-  const std::vector<int>&order = P.order, &ustart = P.ustart;
-  const int nu = (int)P.uid.size();
-  // ---- per-element gather table (fused direct-stiffness sum; single rank only: no halo entries)
-  if (c->nranks == 1 && gather_table) {
-    const int N = N1, D = c->ldim, np = np_e;
-    std::vector<int> surf;
-    for (int p = 0; p < np; ++p)
-      if (is_surface(p, N, D)) surf.push_back(p);
-    const int ns = (int)surf.size();
-    std::vector<int> uof(n);                       // dof -> index of its unique id
-    for (int k = 0; k < nu; ++k)
-      for (int j = ustart[k]; j < ustart[k + 1]; ++j) uof[order[j]] = k;
-    std::vector<int> nb_off((size_t)c->nel * (ns + 1)), nb_idx;
-    nb_idx.reserve((size_t)c->nel * ns * 2);
-    bool overflow = false;
-    for (int e = 0; e < c->nel; ++e) {
-      for (int s = 0; s < ns; ++s) {
-        nb_off[(size_t)e * (ns + 1) + s] = (int)nb_idx.size();
-        const int k = uof[(size_t)e * np + surf[s]];
-        for (int j = ustart[k]; j < ustart[k + 1]; ++j) nb_idx.push_back(order[j]);   // ascending dof order
-        if (nb_idx.size() > (size_t)2000000000) overflow = true;
-      }
-      nb_off[(size_t)e * (ns + 1) + ns] = (int)nb_idx.size();
-    }
-    if (!overflow) {
-      m.ns = ns;
-      NSB_TRY(upload(&m.surf_pts, surf));
-      NSB_TRY(upload(&m.nb_off, nb_off));
-      NSB_TRY(upload(&m.nb_idx, nb_idx));
-    }
-  }
   NSB_TRY(upload(&m.seg_off, P.seg_off));
   NSB_TRY(upload(&m.seg_idx, P.seg_idx));
   NSB_TRY(upload(&m.send_seg, P.send_seg));

@@ -75,13 +75,6 @@ struct GSMap {
   int* rseg_cnt = nullptr;   // parallel to rseg_pos
   double* sendbuf = nullptr; // [3*nshared]
   double* recvbuf = nullptr;
-  // per-element gather table for kernels that fuse the direct-stiffness sum into their load phase (single rank):
-  // for element e and surface slot s (local point surf_pts[s]): dofs nb_idx[nb_off[e*(ns+1)+s] .. nb_off[e*(ns+1)+s+1])
-  // = ALL copies of that node in ascending dof order (own copy included)
-  int ns = 0;
-  int* surf_pts = nullptr;
-  int* nb_off = nullptr;
-  int* nb_idx = nullptr;
 };
 
 // NVLink peer-memory collectives (p2p.cu)
@@ -120,16 +113,6 @@ struct PMG {
   double* rc0 = nullptr;            // un-assembled copy of rc (multi-rank: rc is summed across ranks in place)
   std::vector<int> h_agg;
   std::vector<double> h_d1, h_A2inv;
-  // EXPERIMENTAL (kind 2, single rank, not yet validated on a GPU): Q1 level as a V-cycle on the assembled A_c = P^T E P
-  bool vc_ready = false;
-  int vc_ncolours = 0;
-  int *vc_off = nullptr, *vc_col = nullptr;   // CSR of A_c (rows = local vertices)
-  double* vc_val = nullptr;
-  double* vc_odinv = nullptr;                 // omega / diag(A_c)
-  int* vc_vagg = nullptr;                     // vertex -> aggregate
-  int *vc_aoff = nullptr, *vc_aent = nullptr; // CSR aggregate -> vertices
-  double* vc_A2inv = nullptr;                 // (P2^T A_c P2)^-1
-  double *vc_rv = nullptr, *vc_x = nullptr, *vc_r1 = nullptr;   // work [nv]
 };
 
 struct Ctx {
@@ -187,9 +170,7 @@ struct Ctx {
   double dt = 0;
   int nsteps = 0;
   int check_every_v = 4, check_every_p = 32;
-  bool persistent_gradt = false;
-  bool persistent_pcg = true; // 3-D: persistent, TMA-pipelined k_gradt3p / k_div3p in the pressure-CG loop (NSB_PERSISTENT=0 disables)
-  bool fused_gs = false;      // 3-D, single rank: k_div3 gathers the surface sums itself (no dssum in the pressure loop)
+  bool persistent_pcg = true; // 3-D: persistent, TMA-pipelined div kernels in the pressure-CG loop (NSB_PERSISTENT=0 disables)
   bool pcg_fused = true;      // 3-D, pc_kind 1: fused CG tail (pm_pcg_tail) + coarse levels added in the direction kernel (NSB_PCG_FUSED=0 disables)
 
   double* adv_scratch = nullptr;   // per-CTA fine-mesh work arrays of the advection kernel (L2-resident)
@@ -269,7 +250,7 @@ void sem_build_constmats(int lx1, int lx2, int lxd, ConstMats* cm);
 int gs_setup(Ctx* c, const long long* glo_num);
 int gs_free(Ctx* c);
 int gs_dssum(Ctx* c, double* u, int nfields, long long stride, const CGState* skip_if_done = nullptr);
-int gs_build(Ctx* c, GSMap& m, P2P& p2p, long long n, int N1, int np_e, const long long* glo, bool gather_table);
+int gs_build(Ctx* c, GSMap& m, P2P& p2p, long long n, int N1, int np_e, const long long* glo);
 int gs_dssum_map(Ctx* c, GSMap& m, P2P& p2p, double* u, int nfields, long long stride, const CGState* skip_if_done);
 int gs_free_map(Ctx* c, GSMap& m, P2P& p);
 
@@ -344,7 +325,6 @@ int vk_wavemaker(Ctx* c, const double* dre, const double* dim, const double* are
 
 // ---- pressure preconditioner (pmg.cu)
 int pm_setup(Ctx* c, int set, int nagg_req);
-int pm_setup_vcycle(Ctx* c, int set);
 int pm_apply(Ctx* c, int set, const double* r, double* z, int mode, int prof_slot = 0);
 int pm_pcg_tail(Ctx* c, int set, int init, int prof_slot);
 int pm_pcg_xfix(Ctx* c);                                     // x += alpha p of the last iteration (fused path)   // fused CG update + restriction + element blocks + coarse levels + scalars (3-D)

@@ -3,10 +3,9 @@
 //
 //   k_gradt3 : w_c = D_c^T p      mesh 2 (GL, lx2^3) -> mesh 1 (GLL, lx1^3)   [UPSTREAM navier1.f opgradt/cdtp]
 //   k_div3   : q = sum_c D_c u_c  mesh 1 -> mesh 2                              [UPSTREAM navier1.f opdiv/multd]
-// optionally fused with the CG vector work (direction update before gradt; p.Ep partial after div) and with the
-// gather-scatter: in FUSED mode k_div3 sums the copies of every element-surface node itself from a per-element
-// gather table (all copies, ascending dof order => every copy sees the bit-identical sum), so the separate
-// dssum kernel and its write-back disappear from the pressure loop.
+// optionally fused with the CG vector work (direction update before gradt; p.Ep partial after div).  (r1b: a variant of k_div3
+// that summed the copies of every element-surface node itself from a per-element gather table -- no dssum launch -- was measured
+// slower than the separate segment-sorted dssum, 0.465 vs 0.115 + 0.238 ms, and was removed in r2.)
 //
 // r1a ncu (profiles/r1a_*): the first-generation kernels were bound by the shared-memory pipe (LSU wavefronts 89 %,
 // barrier stalls), not by DRAM.  Changes here: (1) all three components go through each tensor stage together
@@ -208,14 +207,12 @@ k_gradt3(const double* __restrict__ p, double* __restrict__ w, const double* __r
 
 // ------------------------------------------------------------------------------------------------ div
 // MODE 0: q = sign * sum_c D_c (scale_c u_c)      MODE 1: CG (Ep, rho = sum pdir*Ep)
-// FUSED 1: the copies of every surface node are summed here from the gather table (replaces dssum)
-template <int N, int MODE, int FUSED>
+template <int N, int MODE>
 __global__ void __launch_bounds__(PK_TPB, 3)
 k_div3(const double* __restrict__ u, const double* __restrict__ scale0, const double* __restrict__ scale1,
        const double* __restrict__ scale2, double* __restrict__ qout, const double* __restrict__ RW2,
        const double* __restrict__ pdir, CGState* __restrict__ cgs, double* __restrict__ part, unsigned* counter,
-       double* __restrict__ red_out, int finalize, long long n, long long n2, double sign,
-       const int* __restrict__ surf_pts, int ns, const int* __restrict__ nb_off, const int* __restrict__ nb_idx) {
+       double* __restrict__ red_out, int finalize, long long n, long long n2, double sign) {
   constexpr int N2 = N - 2, TPB = PK_TPB;
   constexpr int NP1 = N * N * N, NP2 = N2 * N2 * N2;
   using S1 = Shp<N, N, N>;
@@ -249,51 +246,14 @@ k_div3(const double* __restrict__ u, const double* __restrict__ scale0, const do
     if (MODE == 1) __pipeline_memcpy_async(&srw[9 * NP2 + tid], &pdir[e2 + tid], sizeof(double));
   }
   __pipeline_commit();
-  if (FUSED) {
-    // ---- stage the three (scaled) components, then overwrite the surface nodes with the gathered sums
-    for (int q = tid; q < NP1; q += TPB) {
-      const int o = S1::lin(q);
-      const double s0 = scale0 ? scale0[e1 + q] : 1.0;
-      const double s1 = scale1 ? scale1[e1 + q] : s0;
-      const double s2 = scale2 ? scale2[e1 + q] : s0;
-      su[o] = u[e1 + q] * s0;
-      su[S1::size + o] = u[n + e1 + q] * s1;
-      su[2 * S1::size + o] = u[2 * n + e1 + q] * s2;
-    }
-    __syncthreads();
-    const int* off = nb_off + (long long)blockIdx.x * (ns + 1);
-    for (int s = tid; s < ns; s += TPB) {
-      const int q = surf_pts[s];
-      const int a = off[s], b = off[s + 1];
-      double g0 = 0.0, g1 = 0.0, g2 = 0.0;
-      for (int j = a; j < b; ++j) {
-        const int idx = nb_idx[j];
-        g0 += u[idx];
-        g1 += u[n + idx];
-        g2 += u[2 * n + idx];
-      }
-      const int o = S1::lin(q);
-      const double s0 = scale0 ? scale0[e1 + q] : 1.0;
-      const double s1 = scale1 ? scale1[e1 + q] : s0;
-      const double s2 = scale2 ? scale2[e1 + q] : s0;
-      su[o] = g0 * s0;
-      su[S1::size + o] = g1 * s1;
-      su[2 * S1::size + o] = g2 * s2;
-    }
-    __syncthreads();
-  }
-  // ---- t stage: aJ = J12 u, aD = D12 u along t (same input column, two outputs).  Without the fused gather the
-  //      column is read straight from global memory: lanes run over (j,i), so each of the N loads is coalesced.
+  // ---- t stage: aJ = J12 u, aD = D12 u along t (same input column, two outputs).  The column is read straight from global
+  //      memory: lanes run over (j,i), so each of the N loads is coalesced.
   static_assert(3 * C2::ncol <= TPB, "one task per thread");
   if (tid < 3 * C2::ncol) {
     const int t = tid;
     const int c = t / C2::ncol, col = t - c * C2::ncol;
     double v[N];
-    if (FUSED) {
-      const double* pin = su + c * S1::size + C2::base(col);
-#pragma unroll
-      for (int l = 0; l < N; ++l) v[l] = pin[l * C2::stride];
-    } else {
+    {
       const double* sc = (c == 0 || !scale1) ? scale0 : (c == 1 ? scale1 : scale2);
       const double* pu = u + (long long)c * n + e1 + col;
       if (sc) {
@@ -394,130 +354,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // the previous element is being contracted, so DRAM requests are in flight for the whole life of the CTA instead of
 // only during each CTA's load phase (r1b ncu: k_div3 27 % DRAM, barrier + long-scoreboard stalls).
 template <int N>
-struct GradtP {
-  static constexpr int N2 = N - 2, NP1 = N * N * N, NP2 = N2 * N2 * N2;
-  static constexpr int NIN = 12;                                   // 9 metric arrays, r, dinvE, pdir
-  using SA = Shp<N2, N2, N>;
-  using SB = Shp<N2, N, N>;
-  static constexpr int in_doubles = 2 * NIN * NP2;
-  static constexpr size_t smem = sizeof(double) * (in_doubles + 9 * SA::size + 6 * SB::size) + 2 * sizeof(uint64_t);
-};
-
-// One element of k_gradt3p.  Deliberately NOT inlined: inside the persistent element loop the compiler would treat the
-// constant-bank operator matrices as loop invariants and hoist them into registers (80+ registers and spills, measured).
-template <int N>
-__device__ __noinline__ void gradt3_element(const double* __restrict__ in, double* __restrict__ sq, double* __restrict__ sa,
-                                            double* __restrict__ sb, double* __restrict__ w, double* __restrict__ pdir,
-                                            double beta, long long n, int e, int tid) {
-  using P = GradtP<N>;
-  constexpr int N2 = P::N2, NP1 = P::NP1, NP2 = P::NP2;
-  using S2 = Shp<N2, N2, N2>;
-  using SA = typename P::SA;
-  using SB = typename P::SB;
-  using C0 = ColIn<0, N2, N2, N2>;
-  using C1 = ColIn<1, N2, N2, N>;
-  using C2 = ColIn<2, N2, N, N>;
-  {
-    const long long e2 = (long long)e * NP2, e1 = (long long)e * NP1;
-    if (tid < NP2) {
-      const int q = tid;
-      const double v = in[10 * NP2 + q] * in[9 * NP2 + q] + beta * in[11 * NP2 + q];
-      pdir[e2 + q] = v;
-      const int o = S2::lin(q);
-#pragma unroll
-      for (int g = 0; g < 9; ++g) sq[g * S2::size + o] = in[g * NP2 + q] * v;
-    }
-    __syncthreads();
-    if (tid < 9 * C0::ncol) {
-      const int combo = tid / C0::ncol, col = tid - combo * C0::ncol;
-      const double* pin = sq + combo * S2::size + C0::base(col);
-      double v[N2];
-#pragma unroll
-      for (int l = 0; l < N2; ++l) v[l] = pin[l];
-      double* po = sa + combo * SA::size + col * SA::PI;
-      if (combo < 3) apply_store<N, N2>(cm.D12t, v, po, 1);
-      else apply_store<N, N2>(cm.J12t, v, po, 1);
-    }
-    __syncthreads();
-    if (tid < 6 * C1::ncol) {
-      const int grp = tid / C1::ncol, col = tid - grp * C1::ncol;
-      const int which = grp / 3, c = grp - which * 3;
-      const int bi = C1::base(col);
-      const int bo = (col / N) * N * SB::PI + (col % N);
-      double v[N2], v2[N2];
-      double* po = sb + (c * 2 + which) * SB::size + bo;
-      if (which == 0) {
-#pragma unroll
-        for (int l = 0; l < N2; ++l) { v[l] = sa[c * SA::size + bi + l * C1::stride]; v2[l] = sa[(3 + c) * SA::size + bi + l * C1::stride]; }
-        apply2_store<N, N2>(cm.J12t, v, cm.D12t, v2, po, SB::PI);
-      } else {
-#pragma unroll
-        for (int l = 0; l < N2; ++l) v[l] = sa[(6 + c) * SA::size + bi + l * C1::stride];
-        apply_store<N, N2>(cm.J12t, v, po, SB::PI);
-      }
-    }
-    __syncthreads();
-    if (tid < 3 * C2::ncol) {
-      const int c = tid / C2::ncol, col = tid - c * C2::ncol;
-      const int bi = C2::base(col);
-      double v[N2], v2[N2];
-#pragma unroll
-      for (int l = 0; l < N2; ++l) { v[l] = sb[(c * 2) * SB::size + bi + l * C2::stride]; v2[l] = sb[(c * 2 + 1) * SB::size + bi + l * C2::stride]; }
-      apply2_store<N, N2>(cm.J12t, v, cm.D12t, v2, w + (long long)c * n + e1 + col, N * N);
-    }
-    __syncthreads();
-  }
-}
-
-template <int N>
-__global__ void __launch_bounds__(PK_TPB, 2)
-k_gradt3p(const double* __restrict__ r, double* __restrict__ w, const double* __restrict__ RW2, const double* __restrict__ dinvE,
-          double* __restrict__ pdir, const CGState* __restrict__ cgs, long long n, long long n2, int nel) {
-  using P = GradtP<N>;
-  constexpr int N2 = P::N2, TPB = PK_TPB, NP1 = P::NP1, NP2 = P::NP2, NIN = P::NIN;
-  using S2 = Shp<N2, N2, N2>;
-  using SA = typename P::SA;
-  using SB = typename P::SB;
-  using C0 = ColIn<0, N2, N2, N2>;
-  using C1 = ColIn<1, N2, N2, N>;
-  using C2 = ColIn<2, N2, N, N>;
-  extern __shared__ __align__(128) double dsm[];
-  double* sin = dsm;                                   // [2][NIN][NP2]
-  double* sa = dsm + P::in_doubles;                    // [9][SA::size]
-  double* sb = sa + 9 * SA::size;                      // [6][SB::size]
-  double* sq = sb;                                     // [9][S2::size] products, dead before the s stage writes sb
-  static_assert(9 * S2::size <= 6 * SB::size, "sq alias");
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sb + 6 * SB::size);
-  const int tid = threadIdx.x;
-  if (cgs->done) return;
-  const double beta = cgs->beta;
-  if (tid == 0) {
-    mbar_init(&bar[0], 1);
-    mbar_init(&bar[1], 1);
-    mbar_fence_init();
-  }
-  __syncthreads();
-  auto issue = [&](int e, int st) {
-    double* dst = sin + st * NIN * NP2;
-    const long long e2 = (long long)e * NP2;
-    mbar_expect_tx(&bar[st], NIN * NP2 * (uint32_t)sizeof(double));
-#pragma unroll
-    for (int g = 0; g < 9; ++g) tma_bulk_g2s(dst + g * NP2, RW2 + (long long)g * n2 + e2, NP2 * sizeof(double), &bar[st]);
-    tma_bulk_g2s(dst + 9 * NP2, r + e2, NP2 * sizeof(double), &bar[st]);
-    tma_bulk_g2s(dst + 10 * NP2, dinvE + e2, NP2 * sizeof(double), &bar[st]);
-    tma_bulk_g2s(dst + 11 * NP2, pdir + e2, NP2 * sizeof(double), &bar[st]);
-  };
-  if (tid == 0 && (int)blockIdx.x < nel) issue(blockIdx.x, 0);
-  int it = 0;
-  for (int e = blockIdx.x; e < nel; e += gridDim.x, ++it) {
-    const int st = it & 1;
-    if (tid == 0 && e + (int)gridDim.x < nel) issue(e + gridDim.x, st ^ 1);
-    mbar_wait(&bar[st], (it >> 1) & 1);
-    gradt3_element<N>(sin + st * NIN * NP2, sq, sa, sb, w, pdir, beta, n, e, tid);
-  }
-}
-
-template <int N>
 struct DivP {
   static constexpr int N2 = N - 2, NP1 = N * N * N, NP2 = N2 * N2 * N2;
   using SA = Shp<N2, N, N>;
@@ -526,7 +362,9 @@ struct DivP {
   static constexpr size_t smem = sizeof(double) * (2 * stage + 6 * SA::size + 9 * SB::size) + 2 * sizeof(uint64_t);
 };
 
-// One element of k_div3p (not inlined, see gradt3_element).  Returns this thread's contribution to sum pdir*Ep.
+// One element of k_div3p.  Deliberately NOT inlined: inside the persistent element loop the compiler would treat the constant-bank
+// operator matrices as loop invariants and hoist them into registers (80+ registers and spills, measured).  Returns this thread's
+// contribution to sum pdir*Ep.
 template <int N>
 __device__ __noinline__ double div3_element(const double* __restrict__ in, double* __restrict__ sa, double* __restrict__ sbuf,
                                             double* __restrict__ qout, int e, int tid) {
@@ -968,7 +806,7 @@ __device__ __forceinline__ void ax3p_issue_g(const AxPArgs* A, double* stg, uint
 }
 
 // One element (not inlined: inside the element loop nvcc would hoist the constant-bank operator matrices into registers, see
-// gradt3_element).  actmask: bit f = component f still iterating.
+// div3_element).  actmask: bit f = component f still iterating.
 template <int N>
 __device__ __noinline__ Rho3 ax3p_element(const AxPArgs* __restrict__ A, double* __restrict__ stg, double* __restrict__ su,
                                           double* __restrict__ sr, uint64_t* bar, int e, int e_next, uint32_t parity, int actmask,
@@ -1128,19 +966,11 @@ static int persistent_grid(Ctx* c) {
   return std::min(c->nel, 2 * sms);
 }
 int pk_pcg_dir_gradt(Ctx* c, int adj) {
-  // measured (r1c, cfg 5): persistent gradt 0.198 ms (2 CTAs/SM) vs 0.157 ms one-CTA-per-element (4 CTAs/SM) => opt-in only;
-  // the persistent div (0.191 vs 0.238 ms) is the default.
+  // measured (r1c, cfg 5): a persistent, TMA-pipelined gradt was slower (0.198 ms at 2 CTAs/SM vs 0.157 ms one CTA per element at
+  // 3-4 CTAs/SM) and was removed in r2; the div kernels are persistent.
   // With a separately applied preconditioner (pc_kind != 0) the kernels read z = M^-1 r in place of r and ones in place of 1/diag(E).
   const double* zsrc = c->pc_kind ? c->pz : c->pk[0];
   const double* zscale = c->pc_kind ? c->ones2 : c->dinvE[adj];
-  if (c->persistent_pcg && c->persistent_gradt) {
-    DISPATCH_N(c, NSB_TRY(set_smem(k_gradt3p<N>, GradtP<N>::smem));
-               k_gradt3p<N><<<persistent_grid(c), PK_TPB, GradtP<N>::smem, c->stream>>>(zsrc, c->wk[2], c->RW2, zscale,
-                                                                                       c->pk[2], c->cgs + 3, c->n, c->n2, c->nel));
-    nsb_count_launch();
-    NSB_CUDA(cudaGetLastError());
-    return 0;
-  }
   if (c->pc_kind == 1 && c->pcg_fused) {          // fused preconditioner: pz holds the element-block part, the coarse parts are added here
     const PMG& m = c->pmg[(adj && c->has_adj_masks) ? 1 : 0];
     DISPATCH_N(c, k_gradt3<N, 2><<<c->nel, PK_TPB, 0, c->stream>>>(c->pz, c->wk[2], c->RW2, nullptr, c->pk[2], c->cgs + 3, c->n, c->n2,
@@ -1172,8 +1002,8 @@ static int set_smem(K kernel, size_t bytes) {
 }
 
 int pk_div(Ctx* c, const double* u, const double* s0, const double* s1, const double* s2, double* q, double sign) {
-  DISPATCH_N(c, NSB_TRY(set_smem(k_div3<N, 0, 0>, div3_smem<N>())); k_div3<N, 0, 0><<<c->nel, PK_TPB, div3_smem<N>(), c->stream>>>(u, s0, s1, s2, q, c->RW2, nullptr, nullptr, nullptr, nullptr,
-                                                               nullptr, 0, c->n, c->n2, sign, nullptr, 0, nullptr, nullptr));
+  DISPATCH_N(c, NSB_TRY(set_smem(k_div3<N, 0>, div3_smem<N>())); k_div3<N, 0><<<c->nel, PK_TPB, div3_smem<N>(), c->stream>>>(u, s0, s1, s2, q, c->RW2, nullptr, nullptr, nullptr, nullptr,
+                                                               nullptr, 0, c->n, c->n2, sign));
   nsb_count_launch();
   NSB_CUDA(cudaGetLastError());
   return 0;
@@ -1182,7 +1012,6 @@ int pk_pcg_div(Ctx* c, int adj, int fused) {
   const double* s0 = c->mbinv[adj][0];
   const double* s1 = c->mask_same[adj] ? nullptr : c->mbinv[adj][1];
   const double* s2 = c->mask_same[adj] ? nullptr : c->mbinv[adj][2];
-  const GSMap& m = c->gs;
   static const bool divq = [] { const char* e = getenv("NSB_DIVQ"); return !(e && e[0] == '0'); }();
   if (c->persistent_pcg && !fused && c->mask_same[adj] && divq) {      // single staging buffer with early refill, 3 CTAs per SM
     int sms = 148;
@@ -1204,15 +1033,9 @@ int pk_pcg_div(Ctx* c, int adj, int fused) {
     NSB_CUDA(cudaGetLastError());
     return 0;
   }
-  if (fused) {
-    DISPATCH_N(c, NSB_TRY(set_smem(k_div3<N, 1, 1>, div3_smem<N>())); k_div3<N, 1, 1><<<c->nel, PK_TPB, div3_smem<N>(), c->stream>>>(c->wk[2], s0, s1, s2, c->pk[3], c->RW2, c->pk[2], c->cgs + 3,
-                                                                 c->red_part, c->red_count, c->red_out, c->nranks == 1, c->n,
-                                                                 c->n2, 1.0, m.surf_pts, m.ns, m.nb_off, m.nb_idx));
-  } else {
-    DISPATCH_N(c, NSB_TRY(set_smem(k_div3<N, 1, 0>, div3_smem<N>())); k_div3<N, 1, 0><<<c->nel, PK_TPB, div3_smem<N>(), c->stream>>>(c->wk[2], s0, s1, s2, c->pk[3], c->RW2, c->pk[2], c->cgs + 3,
-                                                                 c->red_part, c->red_count, c->red_out, c->nranks == 1, c->n,
-                                                                 c->n2, 1.0, nullptr, 0, nullptr, nullptr));
-  }
+  DISPATCH_N(c, NSB_TRY(set_smem(k_div3<N, 1>, div3_smem<N>())); k_div3<N, 1><<<c->nel, PK_TPB, div3_smem<N>(), c->stream>>>(c->wk[2], s0, s1, s2, c->pk[3], c->RW2, c->pk[2], c->cgs + 3,
+                                                               c->red_part, c->red_count, c->red_out, c->nranks == 1, c->n,
+                                                               c->n2, 1.0));
   nsb_count_launch();
   NSB_CUDA(cudaGetLastError());
   return 0;

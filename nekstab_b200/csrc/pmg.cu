@@ -204,108 +204,8 @@ __global__ void k_pm_prolong(const double* __restrict__ xv, const int* __restric
 }
 
 // z_e = FDM_e(r_e) + sum_k phi_k xv[vid[e][k]] + x2[agg[e]];  rtz = sum z r  (deterministic two-stage reduction).
-// One warp per element, 8 elements per CTA; tensor stages are warp-synchronous on two shared buffers per warp.
 // mode 0: no CG bookkeeping (operator test); 1: single rank -> the last CTA sets rtz1/beta; 2: multi rank (sum only).
-template <int D, int L>
-__global__ void __launch_bounds__(256) k_pm_apply(const double* __restrict__ r, double* __restrict__ z, int nel,
-                                                  const double* __restrict__ Sg, const double* __restrict__ lamg,
-                                                  const double* __restrict__ xv, const int* __restrict__ vid,
-                                                  const double* __restrict__ x2, const int* __restrict__ agg, CGState* cgs,
-                                                  int mode, double* part, unsigned* counter, double* out) {
-  using S = PmShape<D, L>;
-  constexpr int NP = S::NP, NK = S::NK, NPL = S::NPL, LL = L * L;
-  if (mode && cgs->done) return;
-  __shared__ double sA[8][NP], sB[8][NP], sS[8][D * LL], sL[8][D * L];
-  __shared__ double sred[32];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int e = blockIdx.x * 8 + w;
-  double dot[1] = {0.0};
-  if (e < nel) {
-    double rr[NPL];
-#pragma unroll
-    for (int q = 0; q < NPL; ++q) {
-      const int p = lane + 32 * q;
-      rr[q] = (p < NP) ? r[(long long)e * NP + p] : 0.0;
-      if (p < NP) sA[w][p] = rr[q];
-    }
-    for (int i = lane; i < D * LL; i += 32) sS[w][i] = Sg[(long long)e * D * LL + i];
-    if (lane < D * L) sL[w][lane] = lamg[(long long)e * D * L + lane];
-    __syncwarp();
-    double mx = 0.0;
-#pragma unroll
-    for (int d = 0; d < D; ++d) {
-      double m = sL[w][d * L];
-#pragma unroll
-      for (int i = 1; i < L; ++i) m = fmax(m, sL[w][d * L + i]);
-      mx += m;
-    }
-    // forward: t(.., i_d, ..) = sum_a S_d[a][i_d] t(.., a, ..)
-    double* in = sA[w];
-    double* ou = sB[w];
-#pragma unroll
-    for (int d = 0; d < D; ++d) {
-      const int str = (d == 0) ? 1 : (d == 1 ? L : LL);
-#pragma unroll
-      for (int q = 0; q < NPL; ++q) {
-        const int p = lane + 32 * q;
-        if (p < NP) {
-          const int id = (p / str) % L, base = p - id * str;
-          double s = 0.0;
-#pragma unroll
-          for (int a = 0; a < L; ++a) s = fma(sS[w][d * LL + a * L + id], in[base + a * str], s);
-          if (d == D - 1) {
-            const int i0 = p % L, i1 = (p / L) % L;
-            double den = sL[w][i0] + sL[w][L + i1];
-            if (D == 3) den += sL[w][2 * L + p / LL];
-            s = (den > 1e-12 * mx) ? s / den : 0.0;
-          }
-          ou[p] = s;
-        }
-      }
-      __syncwarp();
-      double* tmp = in; in = ou; ou = tmp;
-    }
-    // backward: t(.., a, ..) = sum_i S_d[a][i] t(.., i, ..)
-#pragma unroll
-    for (int d = 0; d < D; ++d) {
-      const int str = (d == 0) ? 1 : (d == 1 ? L : LL);
-#pragma unroll
-      for (int q = 0; q < NPL; ++q) {
-        const int p = lane + 32 * q;
-        if (p < NP) {
-          const int ia = (p / str) % L, base = p - ia * str;
-          double s = 0.0;
-#pragma unroll
-          for (int i = 0; i < L; ++i) s = fma(sS[w][d * LL + ia * L + i], in[base + i * str], s);
-          ou[p] = s;
-        }
-      }
-      __syncwarp();
-      double* tmp = in; in = ou; ou = tmp;
-    }
-    const double c2 = x2 ? x2[agg[e]] : 0.0;
-    double xk[NK];
-#pragma unroll
-    for (int k = 0; k < NK; ++k) xk[k] = xv ? xv[vid[e * NK + k]] : 0.0;
-#pragma unroll
-    for (int q = 0; q < NPL; ++q) {
-      const int p = lane + 32 * q;
-      if (p < NP) {
-        double v = in[p] + c2;
-#pragma unroll
-        for (int k = 0; k < NK; ++k) v = fma(pm_phi<D, L>(k, p), xk[k], v);
-        z[(long long)e * NP + p] = v;
-        dot[0] = fma(v, rr[q], dot[0]);
-      }
-    }
-  }
-  if (grid_sum_finish<1>(dot, part, counter, out, sred) && mode == 1 && threadIdx.x == 0) {
-    cgs->rtz1 = out[0];
-    cgs->beta = (cgs->iter == 0) ? 0.0 : out[0] / cgs->rtz2;
-  }
-}
-
-// Second-generation element-block kernel (default): the CTA holds EPB elements in shared memory and every thread owns one
+// Element-block kernel: the CTA holds EPB elements in shared memory and every thread owns one
 // COLUMN of one element per tensor stage (L loads, L*L DFMAs against rows of the element's S read as 128-bit broadcasts,
 // L stores) -- ncu on the first generation (one warp per element, one point per lane and stage) showed the shared-memory
 // pipe as the limiter (12 LDS per 6 DFMA) and the Q1 hat functions served from the constant bank with lane-varying indices.
@@ -1253,8 +1153,6 @@ static int pm_download(Ctx* c, std::vector<double>& h, const double* d, long lon
 void pm_free(PMG& m) {
   cudaFree(m.S); cudaFree(m.lam); cudaFree(m.vid); cudaFree(m.voff); cudaFree(m.vent); cudaFree(m.d1inv); cudaFree(m.agg);
   cudaFree(m.aoff); cudaFree(m.aent); cudaFree(m.A2inv); cudaFree(m.rc); cudaFree(m.rc0); cudaFree(m.xc); cudaFree(m.hat); cudaFree(m.xv); cudaFree(m.ra); cudaFree(m.x2);
-  cudaFree(m.vc_off); cudaFree(m.vc_col); cudaFree(m.vc_val); cudaFree(m.vc_odinv); cudaFree(m.vc_vagg); cudaFree(m.vc_aoff);
-  cudaFree(m.vc_aent); cudaFree(m.vc_A2inv); cudaFree(m.vc_rv); cudaFree(m.vc_x); cudaFree(m.vc_r1);
   m = PMG();
 }
 
@@ -1300,62 +1198,6 @@ static int pm_apply_E(Ctx* c, int set, const double* pin, double* pout) {
   return 0;
 }
 
-// ---------------------------------------------------------------------------------------------- EXPERIMENTAL: Q1 V-cycle
-// (kind 2; single rank; compiled but NOT yet validated on a GPU -- CPU prototype and measured gain: oracle/pmg.py q1_cycle,
-// tools/precond_study5.py).  The Q1 level becomes  x = V(rv):  x = w D^-1 rv;  r1 = rv - A_c x;
-// x += P2 (P2^T A_c P2)^-1 P2^T r1;  x += w D^-1 (rv - A_c x)  with A_c = P^T E P assembled at set-up by distance-4 probing.
-__global__ void k_vc_pre(int nv, const int* __restrict__ voff, const int* __restrict__ vent, const double* __restrict__ rc,
-                         const double* __restrict__ odinv, double* __restrict__ rv, double* __restrict__ x, const CGState* skip) {
-  if (skip && skip->done) return;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= nv) return;
-  double s = 0.0;
-  for (int j = voff[t]; j < voff[t + 1]; ++j) s += rc[vent[j]];
-  rv[t] = s;
-  x[t] = odinv[t] * s;
-}
-// out[t] = base[t] + scale[t] * (rv[t] - sum_j A[t][j] x[j]);  scale == nullptr: out = rv - A x
-__global__ void k_vc_spmv(int nv, const int* __restrict__ off, const int* __restrict__ col, const double* __restrict__ val,
-                          const double* __restrict__ rv, const double* __restrict__ x, const double* __restrict__ scale,
-                          const double* __restrict__ base, double* __restrict__ out, const CGState* skip) {
-  if (skip && skip->done) return;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= nv) return;
-  double s = rv[t];
-  for (int j = off[t]; j < off[t + 1]; ++j) s -= val[j] * x[col[j]];
-  out[t] = scale ? base[t] + scale[t] * s : s;
-}
-// one warp per aggregate: ra[a] = sum of r1 over the aggregate's vertices (fixed tree)
-__global__ void k_vc_aggsum(int nagg, const int* __restrict__ aoff, const int* __restrict__ aent, const double* __restrict__ r1,
-                            double* __restrict__ ra, const CGState* skip) {
-  if (skip && skip->done) return;
-  const int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (a >= nagg) return;
-  double s = 0.0;
-  for (int j = aoff[a] + lane; j < aoff[a + 1]; j += 32) s += r1[aent[j]];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-  if (lane == 0) ra[a] = s;
-}
-__global__ void k_vc_addagg(int nv, const int* __restrict__ vagg, const double* __restrict__ x2, double* __restrict__ x,
-                            const CGState* skip) {
-  if (skip && skip->done) return;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < nv) x[t] += x2[vagg[t]];
-}
-static int pm_vcycle(Ctx* c, PMG& m, const CGState* skip) {
-  const int T = 128, nb = (m.nv + T - 1) / T;
-  k_vc_pre<<<nb, T, 0, c->stream>>>(m.nv, m.voff, m.vent, m.rc, m.vc_odinv, m.vc_rv, m.vc_x, skip);
-  k_vc_spmv<<<nb, T, 0, c->stream>>>(m.nv, m.vc_off, m.vc_col, m.vc_val, m.vc_rv, m.vc_x, nullptr, nullptr, m.vc_r1, skip);
-  k_vc_aggsum<<<(m.nagg * 32 + T - 1) / T, T, 0, c->stream>>>(m.nagg, m.vc_aoff, m.vc_aent, m.vc_r1, m.ra, skip);
-  k_pm_gemv<<<(m.nagg * 32 + T - 1) / T, T, 0, c->stream>>>(m.nagg, m.vc_A2inv, m.ra, m.x2, skip);
-  k_vc_addagg<<<nb, T, 0, c->stream>>>(m.nv, m.vc_vagg, m.x2, m.vc_x, skip);
-  k_vc_spmv<<<nb, T, 0, c->stream>>>(m.nv, m.vc_off, m.vc_col, m.vc_val, m.vc_rv, m.vc_x, m.vc_odinv, m.vc_x, m.xv, skip);
-  nsb_count_launch(6);
-  NSB_CUDA(cudaGetLastError());
-  return 0;
-}
-
 // z = M^-1 r.  mode 0: plain operator; 1: inside the pressure CG (skips when converged, updates rtz1/beta)
 int pm_apply(Ctx* c, int set, const double* r, double* z, int mode, int prof_slot) {
   PMG& m = c->pmg[(set && c->has_adj_masks) ? 1 : 0];      // without separate adjoint masks both problems share one E
@@ -1373,25 +1215,13 @@ int pm_apply(Ctx* c, int set, const double* r, double* z, int mode, int prof_slo
   const CGState* skip = mode ? sp : nullptr;
   NSB_TRY(pm_restrict(c, m, r, skip));
   if (prof_slot > 0) cudaEventRecord(c->prof_ev[prof_slot], c->stream);
-  const bool vcyc = c->pc_kind == 2 && m.vc_ready;          // experimental Q1 V-cycle (single rank)
-  if (vcyc) {
-    NSB_TRY(pm_vcycle(c, m, skip));
-  } else {
-    NSB_TRY(pm_coarse_levels(c, m, m.d1inv, skip));
-    if (c->nranks > 1) NSB_TRY(vk_allreduce_sum(c, m.ra, m.nagg));
-    NSB_TRY(pm_gemv(c, m, skip));
-  }
+  NSB_TRY(pm_coarse_levels(c, m, m.d1inv, skip));
+  if (c->nranks > 1) NSB_TRY(vk_allreduce_sum(c, m.ra, m.nagg));
+  NSB_TRY(pm_gemv(c, m, skip));
   if (prof_slot > 0) cudaEventRecord(c->prof_ev[prof_slot + 1], c->stream);
   const int kmode = mode ? (c->nranks == 1 ? 1 : 2) : 0;
-  static const int gen = [] { const char* e = getenv("NSB_PM_APPLY"); return (e && e[0] == '1') ? 1 : 2; }();
-  if (gen == 1) {
-    PM_DISPATCH(c, (k_pm_apply<D, L><<<(c->nel + 7) / 8, 256, 0, c->stream>>>(r, z, c->nel, m.S, m.lam, m.xv, m.vid, m.x2, m.agg, sp,
-                                                                             kmode, c->red_part, c->red_count, c->red_out)));
-  } else {
-    const double* x2p = vcyc ? nullptr : m.x2;              // the V-cycle has its aggregate level inside
-    PM_DISPATCH(c, (k_pm_apply2<D, L><<<(c->nel + Pm2<D, L>::EPB - 1) / Pm2<D, L>::EPB, Pm2<D, L>::NT, 0, c->stream>>>(
-                       r, z, c->nel, m.S, m.lam, m.xv, m.vid, x2p, m.agg, sp, kmode, c->red_part, c->red_count, c->red_out)));
-  }
+  PM_DISPATCH(c, (k_pm_apply2<D, L><<<(c->nel + Pm2<D, L>::EPB - 1) / Pm2<D, L>::EPB, Pm2<D, L>::NT, 0, c->stream>>>(
+                     r, z, c->nel, m.S, m.lam, m.xv, m.vid, m.x2, m.agg, sp, kmode, c->red_part, c->red_count, c->red_out)));
   if (mode && c->nranks > 1) NSB_TRY(vk_cg_finalize_multi(c, sp, 1, 5));
   return 0;
 }
@@ -1483,7 +1313,7 @@ int pm_setup(Ctx* c, int set, int nagg_req) {
   const int D = c->ldim, L1 = c->lx1, L2 = c->lx2, nel = c->nel, np1 = c->np1, NK = (D == 3) ? 8 : 4;
   const int N = L1 - 1, mid = L1 / 2;
   if (c->nranks > 1 && !c->gsv_ready) {    // gather-scatter over the element-vertex mesh: entries (e, corner), 2^ldim per element
-    NSB_TRY(gs_build(c, c->gsv, c->p2pv, (long long)nel * NK, 2, NK, c->vglo.data(), false));
+    NSB_TRY(gs_build(c, c->gsv, c->p2pv, (long long)nel * NK, 2, NK, c->vglo.data()));
     c->gsv_ready = true;
   }
   if (c->vglo.size() != (size_t)nel * NK) { nsb_set_error("pmg: vertex ids missing"); return 1; }
@@ -1676,115 +1506,5 @@ int pm_setup(Ctx* c, int set, int nagg_req) {
   NSB_TRY(pm_upload(&m.A2inv, A2));
   NSB_CUDA(cudaStreamSynchronize(c->stream));
   m.ready = true;
-  return 0;
-}
-
-// EXPERIMENTAL set-up of the Q1 V-cycle (see pm_vcycle): needs pm_setup(c, set, ..) first.  Single rank only.
-int pm_setup_vcycle(Ctx* c, int set) {
-  PMG& m = c->pmg[set];
-  if (!m.ready) { nsb_set_error("pmg: pm_setup must run before pm_setup_vcycle"); return 1; }
-  if (c->nranks > 1) { nsb_set_error("pmg: the Q1 V-cycle (kind 2) is single-rank only"); return 1; }
-  const int NK = (c->ldim == 3) ? 8 : 4, nel = c->nel, nv = m.nv;
-  const double omega = 0.7;
-  std::vector<int> vid((size_t)nel * NK);
-  NSB_CUDA(cudaMemcpy(vid.data(), m.vid, vid.size() * sizeof(int), cudaMemcpyDeviceToHost));
-  // neighbourhoods: adj = share an element; n2 = graph distance <= 2 (the support of a column of A_c)
-  std::vector<std::vector<int>> adj(nv), n2(nv);
-  for (int e = 0; e < nel; ++e)
-    for (int a = 0; a < NK; ++a)
-      for (int b = 0; b < NK; ++b) adj[vid[(size_t)e * NK + a]].push_back(vid[(size_t)e * NK + b]);
-  for (auto& l : adj) { std::sort(l.begin(), l.end()); l.erase(std::unique(l.begin(), l.end()), l.end()); }
-  for (int v = 0; v < nv; ++v) {
-    for (int u : adj[v]) n2[v].insert(n2[v].end(), adj[u].begin(), adj[u].end());
-    std::sort(n2[v].begin(), n2[v].end());
-    n2[v].erase(std::unique(n2[v].begin(), n2[v].end()), n2[v].end());
-  }
-  // distance-4 colouring: columns probed together must not overlap
-  std::vector<int> col(nv, -1), stamp;
-  int ncol = 0;
-  for (int v = 0; v < nv; ++v) {
-    stamp.assign(ncol + 1, 0);
-    for (int u : n2[v])
-      for (int t : n2[u])
-        if (col[t] >= 0) stamp[col[t]] = 1;
-    int cc = 0;
-    while (cc < ncol && stamp[cc]) ++cc;
-    col[v] = cc;
-    if (cc == ncol) ++ncol;
-  }
-  m.vc_ncolours = ncol;
-  // CSR pattern = n2 (symmetric); values by probing
-  std::vector<int> off(nv + 1, 0);
-  for (int v = 0; v < nv; ++v) off[v + 1] = off[v] + (int)n2[v].size();
-  std::vector<int> cols(off[nv]);
-  std::vector<double> vals(off[nv], 0.0);
-  for (int v = 0; v < nv; ++v) std::copy(n2[v].begin(), n2[v].end(), cols.begin() + off[v]);
-  auto entry = [&](int row, int cidx) -> double& {
-    const int* b = cols.data() + off[row];
-    const int* e2 = cols.data() + off[row + 1];
-    return vals[std::lower_bound(b, e2, cidx) - cols.data()];
-  };
-  std::vector<double> xvh(nv), y;
-  for (int cc = 0; cc < ncol; ++cc) {
-    for (int v = 0; v < nv; ++v) xvh[v] = (col[v] == cc) ? 1.0 : 0.0;
-    NSB_CUDA(cudaMemcpyAsync(m.xv, xvh.data(), nv * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    NSB_TRY(pm_prolong(c, m, m.xv, nullptr, c->pk[2]));
-    NSB_TRY(pm_apply_E(c, set, c->pk[2], c->pk[3]));
-    NSB_TRY(pm_restrict(c, m, c->pk[3], nullptr));
-    NSB_TRY(pm_coarse(c, m, nullptr, 0, 0, nullptr));          // plain vertex sums into m.xv
-    NSB_TRY(pm_download(c, y, m.xv, nv));
-    for (int v = 0; v < nv; ++v)
-      if (col[v] == cc)
-        for (int w : n2[v]) entry(w, v) = y[w];                // column v of A_c
-  }
-  for (int i = 0; i < nv; ++i)                                 // symmetrise (the pattern is symmetric)
-    for (int j = off[i]; j < off[i + 1]; ++j)
-      if (cols[j] > i) {
-        double& t = entry(cols[j], i);
-        const double a = 0.5 * (vals[j] + t);
-        vals[j] = a; t = a;
-      }
-  std::vector<double> odinv(nv);
-  for (int i = 0; i < nv; ++i) {
-    const double d = entry(i, i);
-    if (!(d > 0)) { nsb_set_error("pmg: non-positive diagonal of P^T E P at vertex %d", i); return 1; }
-    odinv[i] = omega / d;
-  }
-  // vertex aggregates: the aggregate of the first element that holds the vertex
-  std::vector<int> vagg(nv, -1);
-  for (int e = 0; e < nel; ++e)
-    for (int k = 0; k < NK; ++k)
-      if (vagg[vid[(size_t)e * NK + k]] < 0) vagg[vid[(size_t)e * NK + k]] = m.h_agg[e];
-  const int na = m.nagg;
-  std::vector<int> aoff(na + 1, 0), aent(nv);
-  for (int v = 0; v < nv; ++v) aoff[vagg[v] + 1]++;
-  for (int a = 0; a < na; ++a) aoff[a + 1] += aoff[a];
-  {
-    std::vector<int> fill(aoff.begin(), aoff.end() - 1);
-    for (int v = 0; v < nv; ++v) aent[fill[vagg[v]]++] = v;
-  }
-  std::vector<double> A2((size_t)na * na, 0.0);
-  for (int i = 0; i < nv; ++i)
-    for (int j = off[i]; j < off[i + 1]; ++j) A2[(size_t)vagg[i] * na + vagg[cols[j]]] += vals[j];
-  if (c->ifvcor[set]) {
-    double tr = 0.0;
-    for (int a = 0; a < na; ++a) tr += A2[(size_t)a * na + a];
-    for (auto& v : A2) v += tr / ((double)na * na);
-  }
-  if (c->ifvcor[set] && na == 1) A2[0] = 0.0;
-  else if (!spd_inverse(na, A2)) { nsb_set_error("pmg: vertex-aggregate operator not positive definite"); return 1; }
-  NSB_TRY(pm_upload(&m.vc_off, off));
-  NSB_TRY(pm_upload(&m.vc_col, cols));
-  NSB_TRY(pm_upload(&m.vc_val, vals));
-  NSB_TRY(pm_upload(&m.vc_odinv, odinv));
-  NSB_TRY(pm_upload(&m.vc_vagg, vagg));
-  NSB_TRY(pm_upload(&m.vc_aoff, aoff));
-  NSB_TRY(pm_upload(&m.vc_aent, aent));
-  NSB_TRY(pm_upload(&m.vc_A2inv, A2));
-  NSB_TRY(pm_upload(&m.vc_rv, std::vector<double>(nv, 0.0)));
-  NSB_TRY(pm_upload(&m.vc_x, std::vector<double>(nv, 0.0)));
-  NSB_TRY(pm_upload(&m.vc_r1, std::vector<double>(nv, 0.0)));
-  NSB_CUDA(cudaStreamSynchronize(c->stream));
-  m.vc_ready = true;
   return 0;
 }

@@ -116,29 +116,38 @@ k_gradt3(const double* __restrict__ p, double* __restrict__ w, const double* __r
   const long long e1 = (long long)blockIdx.x * NP1;
   static_assert(NP2 <= TPB, "one mesh-2 point per thread");
   if (MODE == 2) {
-    // xc = the element's 8 corner values of the vertex level + its aggregate value (k_pm_corner_values): 9 doubles per element read by
-    // every thread as warp-uniform (broadcast) loads, no shared-memory staging and no extra barrier.  (First version: xv[vid[..]]
-    // gathered here through shared memory: two dependent, L2-evicted loads + a barrier on the critical path, 0.150 -> 0.183 ms.)
+    // xc = the element's 8 corner values of the vertex level + its aggregate value (k_pm_corner_values), one contiguous record per
+    // element.  Otherwise idle threads fetch it (and the hat-function table) into shared memory while the point threads have their
+    // 12 streaming loads in flight; one barrier, then the interpolation reads shared memory.  History (r2, cfg 5): gathering
+    // xv[vid[..]] here (two dependent, L2-evicted loads before the barrier) 0.183 ms; warp-uniform global loads of xc without a
+    // barrier 0.186 ms (24 loads per thread at a 56-register cap: the compiler split them into two dependent rounds); MODE 1: 0.150 ms.
+    __shared__ double sxc[11], sh1[8];
+    if (tid >= TPB - 9) sxc[tid - (TPB - 9)] = xv[(long long)blockIdx.x * 9 + (tid - (TPB - 9))];
+    else if (tid == TPB - 10) sxc[9] = cgs->beta;        // the CG scalars travel the same way: no global load behind the barrier
+    else if (tid == TPB - 11) sxc[10] = cgs->alpha;
+    else if (tid >= TPB - 32 && tid < TPB - 32 + N2) sh1[tid - (TPB - 32)] = x2[tid - (TPB - 32)];      // x2 = hat-function table
+    double zl = 0.0, pd = 0.0, xo = 0.0, m9[9];
+    if (tid < NP2) {
+      zl = p[e2 + tid];
+      pd = pdir[e2 + tid];
+      xo = xsol[e2 + tid];
+#pragma unroll
+      for (int g = 0; g < 9; ++g) m9[g] = RW2[(long long)g * n2 + e2 + tid];   // coalesced
+    }
+    __syncthreads();
     if (tid < NP2) {
       const int q = tid;
-      const double* xc = xv + (long long)blockIdx.x * 9;
       const int i0 = q % N2, i1 = (q / N2) % N2, i2 = q / (N2 * N2);
-      const double a0 = __ldg(&x2[i0]), a1 = __ldg(&x2[i1]), a2 = __ldg(&x2[i2]);      // x2 = hat-function table (device copy of cm.hat1)
-      const double zl = p[e2 + q], pd = pdir[e2 + q];
+      const double a0 = sh1[i0], a1 = sh1[i1], a2 = sh1[i2];
+      const double c0 = fma(sxc[1] - sxc[0], a0, sxc[0]), c1 = fma(sxc[3] - sxc[2], a0, sxc[2]);
+      const double d0 = fma(sxc[5] - sxc[4], a0, sxc[4]), d1 = fma(sxc[7] - sxc[6], a0, sxc[6]);
+      const double q0 = fma(c1 - c0, a1, c0), q1 = fma(d1 - d0, a1, d0);
+      const double z = (zl + fma(q1 - q0, a2, q0)) + sxc[8];
+      const double v = fma(sxc[9], pd, z);
+      pdir[e2 + q] = v;
       // the solution update of the PREVIOUS iteration rides along here (pd = p_k is in a register anyway): x_{k+1} = x_k + alpha_k p_k;
       // the update of the last iteration is applied by k_pcg_xfix after the loop (this kernel is skipped once converged)
-      xsol[e2 + q] = fma(cgs->alpha, pd, xsol[e2 + q]);
-      double m9[9];
-#pragma unroll
-      for (int g = 0; g < 9; ++g) m9[g] = RW2[(long long)g * n2 + e2 + q];   // coalesced
-      const double x0 = __ldg(&xc[0]), x1 = __ldg(&xc[1]), x2v = __ldg(&xc[2]), x3 = __ldg(&xc[3]);
-      const double x4 = __ldg(&xc[4]), x5 = __ldg(&xc[5]), x6 = __ldg(&xc[6]), x7 = __ldg(&xc[7]), x8 = __ldg(&xc[8]);
-      const double c0 = fma(x1 - x0, a0, x0), c1 = fma(x3 - x2v, a0, x2v);
-      const double d0 = fma(x5 - x4, a0, x4), d1 = fma(x7 - x6, a0, x6);
-      const double q0 = fma(c1 - c0, a1, c0), q1 = fma(d1 - d0, a1, d0);
-      const double z = (zl + fma(q1 - q0, a2, q0)) + x8;
-      const double v = fma(cgs->beta, pd, z);
-      pdir[e2 + q] = v;
+      xsol[e2 + q] = fma(sxc[10], pd, xo);
       const int o = S2::lin(q);
 #pragma unroll
       for (int g = 0; g < 9; ++g) sq[g * S2::size + o] = m9[g] * v;

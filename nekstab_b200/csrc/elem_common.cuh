@@ -99,6 +99,44 @@ __device__ __forceinline__ void contract(const double* __restrict__ in, double* 
   }
 }
 
+// "Surface-first" layout of one element's N^3 points (3-D): the 6 N^2 - 12 N + 8 surface points first -- plane k = 0, plane k = N-1,
+// then for every interior plane its ring (row j = 0, row j = N-1, then the (i = 0, i = N-1) pairs of the interior rows) -- followed by
+// the (N-2)^3 interior points.  The direct-stiffness sum only touches surface points: in the natural layout the i = 0 / i = N-1 points
+// of interior rows sit alone in their 32-byte sectors (r1d ncu: k_gs_sum moved 1.53 x its algorithmic bytes); here the surface block is
+// contiguous.  Used for the vector that travels  producer kernel -> dssum -> consumer kernel  inside the two CG loops.
+template <int N>
+struct SurfFirst {
+  static constexpr int NS = N * N * N - (N - 2) * (N - 2) * (N - 2);
+  static constexpr int B = 4 * N - 4;
+  __host__ __device__ static constexpr int ring(int j, int i) {
+    return j == 0 ? i : (j == N - 1 ? N + i : 2 * N + 2 * (j - 1) + (i == N - 1 ? 1 : 0));
+  }
+  __host__ __device__ static constexpr bool surf_col(int j, int i) { return j == 0 || j == N - 1 || i == 0 || i == N - 1; }
+  // position of point (k, j, i)
+  __host__ __device__ static constexpr int pos(int k, int j, int i) {
+    return k == 0 ? j * N + i
+                  : (k == N - 1 ? N * N + j * N + i
+                                : (surf_col(j, i) ? 2 * N * N + (k - 1) * B + ring(j, i)
+                                                  : NS + ((k - 1) * (N - 2) + (j - 1)) * (N - 2) + (i - 1)));
+  }
+  __host__ __device__ static constexpr int pos_lin(int q) { return pos(q / (N * N), (q / N) % N, q % N); }
+  // a k-column (fixed j, i): first interior-plane position and the stride between interior planes
+  __host__ __device__ static constexpr int mid0(int j, int i) {
+    return surf_col(j, i) ? 2 * N * N + ring(j, i) : NS + (j - 1) * (N - 2) + (i - 1);
+  }
+  __host__ __device__ static constexpr int mids(int j, int i) { return surf_col(j, i) ? B : (N - 2) * (N - 2); }
+};
+// run-time N (host set-up, streaming kernels)
+__host__ __device__ inline int surf_first_pos(int N, int q) {
+  const int i = q % N, j = (q / N) % N, k = q / (N * N);
+  const int NS = N * N * N - (N - 2) * (N - 2) * (N - 2), B = 4 * N - 4;
+  if (k == 0) return j * N + i;
+  if (k == N - 1) return N * N + j * N + i;
+  const bool sc = j == 0 || j == N - 1 || i == 0 || i == N - 1;
+  if (sc) return 2 * N * N + (k - 1) * B + (j == 0 ? i : (j == N - 1 ? N + i : 2 * N + 2 * (j - 1) + (i == N - 1 ? 1 : 0)));
+  return NS + ((k - 1) * (N - 2) + (j - 1)) * (N - 2) + (i - 1);
+}
+
 // deterministic block reduction of NV values (sum); result in thread 0 (all threads must call)
 template <int NV>
 __device__ __forceinline__ void block_sum(double (&v)[NV], double* sred /* >= NV*32 doubles */) {

@@ -11,7 +11,7 @@
 #include <algorithm>
 #include <numeric>
 
-#include "nsb_internal.h"
+#include "elem_common.cuh"
 
 
 template <int NF>
@@ -99,6 +99,7 @@ int gs_free_map(Ctx* c, GSMap& m, P2P& p) {
 }
 int gs_free(Ctx* c) {
   gs_free_map(c, c->gsv, c->p2pv);
+  gs_free_map(c, c->gsp, c->p2pp);
   return gs_free_map(c, c->gs, c->p2p);
 }
 
@@ -132,11 +133,14 @@ static void plan_sort(HostPlan& P, long long n, const long long* glo) {
 }
 
 // ids of this rank's element-surface nodes (ascending): the only nodes another rank can share
-static void plan_candidates(const HostPlan& P, int N, int D, int np, std::vector<long long>& cand) {
+static void plan_candidates(const HostPlan& P, int N, int D, int np, std::vector<long long>& cand, int surf_first = 0) {
   cand.clear();
   const int nu = (int)P.uid.size();
-  for (int k = 0; k < nu; ++k)
-    if (is_surface(P.order[P.ustart[k]] % np, N, D)) cand.push_back(P.uid[k]);
+  const int ns = np - ((D == 3) ? (N - 2) * (N - 2) * (N - 2) : (N - 2) * (N - 2));
+  for (int k = 0; k < nu; ++k) {
+    const int q = P.order[P.ustart[k]] % np;
+    if (surf_first ? (q < ns) : is_surface(q, N, D)) cand.push_back(P.uid[k]);      // surface-first layout: the surface block leads
+  }
 }
 
 // counts[r], ids (concatenated, each rank's list ascending) = every rank's candidate list
@@ -243,18 +247,36 @@ extern "C" int nsb_gs_host_get(int which, int* out) {
   return 0;
 }
 
-int gs_setup(Ctx* c, const long long* glo) { return gs_build(c, c->gs, c->p2p, c->n, c->lx1, c->np1, glo); }
+int gs_setup(Ctx* c, const long long* glo) {
+  NSB_TRY(gs_build(c, c->gs, c->p2p, c->n, c->lx1, c->np1, glo));
+  const char* env = getenv("NSB_PERM");
+  if (c->ldim == 3 && !(env && env[0] == '0')) {
+    // second map for loop vectors kept in the surface-first element layout: same nodes, permuted local positions
+    std::vector<long long> gp((size_t)c->n);
+    std::vector<int> perm(c->np1);
+    for (int q = 0; q < c->np1; ++q) perm[q] = surf_first_pos(c->lx1, q);
+    for (int e = 0; e < c->nel; ++e)
+      for (int q = 0; q < c->np1; ++q) gp[(size_t)e * c->np1 + perm[q]] = glo[(size_t)e * c->np1 + q];
+    NSB_TRY(gs_build(c, c->gsp, c->p2pp, c->n, c->lx1, c->np1, gp.data(), 1));
+    c->gsp_ready = true;
+  }
+  return 0;
+}
+int gs_dssum_w(Ctx* c, double* w, int nfields, bool permuted, const CGState* skip) {
+  if (permuted) return gs_dssum_map(c, c->gsp, c->p2pp, w, nfields, c->n, skip);
+  return gs_dssum_map(c, c->gs, c->p2p, w, nfields, c->n, skip);
+}
 
 // Build a gather-scatter map over `n` local dofs with global ids `glo` (np dofs per element on an N^ldim grid): the
 // velocity mesh (N = lx1) or the element-vertex mesh of the pressure preconditioner (N = 2).
-int gs_build(Ctx* c, GSMap& m, P2P& p2p, long long n, int N1, int np_e, const long long* glo) {
+int gs_build(Ctx* c, GSMap& m, P2P& p2p, long long n, int N1, int np_e, const long long* glo, int surf_first) {
   if (n >= (1LL << 31)) { nsb_set_error("gs_setup: more than 2^31 local dofs"); return 1; }
   HostPlan P;
   plan_sort(P, n, glo);
   std::vector<long long> cnts(c->nranks, 0), all;
   if (c->nranks > 1) {
     std::vector<long long> cand;
-    plan_candidates(P, N1, c->ldim, np_e, cand);
+    plan_candidates(P, N1, c->ldim, np_e, cand, surf_first);
     // allgather counts then ids (padded) through NCCL
     long long mycnt = (long long)cand.size();
     long long* d_cnt = nullptr;

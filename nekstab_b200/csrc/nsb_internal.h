@@ -158,6 +158,12 @@ struct Ctx {
   bool ifvcor[2] = {false, false};
   GSMap gs;
   P2P p2p;
+  GSMap gsp;                 // the velocity-mesh map again, for vectors stored in the surface-first element layout (elem_common.cuh)
+  P2P p2pp;
+  bool gsp_ready = false;
+  bool perm_p = false, perm_h = false;   // surface-first layout of w in the pressure / Helmholtz CG loop (3-D; NSB_PERM=0 disables)
+  bool ax_persistent = true, divq = true;   // NSB_AX_PERSISTENT / NSB_DIVQ (=0 selects the previous kernel generation)
+  double* mbinv_p[2] = {nullptr, nullptr};   // mask*binv in the surface-first layout (pressure loop, masks shared by the components)
   GSMap gsv;                 // gather-scatter over the element-vertex mesh (pressure preconditioner, multi-rank)
   P2P p2pv;                  // its own peer-memory halo channel
   bool gsv_ready = false;
@@ -238,6 +244,13 @@ struct Ctx {
 
 extern Ctx* g_ctx;
 inline double* slot_ptr(Ctx* c, int s) { return c->slab + (long long)s * c->vlen; }
+// the loop vector w of the pressure CG travels gradt -> dssum -> div in the surface-first element layout when every kernel on that
+// route supports it: fused three-level preconditioner (k_gradt3<N,2,1>), k_div3q, one mask set shared by the components
+inline bool perm_p_active(const Ctx* c, int adj) {
+  return c->perm_p && c->ldim == 3 && c->pc_kind == 1 && c->pcg_fused && c->persistent_pcg && c->divq && c->mask_same[adj] &&
+         c->mbinv_p[(adj && c->has_adj_masks) ? 1 : 0] != nullptr;
+}
+inline bool perm_h_active(const Ctx* c) { return c->perm_h && c->ldim == 3 && c->lx1 == 8 && c->ax_persistent; }
 
 // ---- host SEM (sem_host.cpp)
 void sem_zwgll(int n, double* z, double* w);
@@ -250,7 +263,9 @@ void sem_build_constmats(int lx1, int lx2, int lxd, ConstMats* cm);
 int gs_setup(Ctx* c, const long long* glo_num);
 int gs_free(Ctx* c);
 int gs_dssum(Ctx* c, double* u, int nfields, long long stride, const CGState* skip_if_done = nullptr);
-int gs_build(Ctx* c, GSMap& m, P2P& p2p, long long n, int N1, int np_e, const long long* glo);
+int gs_build(Ctx* c, GSMap& m, P2P& p2p, long long n, int N1, int np_e, const long long* glo, int surf_first = 0);
+int gs_dssum_w(Ctx* c, double* w, int nfields, bool permuted, const CGState* skip);   // dssum of a loop vector in natural / surface-first layout
+int vk_permute_surf_first(Ctx* c, double* dst, const double* src);                  // dst[e][pos(q)] = src[e][q]
 int gs_dssum_map(Ctx* c, GSMap& m, P2P& p2p, double* u, int nfields, long long stride, const CGState* skip_if_done);
 int gs_free_map(Ctx* c, GSMap& m, P2P& p);
 
@@ -306,7 +321,7 @@ int vk_press_extrap(Ctx* c, int k);
 int vk_final_update(Ctx* c, int adj, double h2);   // u = u + du + mbinv*w ; p = pt + h2*phi
 // CG pointwise pieces
 int vk_hcg_init(Ctx* c, int ncomp);
-int vk_hcg_update(Ctx* c, int ncomp, int adj);
+int vk_hcg_update(Ctx* c, int ncomp, int adj);   // reads w in the surface-first layout when perm_h_active(c)
 int vk_pcg_init(Ctx* c, int adj);
 int vk_pcg_update(Ctx* c, int adj);
 int vk_dinvH(Ctx* c, double h1, double h2);

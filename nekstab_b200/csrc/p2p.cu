@@ -402,7 +402,7 @@ int p2p_allreduce(Ctx* c, double* dev, int count, int op, CGState* cgs, int ncom
 }
 
 int p2p_check_error(Ctx* c) {
-  for (P2P* p : {&c->p2p, &c->p2pv}) {
+  for (P2P* p : {&c->p2p, &c->p2pv, &c->p2pp}) {
     if (!p->on) continue;
     int e[4] = {0, 0, 0, 0};
     NSB_CUDA(cudaMemcpy(e, p->d_err, sizeof(e), cudaMemcpyDeviceToHost));

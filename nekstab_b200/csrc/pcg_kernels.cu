@@ -91,7 +91,7 @@ __device__ __forceinline__ void apply2_store(const double* __restrict__ M1, cons
 // three-level preconditioner of pmg.cu in its fused form: `p` holds the element-block part zloc of z = M^-1 r (k_pcg_fused); the Q1
 // vertex-mesh part (trilinear interpolation of the element's 8 corner values) and the aggregate value are added here; in this mode the
 // argument `xv` is the per-element table xc[nel][9] (k_pm_corner_values) and `x2` the table of hat-function values at the GL points.
-template <int N, int MODE>
+template <int N, int MODE, int PERM>
 __global__ void __launch_bounds__(PK_TPB, 3)
 k_gradt3(const double* __restrict__ p, double* __restrict__ w, const double* __restrict__ RW2,
          const double* __restrict__ dinvE, double* __restrict__ pdir, const CGState* __restrict__ cgs, long long n,
@@ -210,7 +210,24 @@ k_gradt3(const double* __restrict__ p, double* __restrict__ w, const double* __r
     double v[N2], v2[N2];
 #pragma unroll
     for (int l = 0; l < N2; ++l) { v[l] = sb[c * 2][bi + l * C2::stride]; v2[l] = sb[c * 2 + 1][bi + l * C2::stride]; }
-    apply2_store<N, N2>(cm.J12t, v, cm.D12t, v2, w + (long long)c * n + e1 + col, N * N);
+    if (PERM) {
+      // surface-first element layout (elem_common.cuh SurfFirst): planes k = 0 and N-1 lead, then the rings, then the interior
+      using SF = SurfFirst<N>;
+      const int cj = col / N, ci = col - cj * N;
+      const int m0 = SF::mid0(cj, ci), ms = SF::mids(cj, ci);
+      double* po = w + (long long)c * n + e1;
+#pragma unroll
+      for (int a = 0; a < N; ++a) {
+        double sacc = 0.0;
+#pragma unroll
+        for (int l = 0; l < N2; ++l) sacc = fma(cm.J12t[a * N2 + l], v[l], sacc);
+#pragma unroll
+        for (int l = 0; l < N2; ++l) sacc = fma(cm.D12t[a * N2 + l], v2[l], sacc);
+        po[a == 0 ? col : (a == N - 1 ? N * N + col : m0 + (a - 1) * ms)] = sacc;
+      }
+    } else {
+      apply2_store<N, N2>(cm.J12t, v, cm.D12t, v2, w + (long long)c * n + e1 + col, N * N);
+    }
   }
 }
 
@@ -527,7 +544,7 @@ __device__ __forceinline__ void div3q_issue_b(const DivQArgs* A, double* stg, ui
   for (int g = 0; g < 9; ++g) tma_bulk_g2s(stg + 4 * NP1 + g * NP2, A->RW2 + (long long)g * A->n2 + e2, NP2 * sizeof(double), bar);
 }
 
-template <int N>
+template <int N, int PERM>
 __device__ __noinline__ double div3q_element(const DivQArgs* __restrict__ A, double* __restrict__ stg, double* __restrict__ sa,
                                              double* __restrict__ sbuf, uint64_t* bar, int e, int e_next, uint32_t parity, int tid) {
   using P = DivQ<N>;
@@ -545,8 +562,19 @@ __device__ __noinline__ double div3q_element(const DivQArgs* __restrict__ A, dou
   if (tid < 3 * C2::ncol) {
     const int c = tid / C2::ncol, col = tid - c * C2::ncol;
     double v[N];
+    if (PERM) {                                      // w and mask*binv arrive in the surface-first element layout
+      using SF = SurfFirst<N>;
+      const int cj = col / N, ci = col - cj * N;
+      const int m0 = SF::mid0(cj, ci), ms = SF::mids(cj, ci);
 #pragma unroll
-    for (int l = 0; l < N; ++l) v[l] = stg[c * NP1 + l * N * N + col] * inmb[l * N * N + col];
+      for (int l = 0; l < N; ++l) {
+        const int o = (l == 0) ? col : (l == N - 1 ? N * N + col : m0 + (l - 1) * ms);
+        v[l] = stg[c * NP1 + o] * inmb[o];
+      }
+    } else {
+#pragma unroll
+      for (int l = 0; l < N; ++l) v[l] = stg[c * NP1 + l * N * N + col] * inmb[l * N * N + col];
+    }
     apply_store<N2, N>(cm.J12, v, sa + (c * 2) * SA::size + C2::base(col), C2::stride);
     apply_store<N2, N>(cm.D12, v, sa + (c * 2 + 1) * SA::size + C2::base(col), C2::stride);
   }
@@ -591,7 +619,7 @@ __device__ __noinline__ double div3q_element(const DivQArgs* __restrict__ A, dou
   return rho;
 }
 
-template <int N>
+template <int N, int PERM>
 __global__ void __launch_bounds__(PK_TPB, 3)
 k_div3q(DivQArgs args, CGState* __restrict__ cgs, double* __restrict__ part, unsigned* counter, double* __restrict__ red_out,
         int finalize, int nel) {
@@ -623,7 +651,7 @@ k_div3q(DivQArgs args, CGState* __restrict__ cgs, double* __restrict__ part, uns
   int it = 0;
   for (int e = blockIdx.x; e < nel; e += gridDim.x, ++it) {
     const int en = (e + (int)gridDim.x < nel) ? e + (int)gridDim.x : -1;
-    rho[0] += div3q_element<N>(&sargs, stg, sa, sbuf, bar, e, en, (uint32_t)(it & 1), tid);
+    rho[0] += div3q_element<N, PERM>(&sargs, stg, sa, sbuf, bar, e, en, (uint32_t)(it & 1), tid);
   }
   if (grid_sum_finish<1>(rho, part, counter, red_out, sred) && finalize && tid == 0) {
     cgs->rho = red_out[0];
@@ -781,6 +809,7 @@ struct AxPArgs {
   double* pdir; double* w;
   long long n;
   double h1, h2;
+  int perm;                 // 1: w is written in the surface-first element layout (read back by k_hcg_update through the same map)
 };
 template <int N>
 struct AxP {
@@ -884,13 +913,14 @@ __device__ __noinline__ Rho3 ax3p_element(const AxPArgs* __restrict__ A, double*
   Rho3 rho = {0.0, 0.0, 0.0};
   if (tid < NP1) {
     const int o = S1::lin(tid);
+    const int wpos = A->perm ? SurfFirst<N>::pos_lin(tid) : tid;
     double rr[3] = {0.0, 0.0, 0.0};
 #pragma unroll
     for (int f = 0; f < 3; ++f)
       if (actmask & (1 << f)) {
         const double* p0 = sr + (f * 3) * S1::size + o;
         const double hv = A->h1 * ((p0[0] + p0[S1::size]) + p0[2 * S1::size]) + A->h2 * bm * uo[f];
-        A->w[(long long)f * A->n + e0 + tid] = hv;
+        A->w[(long long)f * A->n + e0 + wpos] = hv;
         rr[f] = uo[f] * hv;
       }
     rho.a = rr[0]; rho.b = rr[1]; rho.c = rr[2];
@@ -962,7 +992,7 @@ int pk_upload_constants(const ConstMats& h) {
   } while (0)
 
 int pk_gradt(Ctx* c, const double* p, double* w) {
-  DISPATCH_N(c, k_gradt3<N, 0><<<c->nel, PK_TPB, 0, c->stream>>>(p, w, c->RW2, nullptr, nullptr, nullptr, c->n, c->n2, nullptr, nullptr, nullptr, nullptr, nullptr));
+  DISPATCH_N(c, k_gradt3<N, 0, 0><<<c->nel, PK_TPB, 0, c->stream>>>(p, w, c->RW2, nullptr, nullptr, nullptr, c->n, c->n2, nullptr, nullptr, nullptr, nullptr, nullptr));
   nsb_count_launch();
   NSB_CUDA(cudaGetLastError());
   return 0;
@@ -982,13 +1012,18 @@ int pk_pcg_dir_gradt(Ctx* c, int adj) {
   const double* zscale = c->pc_kind ? c->ones2 : c->dinvE[adj];
   if (c->pc_kind == 1 && c->pcg_fused) {          // fused preconditioner: pz holds the element-block part, the coarse parts are added here
     const PMG& m = c->pmg[(adj && c->has_adj_masks) ? 1 : 0];
-    DISPATCH_N(c, k_gradt3<N, 2><<<c->nel, PK_TPB, 0, c->stream>>>(c->pz, c->wk[2], c->RW2, nullptr, c->pk[2], c->cgs + 3, c->n, c->n2,
-                                                                m.xc, nullptr, m.hat, nullptr, c->pk[1]));
+    if (perm_p_active(c, adj)) {
+      DISPATCH_N(c, k_gradt3<N, 2, 1><<<c->nel, PK_TPB, 0, c->stream>>>(c->pz, c->wk[2], c->RW2, nullptr, c->pk[2], c->cgs + 3, c->n, c->n2,
+                                                                     m.xc, nullptr, m.hat, nullptr, c->pk[1]));
+    } else {
+      DISPATCH_N(c, k_gradt3<N, 2, 0><<<c->nel, PK_TPB, 0, c->stream>>>(c->pz, c->wk[2], c->RW2, nullptr, c->pk[2], c->cgs + 3, c->n, c->n2,
+                                                                     m.xc, nullptr, m.hat, nullptr, c->pk[1]));
+    }
     nsb_count_launch();
     NSB_CUDA(cudaGetLastError());
     return 0;
   }
-  DISPATCH_N(c, k_gradt3<N, 1><<<c->nel, PK_TPB, 0, c->stream>>>(zsrc, c->wk[2], c->RW2, zscale, c->pk[2], c->cgs + 3,
+  DISPATCH_N(c, k_gradt3<N, 1, 0><<<c->nel, PK_TPB, 0, c->stream>>>(zsrc, c->wk[2], c->RW2, zscale, c->pk[2], c->cgs + 3,
                                                               c->n, c->n2, nullptr, nullptr, nullptr, nullptr, nullptr));
   nsb_count_launch();
   NSB_CUDA(cudaGetLastError());
@@ -1021,14 +1056,20 @@ int pk_pcg_div(Ctx* c, int adj, int fused) {
   const double* s0 = c->mbinv[adj][0];
   const double* s1 = c->mask_same[adj] ? nullptr : c->mbinv[adj][1];
   const double* s2 = c->mask_same[adj] ? nullptr : c->mbinv[adj][2];
-  static const bool divq = [] { const char* e = getenv("NSB_DIVQ"); return !(e && e[0] == '0'); }();
-  if (c->persistent_pcg && !fused && c->mask_same[adj] && divq) {      // single staging buffer with early refill, 3 CTAs per SM
+  if (c->persistent_pcg && !fused && c->mask_same[adj] && c->divq) {      // single staging buffer with early refill, 3 CTAs per SM
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-    DISPATCH_N(c, DivQArgs a{c->wk[2], s0, c->RW2, c->pk[2], c->pk[3], c->n, c->n2};
-               NSB_TRY(set_smem(k_div3q<N>, DivQ<N>::smem));
-               k_div3q<N><<<std::min(c->nel, 3 * sms), PK_TPB, DivQ<N>::smem, c->stream>>>(a, c->cgs + 3, c->red_part, c->red_count, c->red_out,
-                                                                                         c->nranks == 1, c->nel));
+    if (perm_p_active(c, adj)) {                                  // w produced by k_gradt3<N,2,1> in the surface-first layout
+      DISPATCH_N(c, DivQArgs a{c->wk[2], c->mbinv_p[(adj && c->has_adj_masks) ? 1 : 0], c->RW2, c->pk[2], c->pk[3], c->n, c->n2};
+                 NSB_TRY(set_smem(k_div3q<N, 1>, DivQ<N>::smem));
+                 k_div3q<N, 1><<<std::min(c->nel, 3 * sms), PK_TPB, DivQ<N>::smem, c->stream>>>(a, c->cgs + 3, c->red_part, c->red_count,
+                                                                                              c->red_out, c->nranks == 1, c->nel));
+    } else {
+      DISPATCH_N(c, DivQArgs a{c->wk[2], s0, c->RW2, c->pk[2], c->pk[3], c->n, c->n2};
+                 NSB_TRY(set_smem(k_div3q<N, 0>, DivQ<N>::smem));
+                 k_div3q<N, 0><<<std::min(c->nel, 3 * sms), PK_TPB, DivQ<N>::smem, c->stream>>>(a, c->cgs + 3, c->red_part, c->red_count,
+                                                                                              c->red_out, c->nranks == 1, c->nel));
+    }
     nsb_count_launch();
     NSB_CUDA(cudaGetLastError());
     return 0;
@@ -1075,10 +1116,9 @@ static int launch_axhelm3(Ctx* c, int mode, const double* u, double* w, const do
 
 int pk_axhelm(Ctx* c, int mode, const double* u, double* w, const double* b, int nfields, double h1, double h2) {
   static const bool pf = [] { const char* e = getenv("NSB_AX_PREFETCH"); return !(e && e[0] == '0'); }();
-  static const bool pers = [] { const char* e = getenv("NSB_AX_PERSISTENT"); return !(e && e[0] == '0'); }();
-  if (mode == 2 && nfields == 3 && pers && c->lx1 == 8) {      // Helmholtz-CG head: persistent, TMA-pipelined (lx1 = 8: 112 KB per CTA)
+  if (mode == 2 && nfields == 3 && c->ax_persistent && c->lx1 == 8) {      // Helmholtz-CG head: persistent, TMA-pipelined (lx1 = 8: 112 KB per CTA)
     constexpr int N = 8;
-    AxPArgs a{c->rk, c->dinvH, c->G, c->bm1, c->wk[1], c->wk[2], c->n, h1, h2};
+    AxPArgs a{c->rk, c->dinvH, c->G, c->bm1, c->wk[1], c->wk[2], c->n, h1, h2, perm_h_active(c) ? 1 : 0};
     NSB_TRY(set_smem(k_axhelm3p<N>, AxP<N>::smem));
     k_axhelm3p<N><<<persistent_grid(c), AxCfg<N>::TPB, AxP<N>::smem, c->stream>>>(a, c->cgs, c->red_part, c->red_count, c->red_out,
                                                                                 c->nranks == 1, c->nel);

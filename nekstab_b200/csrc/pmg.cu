@@ -1258,7 +1258,8 @@ int pm_pcg_tail(Ctx* c, int set, int init, int prof_slot) {
                        c->red_part, c->red_count, sc)));
   }
   if (prof_slot > 0) cudaEventRecord(c->prof_ev[prof_slot], c->stream);
-  if (multi) NSB_TRY(gs_dssum_map(c, c->gsv, c->p2pv, m.rc, 1, 0, sp));                 // vertex sums across elements and ranks
+  // vertex sums across elements and ranks (init: the CG state may be stale -- operator-level calls -- so nothing may be skipped)
+  if (multi) NSB_TRY(gs_dssum_map(c, c->gsv, c->p2pv, m.rc, 1, 0, init ? nullptr : sp));
   const int vthreads = ((std::max(m.nv, m.nagg) + 31) / 32) * 32;
   const long long nthr = vthreads + 32LL * m.nagg_loc;
   k_pm_coarse_dot<<<(int)((nthr + 127) / 128), 128, 0, c->stream>>>(m.nv, m.voff, m.vent, m.d1inv, m.rc, multi ? m.rc0 : m.rc, m.xv, m.nagg,

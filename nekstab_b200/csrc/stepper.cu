@@ -131,7 +131,7 @@ int st_helmholtz(Ctx* c, int adj, double h1, double h2, int* iters) {
       NSB_TRY(ek_hcg_dir_ax(c, nc, h1, h2));
       if (c->nranks > 1) NSB_TRY(vk_cg_finalize_multi(c, c->cgs, nc, 2));
       prof_mark(c, sm, 1);
-      NSB_TRY(gs_dssum(c, c->wk[2], nc, c->n, nullptr));
+      NSB_TRY(gs_dssum_w(c, c->wk[2], nc, nc == 3 && perm_h_active(c), nullptr));
       prof_mark(c, sm, 2);
       NSB_TRY(vk_hcg_update(c, nc, adj));
       prof_mark(c, sm, 3);
@@ -250,7 +250,7 @@ int st_pressure(Ctx* c, int adj, int* iters) {
       prof_mark(c, sm, 4);
       NSB_TRY(ek_pcg_dir_gradt(c, adj));
       prof_mark(c, sm, 5);
-      NSB_TRY(gs_dssum(c, c->wk[2], c->ldim, c->n, sp));
+      NSB_TRY(gs_dssum_w(c, c->wk[2], c->ldim, perm_p_active(c, adj), sp));
       prof_mark(c, sm, 6);
       NSB_TRY(ek_pcg_div(c, adj));
       if (c->nranks > 1) NSB_TRY(vk_cg_finalize_multi(c, sp, 1, 2));

@@ -58,6 +58,18 @@ int nsb_set_params(double viscosity, double density, double tol_v, double tol_p,
 int nsb_set_weights(const double* bm1s);
 /* ubase, vbase, wbase (core/NEKSTAB: /nStab_bflows/; loaded at core/eigensolvers.f:180-186). */
 int nsb_set_baseflow(const double* ubase, const double* vbase, const double* wbase);
+/* Floquet / UPO analysis (uparam(1) = 3.11 direct, 3.21 adjoint; core/matvec.f:187-236, 277-320): with enable != 0 the base flow is
+ * advanced with the FULL Navier-Stokes stepper next to the perturbation during the first nsb_matvec (Nek5000's `ifbase`), its orbit --
+ * the reference's uor, vor, wor(lv, nsteps), core/krylov_subspace.f:18 -- is stored in device memory and replayed by every later
+ * matvec (`ifstorebase = .true.`, core/usr_extra.f:24).  pbase (mesh 2; NULL = 0) is the pressure the base flow starts from (the P
+ * field of the UPO file).  nsb_set_baseflow / nsb_set_timestep with a different nsteps discard the stored orbit.
+ * nsb_get_orbit returns the stored snapshot U^{istep}, 1 <= istep <= nsteps (components may be NULL). */
+int nsb_set_floquet(int enable, const double* pbase);
+/* Sponge forcing of the FULL Navier-Stokes stepper (nsb_nonlinear_forward_map, the co-evolving Floquet base flow): the jp = 0 branch of
+ * nekStab_forcing (core/utils.f:166-171), f += spng_str * spng_fun * (spng_vr - u) with spng_vr = the field held at nekStab_init
+ * (core/utils.f:240).  ur/vr/wr NULL: the current base flow is the reference.  spng_str = 0 (the default) switches it off. */
+int nsb_set_dns_sponge(double spng_str, const double* ur, const double* vr, const double* wr);
+int nsb_get_orbit(int istep, double* u, double* v, double* w);
 /* spng_fun (core/NEKSTAB: /nStab_sponge/): perturbation forcing -spng_fun*u' (core/utils.f:172-177).
  * NULL switches the sponge off (spng_str == 0). */
 int nsb_set_sponge(const double* spng_fun);

@@ -114,7 +114,7 @@ extern "C" int nsb_finalize(void) {
   drop_graphs(c);
   gs_free(c);
   double* ptrs[] = {c->xyz[0], c->xyz[1], c->xyz[2], c->R, c->jac, c->bm1, c->binv, c->mult, c->bm1s, c->G, c->RW2, c->bm2inv,
-                    c->Rd, c->hdiagA, c->hdiagB, c->dinvH, c->ub, c->spng, c->u, c->ulag[0], c->ulag[1], c->f[0], c->f[1],
+                    c->Rd, c->hdiagA, c->hdiagB, c->dinvH, c->ub0, c->pb0, c->orbit, c->spng_ref, c->spng, c->u, c->ulag[0], c->ulag[1], c->f[0], c->f[1],
                     c->f[2], c->pr, c->prlag, c->pt, c->wk[0], c->wk[1], c->wk[2], c->wk[3], c->rk, c->pk[0], c->pk[1],
                     c->pk[2], c->pk[3], c->pk[4], c->red_part, c->red_out, c->slab, c->hbuf, c->hpart};
   for (double* p : ptrs) if (p) cudaFree(p);
@@ -124,6 +124,11 @@ extern "C" int nsb_finalize(void) {
     if (c->dinvE[s]) cudaFree(c->dinvE[s]);
   }
   if (c->projX) { cudaFree(c->projX); cudaFree(c->projEX); }
+  {
+    Ctx::StepState& b = c->base_state;
+    double* bp[] = {b.u, b.ulag[0], b.ulag[1], b.f[0], b.f[1], b.f[2], b.pr, b.prlag};
+    for (double* q : bp) if (q) cudaFree(q);
+  }
   pm_free(c->pmg[0]); pm_free(c->pmg[1]);
   for (int s2 = 0; s2 < 2; ++s2) if (c->mbinv_p[s2]) cudaFree(c->mbinv_p[s2]);
   if (c->adv_scratch) cudaFree(c->adv_scratch);
@@ -300,13 +305,62 @@ extern "C" int nsb_set_weights(const double* bm1s) {
 }
 extern "C" int nsb_set_baseflow(const double* u, const double* v, const double* w) {
   REQUIRE_CTX();
-  if (!c->ub) NSB_TRY(dalloc(&c->ub, c->n * c->ldim));
+  if (!c->ub0) NSB_TRY(dalloc(&c->ub0, c->n * c->ldim));
+  c->ub = c->ub0;
   const double* h[3] = {u, v, w};
   for (int d = 0; d < c->ldim; ++d) {
     if (!h[d]) { nsb_set_error("base-flow component %d is NULL", d); return 1; }
-    NSB_TRY(h2d(c, c->ub + d * c->n, h[d], c->n));
+    NSB_TRY(h2d(c, c->ub0 + d * c->n, h[d], c->n));
+  }
+  c->orbit_ready = false;                       // a new base flow invalidates a stored orbit
+  NSB_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+// Sponge forcing of the FULL Navier-Stokes stepper (nonlinear_forward_map, the co-evolving Floquet base flow): the jp = 0 branch of
+// nekStab_forcing (core/utils.f:166-171), f += spng_str * spng_fun * (spng_vr - u), spng_vr = the field held at nekStab_init
+// (core/utils.f:240).  ur/vr/wr NULL: the current base flow is taken as the reference.  spng_str = 0 switches it off (the default).
+extern "C" int nsb_set_dns_sponge(double spng_str, const double* ur, const double* vr, const double* wr) {
+  REQUIRE_CTX();
+  c->spng_str_dns = spng_str;
+  if (spng_str == 0.0) return 0;
+  if (!c->spng) { nsb_set_error("nsb_set_dns_sponge: call nsb_set_sponge first (spng_fun)"); return 1; }
+  if (!c->spng_ref) NSB_TRY(dalloc(&c->spng_ref, c->n * c->ldim));
+  const double* h[3] = {ur, vr, wr};
+  if (!ur) {
+    if (!c->ub0) { nsb_set_error("nsb_set_dns_sponge: no reference field and no base flow"); return 1; }
+    NSB_TRY(vk_copy(c, c->spng_ref, c->ub0, c->n * c->ldim));
+  } else {
+    for (int d = 0; d < c->ldim; ++d) {
+      if (!h[d]) { nsb_set_error("nsb_set_dns_sponge: reference component %d is NULL", d); return 1; }
+      NSB_TRY(h2d(c, c->spng_ref + d * c->n, h[d], c->n));
+    }
   }
   NSB_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+// Floquet / UPO analysis (uparam(1) = 3.11 / 3.21, core/matvec.f:192,278): the base flow is advanced with the full Navier-Stokes
+// stepper next to the perturbation during the first matvec (Nek's `ifbase`), its orbit uor, vor, wor(lv, nsteps) is kept in HBM and
+// replayed by every later matvec (`ifstorebase = .true.`, core/usr_extra.f:24).  pbase (mesh 2, may be NULL = 0): pressure the base
+// flow starts from (the P field of the UPO file).  enable = 0 switches back to a frozen base flow and frees the orbit.
+extern "C" int nsb_set_floquet(int enable, const double* pbase) {
+  REQUIRE_CTX();
+  c->floquet = enable != 0;
+  c->orbit_ready = false;
+  if (pbase) {
+    if (!c->pb0) NSB_TRY(dalloc(&c->pb0, c->n2));
+    NSB_TRY(h2d(c, c->pb0, pbase, c->n2));
+    NSB_CUDA(cudaStreamSynchronize(c->stream));
+  } else if (c->pb0) { cudaFree(c->pb0); c->pb0 = nullptr; }
+  if (!enable && c->orbit) { cudaFree(c->orbit); c->orbit = nullptr; c->orbit_steps = 0; }
+  return 0;
+}
+// Base-flow orbit snapshot U^{istep} (1 <= istep <= nsteps) after the first Floquet matvec -- what the reference keeps in uor, vor, wor
+extern "C" int nsb_get_orbit(int istep, double* u, double* v, double* w) {
+  REQUIRE_CTX();
+  if (!c->orbit || !c->orbit_ready || istep < 1 || istep > c->orbit_steps) { nsb_set_error("nsb_get_orbit: no stored orbit / step out of range"); return 1; }
+  double* h[3] = {u, v, w};
+  for (int d = 0; d < c->ldim; ++d)
+    if (h[d]) NSB_TRY(d2h(c, h[d], c->orbit + ((long long)(istep - 1) * c->ldim + d) * c->n, c->n));
   return 0;
 }
 extern "C" int nsb_set_sponge(const double* spng) {
@@ -593,8 +647,10 @@ extern "C" int nsb_nonlinear_forward_map(int sq, int sf) {
   double* f = slot_ptr(c, sf);
   NSB_TRY(st_linearized_map(c, 2, q, f));
   NSB_TRY(vk_axpy(c, f, -1.0, q, c->vlen));
-  if (!c->ub) NSB_TRY(dalloc(&c->ub, c->n * c->ldim));
-  return vk_copy(c, c->ub, q, c->n * c->ldim);
+  if (!c->ub0) NSB_TRY(dalloc(&c->ub0, c->n * c->ldim));
+  c->ub = c->ub0;
+  c->orbit_ready = false;
+  return vk_copy(c, c->ub0, q, c->n * c->ldim);
 }
 // prepare_linearized_solver on the velocity of a Krylov vector instead of the stored base flow (newton_krylov calls it on
 // the current Newton iterate, core/newton_krylov.f:69 with vx,vy,vz = q)

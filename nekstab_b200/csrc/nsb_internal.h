@@ -183,7 +183,17 @@ struct Ctx {
   size_t adv_scratch_words = 0;
 
   // base flow, sponge
-  double* ub = nullptr;     // [d][n]
+  double* ub = nullptr;     // [d][n]  the base flow the explicit terms see (Floquet: re-pointed into the stored orbit every step)
+  double* ub0 = nullptr;    // [d][n]  the base flow given by nsb_set_baseflow (owner of the allocation)
+  double spng_str_dns = 0.0; // DNS sponge strength (jp = 0 branch of nekStab_forcing, core/utils.f:166-171); 0 = off
+  double* spng_ref = nullptr; // [d][n] its reference field spng_vr (core/utils.f:240)
+  double* pb0 = nullptr;    // [n2]    its pressure (optional; initial pressure of the co-evolving base flow)
+  // Floquet / UPO: ifbase co-evolution of the base flow with the full Navier-Stokes stepper and orbit storage (core/matvec.f:187-236)
+  bool floquet = false, orbit_ready = false;
+  double* orbit = nullptr;  // [orbit_steps][d][n]  uor, vor, wor (core/krylov_subspace.f:18)
+  int orbit_steps = 0;
+  struct StepState { double* u = nullptr; double* ulag[2] = {nullptr, nullptr}; double* f[3] = {nullptr, nullptr, nullptr}; double* pr = nullptr; double* prlag = nullptr; };
+  StepState base_state;     // time-stepper state of the co-evolving base flow
   double* spng = nullptr;   // [n] or null
 
   // stepper state (all device)
@@ -335,6 +345,7 @@ int vk_multiaxpy_raw(Ctx* c, int k, const double* Q, long long vlen, const doubl
                      double* out);
 int vk_rotate(Ctx* c, int k, int first_slot, const double* S_dev, int lds);
 int vk_fp64_peak(Ctx* c, double* tflops);
+int vk_sponge_dns(Ctx* c, double* f, const double* u);       // f += bm1 * spng_str * spng_fun * (spng_vr - u)
 int vk_rotate_pair(Ctx* c, double* are, double* aim, double g, double d, long long n);
 int vk_wavemaker(Ctx* c, const double* dre, const double* dim, const double* are, const double* aim, double* wm);
 

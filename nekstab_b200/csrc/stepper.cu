@@ -14,6 +14,7 @@
 // device memory (CGState); the host only polls the flag every `check_every` iterations, and kernels of
 // iterations issued past convergence exit immediately, so results do not depend on the polling interval.
 #include <cmath>
+#include <utility>
 
 #include "nsb_internal.h"
 
@@ -306,6 +307,7 @@ static int one_step(Ctx* c, int istep, int kind) {
     // f = -B (u.grad)u : the direct perturbation form with U = u' = u gives 2 C(u)u  [UPSTREAM navier1.f makef -> advab -> convop]
     NSB_TRY(ek_advab(c, 0, c->u, c->u, nullptr, fnew));
     NSB_TRY(vk_scale(c, fnew, 0.5, dn));
+    NSB_TRY(vk_sponge_dns(c, fnew, c->u));        // + B spng_str spng_fun (spng_vr - u) when the DNS sponge is set (core/utils.f:166-171)
   } else {
     NSB_TRY(ek_advab(c, adj, c->u, c->ub, c->spng, fnew));
   }
@@ -337,21 +339,67 @@ static int one_step(Ctx* c, int istep, int kind) {
   return 0;
 }
 
+// ---- Floquet / UPO support: the base flow co-evolves with the full Navier-Stokes stepper (Nek's `ifbase`), the orbit is stored in HBM on
+//      the first matvec and replayed afterwards (`ifstorebase`): forward_linearized_map core/matvec.f:187-236, adjoint :277-320.
+static void swap_state(Ctx* c, Ctx::StepState& s) {
+  std::swap(c->u, s.u); std::swap(c->ulag[0], s.ulag[0]); std::swap(c->ulag[1], s.ulag[1]);
+  std::swap(c->f[0], s.f[0]); std::swap(c->f[1], s.f[1]); std::swap(c->f[2], s.f[2]);
+  std::swap(c->pr, s.pr); std::swap(c->prlag, s.prlag);
+}
+static int floquet_prepare(Ctx* c) {
+  const long long dn = c->n * c->ldim;
+  Ctx::StepState& b = c->base_state;
+  if (!b.u) {
+    NSB_TRY(dalloc(&b.u, dn)); NSB_TRY(dalloc(&b.ulag[0], dn)); NSB_TRY(dalloc(&b.ulag[1], dn));
+    for (int j = 0; j < 3; ++j) NSB_TRY(dalloc(&b.f[j], dn));
+    NSB_TRY(dalloc(&b.pr, c->n2)); NSB_TRY(dalloc(&b.prlag, c->n2));
+  }
+  if (c->orbit_steps != c->nsteps || !c->orbit) {
+    if (c->orbit) cudaFree(c->orbit);
+    c->orbit = nullptr;
+    NSB_TRY(dalloc(&c->orbit, (long long)c->nsteps * dn));      // "ALLOCATING ORBIT WITH NSTEPS" core/matvec.f:201-209
+    c->orbit_steps = c->nsteps;
+    c->orbit_ready = false;
+  }
+  if (!c->orbit_ready) {                                       // the base flow starts from the given field (opcopy(vx.. <- ubase), core/matvec.f:103)
+    NSB_TRY(vk_copy(c, b.u, c->ub0, dn));
+    if (c->pb0) NSB_TRY(vk_copy(c, b.pr, c->pb0, c->n2));
+    else NSB_TRY(vk_fill(c, b.pr, 0.0, c->n2));
+  }
+  return 0;
+}
+
 // vin / vout: device Krylov vectors [vx|vy|(vz)|pr]
 int st_linearized_map(Ctx* c, int adjoint, const double* vin, double* vout) {
   if (c->nsteps <= 0 || c->dt <= 0) { nsb_set_error("time step not set: call nsb_prepare_linearized_solver / nsb_set_timestep"); return 1; }
   if (!c->ub && adjoint != 2) { nsb_set_error("base flow not set: call nsb_set_baseflow"); return 1; }
   const long long dn = c->n * c->ldim;
-  const int adj = (adjoint && c->has_adj_masks) ? 1 : 0;
+  const bool flq = c->floquet && adjoint != 2;
+  if (flq) NSB_TRY(floquet_prepare(c));
   NSB_CUDA(cudaEventRecord(c->ev0, c->stream));
   NSB_TRY(vk_copy(c, c->u, vin, dn));            // nopcopy(vxp,..,prp <- q)   core/matvec.f:212
   NSB_TRY(vk_copy(c, c->pr, vin + dn, c->n2));
-  for (int istep = 1; istep <= c->nsteps; ++istep) {
+  int rc = 0;
+  for (int istep = 1; istep <= c->nsteps && !rc; ++istep) {
     if (c->step_cb) c->step_cb(istep, (istep - 1) * c->dt, c->step_cb_user);     // nekstab_usrchk(), core/matvec.f:221,304
-    int rc = one_step(c, istep, adjoint);
-    if (rc) return rc;
-    (void)adj;
+    if (flq) {
+      if (!c->orbit_ready) {                     // first matvec: advance the base flow (full NS step) and store U^{istep} (:224-227)
+        swap_state(c, c->base_state);
+        rc = one_step(c, istep, 2);
+        swap_state(c, c->base_state);
+        if (rc) break;
+        NSB_TRY(vk_copy(c, c->orbit + (long long)(istep - 1) * dn, c->base_state.u, dn));
+      }
+      // the perturbation's explicit terms of step istep see U^{istep-1}: the given field at step 1, then the stored orbit (:228-231)
+      c->ub = (istep == 1) ? c->ub0 : c->orbit + (long long)(istep - 2) * dn;
+    }
+    rc = one_step(c, istep, adjoint);
   }
+  if (flq) {
+    c->ub = c->ub0;
+    if (!rc) c->orbit_ready = true;              // ifbase = .false.; init = .true.  (:234-236)
+  }
+  if (rc) return rc;
   NSB_TRY(vk_copy(c, vout, c->u, dn));           // nopcopy(f <- vxp,..,prp)   core/matvec.f:239
   NSB_TRY(vk_copy(c, vout + dn, c->pr, c->n2));
   NSB_CUDA(cudaEventRecord(c->ev1, c->stream));

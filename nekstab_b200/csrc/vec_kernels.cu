@@ -84,6 +84,22 @@ int vk_allreduce_max(Ctx* c, double* dev, int count) {
   return 0;
 }
 
+// full Navier-Stokes step with the sponge on (jp = 0 branch of nekStab_forcing, core/utils.f:166-171):
+// f_c += bm1 * spng_str * spng_fun * (spng_vr_c - u_c)
+__global__ void k_sponge_dns(double* __restrict__ f, const double* __restrict__ u, const double* __restrict__ ref,
+                             const double* __restrict__ spng, const double* __restrict__ bm1, double str, long long n, int D) {
+  const long long tot = n * D;
+  GSTRIDE(i, tot) {
+    const long long ip = i % n;
+    f[i] = fma(bm1[ip] * str * spng[ip], ref[i] - u[i], f[i]);
+  }
+}
+int vk_sponge_dns(Ctx* c, double* f, const double* u) {
+  if (c->spng_str_dns == 0.0 || !c->spng || !c->spng_ref) return 0;
+  LAUNCH1(k_sponge_dns, c->n * c->ldim, f, u, c->spng_ref, c->spng, c->bm1, c->spng_str_dns, c->n, c->ldim);
+  return 0;
+}
+
 // dst[e][pos(q)] = src[e][q]: natural -> surface-first element layout (elem_common.cuh), 3-D
 __global__ void k_permute_sf(double* __restrict__ dst, const double* __restrict__ src, long long n, int N) {
   const int np = N * N * N;

@@ -60,6 +60,9 @@ _SIGS = {
     "nsb_set_weights": [_dp],
     "nsb_set_baseflow": [_dp] * 3,
     "nsb_set_sponge": [_dp],
+    "nsb_set_floquet": [C.c_int, _dp],
+    "nsb_set_dns_sponge": [C.c_double, _dp, _dp, _dp],
+    "nsb_get_orbit": [C.c_int, _dp, _dp, _dp],
     "nsb_prepare_linearized_solver": [C.c_double, C.c_double, _dp, _ip, _dp],
     "nsb_set_timestep": [C.c_double, C.c_int],
     "nsb_set_ifvcor": [C.c_int, C.c_int],
@@ -257,6 +260,20 @@ class NekStabB200:
             return
         self._step_cb = self.STEP_CB(lambda istep, t, _u: fn(istep, t))        # keep a reference: ctypes callbacks must outlive the call
         _ck(self.lib.nsb_set_step_callback(C.cast(self._step_cb, C.c_void_p), None))
+
+    def set_floquet(self, enable, pbase=None):
+        """Floquet / UPO mode: base-flow co-evolution + orbit storage (core/matvec.f:187-236)."""
+        pb = None if pbase is None else _arr(pbase).reshape(self.n2)
+        _ck(self.lib.nsb_set_floquet(int(enable), _p(pb)))
+
+    def set_dns_sponge(self, spng_str, ref=None):
+        r = [None] * 3 if ref is None else self._vec3(ref)
+        _ck(self.lib.nsb_set_dns_sponge(float(spng_str), _p(r[0]), _p(r[1]), _p(r[2])))
+
+    def get_orbit(self, istep):
+        u, us = self._out3()
+        _ck(self.lib.nsb_get_orbit(int(istep), _p(us[0]), _p(us[1]), _p(us[2])))
+        return u
 
     def set_projection(self, mxprev):
         _ck(self.lib.nsb_set_projection(int(mxprev)))

@@ -58,6 +58,7 @@ class LinearizedStepper:
         self._lu_e = None
         self._ediag = None
         self.pressure_precond = pressure_precond     # None: Jacobi; else an object with .apply(r) (oracle/pmg.py PMG)
+        self.spng_str_dns, self.spng_ref = 0.0, None # DNS sponge: jp = 0 branch of nekStab_forcing (core/utils.f:166-171)
         self.iters_v, self.iters_p = [], []
         self.dt = None
 
@@ -159,7 +160,10 @@ class LinearizedStepper:
         s = self.s
         if adjoint == "nonlinear":
             # full Navier-Stokes: f = -B (u.grad)u [UPSTREAM navier1.f makef/advab -> convop]; C(u)u = advab_direct(u,u)/2
-            return -0.5 * s.advab_direct(u, u)
+            f = -0.5 * s.advab_direct(u, u)
+            if self.spng_str_dns != 0.0 and self.spng is not None:
+                f = f + s.bm1 * self.spng_str_dns * self.spng * (self.spng_ref - u)
+            return f
         f = -(s.advab_adjoint(u, self.ub) if adjoint else s.advab_direct(u, self.ub))
         if self.spng is not None:
             f = f - s.bm1 * self.spng * u
@@ -210,6 +214,26 @@ class LinearizedStepper:
             if record is not None:
                 record(istep, u, pr)
         return u, pr
+
+    def floquet_map(self, v, p, nsteps, dt, adjoint=False, orbit=None, pbase=None):
+        """forward / adjoint_linearized_map with `ifbase` (uparam(1) = 3.11 / 3.21, core/matvec.f:187-236, 277-320): the base flow
+        is advanced with the full stepper next to the perturbation; the perturbation's explicit terms of step n see U^{n-1} (the given
+        base flow at step 1).  Returns (u, p, orbit); pass the returned orbit (list of U^1..U^nsteps) back in to replay it
+        (`ifstorebase`)."""
+        s, d = self.s, self.s.ldim
+        ub0 = self.ub
+        if orbit is None:
+            orbit = []
+            st = {"u": ub0.copy(), "pr": np.zeros(s.eshape2) if pbase is None else pbase.reshape(s.eshape2).copy()}
+            self.linearized_map(st["u"], st["pr"], nsteps, dt, adjoint="nonlinear", record=lambda i, u, pr: orbit.append(u.copy()))
+        try:
+            def rec(i, u, pr):
+                self.ub = orbit[i - 1]              # after step i the base flow is U^i (seen by step i + 1)
+            self.ub = ub0
+            out = self.linearized_map(v, p, nsteps, dt, adjoint=adjoint, record=rec)
+        finally:
+            self.ub = ub0
+        return out[0], out[1], orbit
 
     def inner(self, a, b, bm1s=None):
         """krylov_inner_product (core/krylov_subspace.f:24-56) velocity part."""

@@ -1,0 +1,95 @@
+"""Floquet / UPO path on the GPU: base-flow co-evolution with the full Navier-Stokes stepper (`ifbase`) and orbit
+storage in HBM (`ifstorebase`, uor/vor/wor) -- forward_linearized_map core/matvec.f:187-236, adjoint :277-320.
+(1) parity with the oracle's floquet_map on small 2-D / 3-D meshes (direct and adjoint, first matvec = co-evolution, second =
+replay of the stored orbit, the orbit itself); (2) the shipped Floquet example (examples/cylinder/stability/direct_Floquet:
+uparam(1) = 3.11, the UPO snapshot BF_1cyl0.f00001 with period 7.9213, sponge 5/5/1.7): KAT-steps 795 = file istep - 1 and the
+leading Floquet multipliers of Spectre_Hd.dat."""
+import os
+
+import numpy as np
+import pytest
+
+from util import GOLD, make_oracle, rel, small_cases, smooth_field
+
+pytestmark = pytest.mark.gpu
+CASES = small_cases()
+
+
+def energy_rel(s, a, b):
+    d = a - b
+    num = sum(np.sum(d[k] ** 2 * s.bm1) for k in range(s.ldim))
+    den = sum(np.sum(b[k] ** 2 * s.bm1) for k in range(s.ldim))
+    return float(np.sqrt(num / den))
+
+
+@pytest.mark.parametrize("name", ["box2d_n6_outflow", "box3d_n8_outflow"])
+def test_floquet_map_against_oracle(name):
+    from nekstab_b200 import lib
+    from oracle.stepper import LinearizedStepper
+    c = CASES[name]
+    s = make_oracle(c)
+    g = lib.NekStabB200(c)
+    try:
+        nsteps, dt, str_dns = 6, 2.0e-3, 1.7
+        g.set_params(1.0 / c.re, 1.0, 1e-13, 1e-13, 3000, 100000)
+        g.set_timestep(dt, nsteps)
+        g.vec_alloc(3)
+        g.set_dns_sponge(str_dns)                       # reference field = the base flow (spng_vr = the field at init, core/utils.f:240)
+        g.set_floquet(1)
+        st = LinearizedStepper(s, c.ubase, c.re, c.spng_fun, solver="direct", ifvcor=c.ifvcor)
+        st.spng_str_dns, st.spng_ref = str_dns, st.ub.copy()
+        v0 = smooth_field(c, 9).reshape((c.ldim,) + s.eshape)
+        p0 = np.zeros(s.eshape2)
+        g.vec_upload(0, v0, p0)
+        orbit = None
+        for mode, adj in ((lib.DIRECT, False), (lib.ADJOINT, True), (lib.DIRECT, False)):
+            g.matvec(mode, 0, 1)                          # 1st call: co-evolution + storage; later calls: replay
+            v, p = g.vec_download(1)
+            vo, po, orbit = st.floquet_map(v0, p0, nsteps, dt, adjoint=adj, orbit=orbit)
+            assert energy_rel(s, v.reshape(vo.shape), vo) < 1e-10, (name, mode)
+            assert rel(p, po) < 1e-6
+        for k in (1, nsteps):
+            assert energy_rel(s, g.get_orbit(k).reshape(orbit[k - 1].shape), orbit[k - 1]) < 1e-11
+        # the co-evolving base flow matters: a frozen base flow gives a different answer
+        g.set_floquet(0)
+        g.matvec(lib.DIRECT, 0, 2)
+        vf, _ = g.vec_download(2)
+        vo, _, _ = st.floquet_map(v0, p0, nsteps, dt, orbit=orbit)
+        assert energy_rel(s, vf.reshape(vo.shape), vo) > 1e-8
+    finally:
+        g.close()
+
+
+def test_cylinder_floquet_example_multipliers():
+    from nekstab_b200 import cases, lib
+    g = np.load(os.path.join(GOLD, "cyl.npz"))
+    u = np.load(os.path.join(GOLD, "cyl_upo.npz"))
+    c = cases.cylinder_case(g)                          # mesh, masks, sponge 5/5 as in direct_Floquet/1cyl.par
+    lx = int(u["lx1"])
+    c.ubase = u["U"].reshape(-1, 2, lx * lx).transpose(1, 0, 2).astype(np.float64)
+    c.end_time = float(u["time"])                       # "endTime will be adjusted from the UPO file" (1cyl.par:5)
+    k_dim = 40
+    ctx = lib.NekStabB200(c)
+    try:
+        ctx.set_params(1.0 / c.re, 1.0, c.tol_v, c.tol_p, 2000, 100000)
+        ctx.set_pressure_preconditioner(1, 64)
+        dt, nsteps, _ = ctx.prepare_linearized_solver(c.end_time)
+        assert nsteps == int(u["istep"]) - 1 == 795                      # KAT-steps
+        from nekstab_b200 import restart
+        p2 = restart.pressure_to_mesh2(u["P"].reshape(c.nel, -1).astype(np.float64), c.lx1, 2)
+        ctx.set_dns_sponge(1.7)
+        ctx.set_floquet(1, p2)
+        ctx.vec_alloc(k_dim + 3)
+        ctx.vec_upload(k_dim + 1, cases.add_noise(c), None)
+        ctx.normalize(k_dim + 1)
+        ctx.matvec(lib.DIRECT, k_dim + 1, 0)
+        ctx.normalize(0)
+        vals, res, V, ncv, scnt = ctx.krylov_schur(lib.DIRECT, k_dim, 0, eigen_tol=1e-6, schur_del=0.1, seed_slot=0)
+        ref = u["Spectre_Hd"]
+        print("floquet multipliers:", vals[:8], "residuals", res[:8], "reference", ref[:8, 0])
+        lead = vals[int(np.argmax(np.abs(vals)))]
+        assert abs(lead.imag) < 1e-6 and abs(lead.real - ref[0, 0]) < 5e-6 * ref[0, 0], (lead, ref[0])       # 1.000846 (7 digits shipped)
+        j = int(np.argmin(np.abs(vals - ref[5, 0])))
+        assert abs(vals[j] - ref[5, 0]) < 1e-4, (vals[j], ref[5, 0])                                          # 0.8117152
+    finally:
+        ctx.close()

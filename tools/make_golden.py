@@ -7,6 +7,7 @@ What is extracted (SURVEY.md 8c "golden vectors"):
             .../adjoint/Spectre_*.dat, .../postproc/sensitivity_budget_wavemaker/{dRe,dIm}1cyl0.f00001,
             element->rank maps of the field files (partition KAT)
   bfs.npz : examples/back_fstep/transient_growth/{BF_bfs0,pRebfs0,orebfs0}.f00001, bfs.ma2, bfs.re2
+  cyl_upo.npz : examples/cylinder/stability/direct_Floquet/{BF_1cyl0.f00001 (the UPO snapshot), Spectre_Hd.dat, Spectre_NSd_conv.dat}
   cav.npz : examples/lid_driven/{BF_cav0.f00001, cav.ma2, cav.re2} (config 3; the shipped base flow lives on y in [0, 1.2]
             although cav.par:9 sets the aspect ratio 1.5 that cav.usr:107-109 rescales the mesh to: the fixture's own
             coordinates are kept, SURVEY.md 8 cfg-3 caveat)
@@ -114,6 +115,17 @@ def cav():
     print("cav.npz", os.path.getsize(f"{OUT}/cav.npz") / 1e6, "MB")
 
 
+def cyl_upo():
+    """examples/cylinder/stability/direct_Floquet: the periodic orbit snapshot the Floquet example starts from (`startFrom =
+    BF_1cyl0.f00001 # here UPO file`, 1cyl.par:2; time = the period 7.9213, istep = 796) and its shipped Floquet spectrum."""
+    d = f"{REF}/examples/cylinder/stability/direct_Floquet"
+    bf = nekio.read_field(f"{d}/BF_1cyl0.f00001").sort_global()
+    out = dict(lx1=bf.nx, U=bf.data["U"][:, :, 0], P=bf.data["P"][:, 0], time=bf.time, istep=bf.istep,
+               Spectre_Hd=nekio.read_spectre(f"{d}/Spectre_Hd.dat"), Spectre_NSd_conv=nekio.read_spectre(f"{d}/Spectre_NSd_conv.dat"))
+    np.savez_compressed(f"{OUT}/cyl_upo.npz", **out)
+    print("cyl_upo.npz", os.path.getsize(f"{OUT}/cyl_upo.npz") / 1e6, "MB")
+
+
 def spectrum_text():
     """First lines of the shipped spectrum files as TEXT: pins the '(3E15.7)' writer of nekstab_b200/restart.py byte for byte."""
     d = f"{REF}/examples/cylinder/stability/direct"
@@ -127,8 +139,12 @@ if __name__ == "__main__":
     if "--cav-only" in sys.argv:
         cav()
         sys.exit(0)
+    if "--upo-only" in sys.argv:
+        cyl_upo()
+        sys.exit(0)
     if "--spectrum-only" not in sys.argv:
         cyl()
         bfs()
         cav()
+        cyl_upo()
     spectrum_text()

@@ -79,12 +79,6 @@ static int setup_masks(Ctx* c, int set, const double* m0, const double* m1, cons
     NSB_TRY(vk_copy(c, c->mbinv[set][d], c->mask[set][d], c->n));
     NSB_TRY(vk_mul(c, c->mbinv[set][d], c->binv, c->n));
   }
-  if (c->gsp_ready && c->mask_same[set]) {       // mask*binv once more in the surface-first element layout (k_div3q<N,1>)
-    if (c->mbinv_p[set]) cudaFree(c->mbinv_p[set]);
-    c->mbinv_p[set] = nullptr;
-    NSB_TRY(dalloc(&c->mbinv_p[set], c->n));
-    NSB_TRY(vk_permute_surf_first(c, c->mbinv_p[set], c->mbinv[set][0]));
-  }
   NSB_TRY(dalloc(&c->dinvE[set], c->n2));
   NSB_TRY(ek_ediag(c, set));
   NSB_TRY(vk_dot3(c, c->dinvE[set], c->dinvE[set], nullptr, c->n2, c->red_out + 9));   // sum diag(E)^2 (scale for the test below)
@@ -130,7 +124,6 @@ extern "C" int nsb_finalize(void) {
     for (double* q : bp) if (q) cudaFree(q);
   }
   pm_free(c->pmg[0]); pm_free(c->pmg[1]);
-  for (int s2 = 0; s2 < 2; ++s2) if (c->mbinv_p[s2]) cudaFree(c->mbinv_p[s2]);
   if (c->adv_scratch) cudaFree(c->adv_scratch);
   if (c->pz) cudaFree(c->pz);
   if (c->ones2) cudaFree(c->ones2);
@@ -254,9 +247,7 @@ extern "C" int nsb_init(int ldim, int lx1, int lxd, int lx2, int nelv, long long
   c->pcg_fused = !(nt && nt[0] == '0');
   const char* na = getenv("NSB_AX_PERSISTENT");
   c->ax_persistent = !(na && na[0] == '0');
-  const char* nq = getenv("NSB_DIVQ");
-  c->divq = !(nq && nq[0] == '0');
-  c->perm_p = c->perm_h = c->gsp_ready;          // surface-first layout of the CG loop vectors (gs.cu builds the second map; NSB_PERM=0: off)
+  c->perm_h = c->gsp_ready;                      // surface-first layout of the Helmholtz loop vector (gs.cu builds the second map; NSB_PERM=0: off)
   NSB_CUDA(cudaStreamSynchronize(c->stream));
   const char* pcv = getenv("NSB_PRECOND");
   if (pcv && pcv[0] == '1') NSB_TRY(nsb_set_pressure_preconditioner(1, 0));

@@ -397,7 +397,7 @@ __device__ __forceinline__ void fine_expand(const double* su, double* sa, double
 // L2; with 256 threads this lets 2 CTAs share an SM (first generation: 512 threads x 128 registers + 156 KB = 1 CTA/SM,
 // 6 % of the FP64 peak, most threads idle in the 64-column first tensor stage).
 // one element; `fine` = the persistent fine-mesh arrays (shared memory or the CTA's global scratch slot).  Kept out of line:
-// inlined into the persistent element loop nvcc hoists the constant-bank matrices into registers and spills (see k_div3p).
+// inlined into the persistent element loop nvcc hoists the constant-bank matrices into registers and spills (see div3q_element in pcg_kernels.cu).
 template <int D, int N, int ADJ>
 __device__ __noinline__ void advab_element(const double* __restrict__ up, const double* __restrict__ ub,
                                            const double* __restrict__ Rd, const double* __restrict__ bm1,

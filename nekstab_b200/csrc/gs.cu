@@ -250,7 +250,7 @@ extern "C" int nsb_gs_host_get(int which, int* out) {
 int gs_setup(Ctx* c, const long long* glo) {
   NSB_TRY(gs_build(c, c->gs, c->p2p, c->n, c->lx1, c->np1, glo));
   const char* env = getenv("NSB_PERM");
-  if (c->ldim == 3 && !(env && env[0] == '0')) {
+  if (c->ldim == 3 && c->lx1 == 8 && !(env && env[0] == '0')) {      // used by the Helmholtz loop of the lx1 = 8 path (k_axhelm3p)
     // second map for loop vectors kept in the surface-first element layout: same nodes, permuted local positions
     std::vector<long long> gp((size_t)c->n);
     std::vector<int> perm(c->np1);

@@ -161,9 +161,8 @@ struct Ctx {
   GSMap gsp;                 // the velocity-mesh map again, for vectors stored in the surface-first element layout (elem_common.cuh)
   P2P p2pp;
   bool gsp_ready = false;
-  bool perm_p = false, perm_h = false;   // surface-first layout of w in the pressure / Helmholtz CG loop (3-D; NSB_PERM=0 disables)
-  bool ax_persistent = true, divq = true;   // NSB_AX_PERSISTENT / NSB_DIVQ (=0 selects the previous kernel generation)
-  double* mbinv_p[2] = {nullptr, nullptr};   // mask*binv in the surface-first layout (pressure loop, masks shared by the components)
+  bool perm_h = false;       // surface-first layout of w in the Helmholtz CG loop (3-D, lx1 = 8; NSB_PERM=0 disables)
+  bool ax_persistent = true;   // NSB_AX_PERSISTENT=0 selects the one-element-per-CTA k_axhelm3 (the only form for lx1 != 8)
   GSMap gsv;                 // gather-scatter over the element-vertex mesh (pressure preconditioner, multi-rank)
   P2P p2pv;                  // its own peer-memory halo channel
   bool gsv_ready = false;
@@ -254,12 +253,9 @@ struct Ctx {
 
 extern Ctx* g_ctx;
 inline double* slot_ptr(Ctx* c, int s) { return c->slab + (long long)s * c->vlen; }
-// the loop vector w of the pressure CG travels gradt -> dssum -> div in the surface-first element layout when every kernel on that
-// route supports it: fused three-level preconditioner (k_gradt3<N,2,1>), k_div3q, one mask set shared by the components
-inline bool perm_p_active(const Ctx* c, int adj) {
-  return c->perm_p && c->ldim == 3 && c->pc_kind == 1 && c->pcg_fused && c->persistent_pcg && c->divq && c->mask_same[adj] &&
-         c->mbinv_p[(adj && c->has_adj_masks) ? 1 : 0] != nullptr;
-}
+// The loop vector w = H p of the Helmholtz CG travels k_axhelm3p -> dssum -> k_hcg_update in the surface-first element layout
+// (elem_common.cuh).  (r2, measured: the same layout in the pressure loop made the dssum 0.022 ms faster but k_gradt3's strided stores
+// and k_div3q's shared-memory reads 0.021 ms slower -- removed there.)
 inline bool perm_h_active(const Ctx* c) { return c->perm_h && c->ldim == 3 && c->lx1 == 8 && c->ax_persistent; }
 
 // ---- host SEM (sem_host.cpp)
@@ -275,7 +271,6 @@ int gs_free(Ctx* c);
 int gs_dssum(Ctx* c, double* u, int nfields, long long stride, const CGState* skip_if_done = nullptr);
 int gs_build(Ctx* c, GSMap& m, P2P& p2p, long long n, int N1, int np_e, const long long* glo, int surf_first = 0);
 int gs_dssum_w(Ctx* c, double* w, int nfields, bool permuted, const CGState* skip);   // dssum of a loop vector in natural / surface-first layout
-int vk_permute_surf_first(Ctx* c, double* dst, const double* src);                  // dst[e][pos(q)] = src[e][q]
 int gs_dssum_map(Ctx* c, GSMap& m, P2P& p2p, double* u, int nfields, long long stride, const CGState* skip_if_done);
 int gs_free_map(Ctx* c, GSMap& m, P2P& p);
 

@@ -91,8 +91,8 @@ __device__ __forceinline__ void apply2_store(const double* __restrict__ M1, cons
 // three-level preconditioner of pmg.cu in its fused form: `p` holds the element-block part zloc of z = M^-1 r (k_pcg_fused); the Q1
 // vertex-mesh part (trilinear interpolation of the element's 8 corner values) and the aggregate value are added here; in this mode the
 // argument `xv` is the per-element table xc[nel][9] (k_pm_corner_values) and `x2` the table of hat-function values at the GL points.
-template <int N, int MODE, int PERM>
-__global__ void __launch_bounds__(PK_TPB, 3)
+template <int N, int MODE>
+__global__ void __launch_bounds__(PK_TPB, 4)      // 40 registers: FOUR CTAs per SM (r2: MODE 2 at 54 registers / 3 CTAs per SM cost 0.03 ms)
 k_gradt3(const double* __restrict__ p, double* __restrict__ w, const double* __restrict__ RW2,
          const double* __restrict__ dinvE, double* __restrict__ pdir, const CGState* __restrict__ cgs, long long n,
          long long n2, const double* __restrict__ xv, const int* __restrict__ vid, const double* __restrict__ x2,
@@ -202,32 +202,19 @@ k_gradt3(const double* __restrict__ p, double* __restrict__ w, const double* __r
   }
   __syncthreads();
   // ---- t stage: w_c = J12^T sb[c*2] + D12^T sb[c*2+1], stored straight to global memory (coalesced in (j,i))
-  static_assert(3 * C2::ncol <= TPB, "one task per thread");
-  if (tid < 3 * C2::ncol) {
-    const int t = tid;
+  //      Every column is shared by two threads (outputs k < N/2 and k >= N/2): 6 N^2 = 384 equal tasks instead of 192 tasks of twice
+  //      the length with half the CTA waiting at the exit (r2 ncu: barrier stalls 6.7 warps per issue, 48 % of the warp slots active).
+  static_assert(6 * C2::ncol <= TPB && N % 2 == 0, "one task per thread");
+  if (tid < 6 * C2::ncol) {
+    const int half = tid / (3 * C2::ncol), t = tid - half * 3 * C2::ncol;
     const int c = t / C2::ncol, col = t - c * C2::ncol;
     const int bi = C2::base(col);
     double v[N2], v2[N2];
 #pragma unroll
     for (int l = 0; l < N2; ++l) { v[l] = sb[c * 2][bi + l * C2::stride]; v2[l] = sb[c * 2 + 1][bi + l * C2::stride]; }
-    if (PERM) {
-      // surface-first element layout (elem_common.cuh SurfFirst): planes k = 0 and N-1 lead, then the rings, then the interior
-      using SF = SurfFirst<N>;
-      const int cj = col / N, ci = col - cj * N;
-      const int m0 = SF::mid0(cj, ci), ms = SF::mids(cj, ci);
-      double* po = w + (long long)c * n + e1;
-#pragma unroll
-      for (int a = 0; a < N; ++a) {
-        double sacc = 0.0;
-#pragma unroll
-        for (int l = 0; l < N2; ++l) sacc = fma(cm.J12t[a * N2 + l], v[l], sacc);
-#pragma unroll
-        for (int l = 0; l < N2; ++l) sacc = fma(cm.D12t[a * N2 + l], v2[l], sacc);
-        po[a == 0 ? col : (a == N - 1 ? N * N + col : m0 + (a - 1) * ms)] = sacc;
-      }
-    } else {
-      apply2_store<N, N2>(cm.J12t, v, cm.D12t, v2, w + (long long)c * n + e1 + col, N * N);
-    }
+    double* po = w + (long long)c * n + e1 + col + (long long)half * (N / 2) * N * N;
+    if (half == 0) apply2_store<N / 2, N2>(cm.J12t, v, cm.D12t, v2, po, N * N);
+    else apply2_store<N / 2, N2>(cm.J12t + (N / 2) * N2, v, cm.D12t + (N / 2) * N2, v2, po, N * N);
   }
 }
 
@@ -379,137 +366,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // element (metrics, CG vectors, the three w components) is moved by bulk TMA copies into a double-buffered stage while
 // the previous element is being contracted, so DRAM requests are in flight for the whole life of the CTA instead of
 // only during each CTA's load phase (r1b ncu: k_div3 27 % DRAM, barrier + long-scoreboard stalls).
-template <int N>
-struct DivP {
-  static constexpr int N2 = N - 2, NP1 = N * N * N, NP2 = N2 * N2 * N2;
-  using SA = Shp<N2, N, N>;
-  using SB = Shp<N2, N2, N>;
-  static constexpr int stage = 4 * NP1 + 10 * NP2;                 // w (3 comps), mask*binv, 9 metric arrays, pdir
-  static constexpr size_t smem = sizeof(double) * (2 * stage + 6 * SA::size + 9 * SB::size) + 2 * sizeof(uint64_t);
-};
-
-// One element of k_div3p.  Deliberately NOT inlined: inside the persistent element loop the compiler would treat the constant-bank
-// operator matrices as loop invariants and hoist them into registers (80+ registers and spills, measured).  Returns this thread's
-// contribution to sum pdir*Ep.
-template <int N>
-__device__ __noinline__ double div3_element(const double* __restrict__ in, double* __restrict__ sa, double* __restrict__ sbuf,
-                                            double* __restrict__ qout, int e, int tid) {
-  using P = DivP<N>;
-  constexpr int N2 = P::N2, NP1 = P::NP1, NP2 = P::NP2;
-  using SA = typename P::SA;
-  using SB = typename P::SB;
-  using C2 = ColIn<2, N, N, N>;
-  using C1 = ColIn<1, N2, N, N>;
-  using C0 = ColIn<0, N2, N2, N>;
-  double* spart = sa;
-  double rho[1] = {0.0};
-  {
-    const double* inmb = in + 3 * NP1;
-    const double* inrw = in + 4 * NP1;
-    // ---- t stage: columns along t straight from the (unpitched) staged element: lanes run over (j,i) => conflict free
-    if (tid < 3 * C2::ncol) {
-      const int c = tid / C2::ncol, col = tid - c * C2::ncol;
-      double v[N];
-#pragma unroll
-      for (int l = 0; l < N; ++l) v[l] = in[c * NP1 + l * N * N + col] * inmb[l * N * N + col];
-      apply_store<N2, N>(cm.J12, v, sa + (c * 2) * SA::size + C2::base(col), C2::stride);
-      apply_store<N2, N>(cm.D12, v, sa + (c * 2 + 1) * SA::size + C2::base(col), C2::stride);
-    }
-    __syncthreads();
-    if (tid < 6 * C1::ncol) {
-      const int grp = tid / C1::ncol, col = tid - grp * C1::ncol;
-      const int which = grp / 3, c = grp - which * 3;
-      const int bi = C1::base(col);
-      const int bo = (col / N) * N2 * SB::PI + (col % N);
-      double v[N];
-#pragma unroll
-      for (int l = 0; l < N; ++l) v[l] = sa[(c * 2 + which) * SA::size + bi + l * C1::stride];
-      apply_store<N2, N>(cm.J12, v, sbuf + (c * 3 + (which == 0 ? 0 : 2)) * SB::size + bo, SB::PI);
-      if (which == 0) apply_store<N2, N>(cm.D12, v, sbuf + (c * 3 + 1) * SB::size + bo, SB::PI);
-    }
-    __syncthreads();
-    if (tid < 9 * C0::ncol) {
-      const int grp = tid / C0::ncol, col = tid - grp * C0::ncol;
-      const int dir = grp / 3, c = grp - dir * 3;
-      const double* b0 = sbuf + (c * 3 + dir) * SB::size + C0::base(col);
-      double v[N];
-#pragma unroll
-      for (int l = 0; l < N; ++l) v[l] = b0[l];
-      double* po = spart + grp * NP2 + col * N2;
-      if (dir == 0) apply_store<N2, N>(cm.D12, v, po, 1);
-      else apply_store<N2, N>(cm.J12, v, po, 1);
-    }
-    __syncthreads();
-    if (tid < NP2) {
-      const int q = tid;
-      double acc = 0.0;
-#pragma unroll
-      for (int g = 0; g < 9; ++g) acc = fma(inrw[g * NP2 + q], spart[g * NP2 + q], acc);
-      qout[(long long)e * NP2 + q] = acc;
-      rho[0] += inrw[9 * NP2 + q] * acc;
-    }
-    __syncthreads();
-  }
-  return rho[0];
-}
-
-template <int N>
-__global__ void __launch_bounds__(PK_TPB, 2)
-k_div3p(const double* __restrict__ u, const double* __restrict__ mbinv, double* __restrict__ qout, const double* __restrict__ RW2,
-        const double* __restrict__ pdir, CGState* __restrict__ cgs, double* __restrict__ part, unsigned* counter,
-        double* __restrict__ red_out, int finalize, long long n, long long n2, int nel) {
-  using P = DivP<N>;
-  constexpr int N2 = P::N2, TPB = PK_TPB, NP1 = P::NP1, NP2 = P::NP2, STG = P::stage;
-  using SA = typename P::SA;
-  using SB = typename P::SB;
-  using C2 = ColIn<2, N, N, N>;
-  using C1 = ColIn<1, N2, N, N>;
-  using C0 = ColIn<0, N2, N2, N>;
-  extern __shared__ __align__(128) double dsm[];
-  double* sin = dsm;                                   // [2][STG]
-  double* sa = dsm + 2 * STG;                          // [6][SA::size], reused for the 9 partial arrays
-  double* sbuf = sa + 6 * SA::size;                    // [9][SB::size]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sbuf + 9 * SB::size);
-  __shared__ double sred[32];
-  double* spart = sa;
-  static_assert(9 * NP2 <= 6 * SA::size, "spart alias");
-  const int tid = threadIdx.x;
-  if (cgs->done) return;
-  if (tid == 0) {
-    mbar_init(&bar[0], 1);
-    mbar_init(&bar[1], 1);
-    mbar_fence_init();
-  }
-  __syncthreads();
-  auto issue = [&](int e, int st) {
-    double* dst = sin + st * STG;
-    const long long e1 = (long long)e * NP1, e2 = (long long)e * NP2;
-    mbar_expect_tx(&bar[st], STG * (uint32_t)sizeof(double));
-#pragma unroll
-    for (int c = 0; c < 3; ++c) tma_bulk_g2s(dst + c * NP1, u + (long long)c * n + e1, NP1 * sizeof(double), &bar[st]);
-    tma_bulk_g2s(dst + 3 * NP1, mbinv + e1, NP1 * sizeof(double), &bar[st]);
-#pragma unroll
-    for (int g = 0; g < 9; ++g) tma_bulk_g2s(dst + 4 * NP1 + g * NP2, RW2 + (long long)g * n2 + e2, NP2 * sizeof(double), &bar[st]);
-    tma_bulk_g2s(dst + 4 * NP1 + 9 * NP2, pdir + e2, NP2 * sizeof(double), &bar[st]);
-  };
-  if (tid == 0 && (int)blockIdx.x < nel) issue(blockIdx.x, 0);
-  double rho[1] = {0.0};
-  int it = 0;
-  for (int e = blockIdx.x; e < nel; e += gridDim.x, ++it) {
-    const int st = it & 1;
-    if (tid == 0 && e + (int)gridDim.x < nel) issue(e + gridDim.x, st ^ 1);
-    mbar_wait(&bar[st], (it >> 1) & 1);
-    rho[0] += div3_element<N>(sin + st * STG, sa, sbuf, qout, e, tid);
-  }
-  if (grid_sum_finish<1>(rho, part, counter, red_out, sred) && finalize && tid == 0) {
-    cgs->rho = red_out[0];
-    cgs->alpha = cgs->rtz1 / red_out[0];
-  }
-}
-
 // ------------------------------------------------------------------------------------------------ k_div3q: single staging buffer, early refill
-// r1d ncu on k_div3p: 59 % of the HBM roofline, 15 % of the stall samples in the mbarrier wait -- two stages at 2 CTAs/SM (111 KB per
-// CTA) do not keep enough bytes in flight.  Here the element's inputs live in ONE staging buffer whose two halves are refilled as
+// r1's k_div3p (double-buffered stage, 111 KB per CTA, 2 CTAs/SM): 59 % of the HBM roofline, 15 % of the stall samples in the mbarrier
+// wait -- not enough bytes in flight; replaced by this kernel in r2 (0.186 -> 0.176 ms).  Here the element's inputs live in ONE staging buffer whose two halves are refilled as
 // soon as they have been consumed (the scheme of k_axhelm3p):
 //   half A (w x3, mask*binv)   consumed by the t stage      -> element e+1 requested right after the t-stage barrier
 //   half B (9 metric arrays)   consumed by the final stage  -> element e+1 requested right after the final stage
@@ -544,7 +403,7 @@ __device__ __forceinline__ void div3q_issue_b(const DivQArgs* A, double* stg, ui
   for (int g = 0; g < 9; ++g) tma_bulk_g2s(stg + 4 * NP1 + g * NP2, A->RW2 + (long long)g * A->n2 + e2, NP2 * sizeof(double), bar);
 }
 
-template <int N, int PERM>
+template <int N>
 __device__ __noinline__ double div3q_element(const DivQArgs* __restrict__ A, double* __restrict__ stg, double* __restrict__ sa,
                                              double* __restrict__ sbuf, uint64_t* bar, int e, int e_next, uint32_t parity, int tid) {
   using P = DivQ<N>;
@@ -559,24 +418,16 @@ __device__ __noinline__ double div3q_element(const DivQArgs* __restrict__ A, dou
   const double* inrw = stg + 4 * NP1;
   const double pd = (tid < NP2) ? A->pdir[(long long)e * NP2 + tid] : 0.0;      // needed in the final stage only: latency hidden
   mbar_wait(&bar[0], parity);
-  if (tid < 3 * C2::ncol) {
-    const int c = tid / C2::ncol, col = tid - c * C2::ncol;
+  // t stage: every column is shared by two threads (the J12 and the D12 product): 6 N^2 = 384 equal tasks instead of 192 tasks of
+  // twice the length with half the CTA waiting at the barrier (r2 ncu: barrier stalls 7.6 warps per issue)
+  if (tid < 6 * C2::ncol) {
+    const int which = tid / (3 * C2::ncol), t = tid - which * 3 * C2::ncol;
+    const int c = t / C2::ncol, col = t - c * C2::ncol;
     double v[N];
-    if (PERM) {                                      // w and mask*binv arrive in the surface-first element layout
-      using SF = SurfFirst<N>;
-      const int cj = col / N, ci = col - cj * N;
-      const int m0 = SF::mid0(cj, ci), ms = SF::mids(cj, ci);
 #pragma unroll
-      for (int l = 0; l < N; ++l) {
-        const int o = (l == 0) ? col : (l == N - 1 ? N * N + col : m0 + (l - 1) * ms);
-        v[l] = stg[c * NP1 + o] * inmb[o];
-      }
-    } else {
-#pragma unroll
-      for (int l = 0; l < N; ++l) v[l] = stg[c * NP1 + l * N * N + col] * inmb[l * N * N + col];
-    }
-    apply_store<N2, N>(cm.J12, v, sa + (c * 2) * SA::size + C2::base(col), C2::stride);
-    apply_store<N2, N>(cm.D12, v, sa + (c * 2 + 1) * SA::size + C2::base(col), C2::stride);
+    for (int l = 0; l < N; ++l) v[l] = stg[c * NP1 + l * N * N + col] * inmb[l * N * N + col];
+    if (which == 0) apply_store<N2, N>(cm.J12, v, sa + (c * 2) * SA::size + C2::base(col), C2::stride);
+    else apply_store<N2, N>(cm.D12, v, sa + (c * 2 + 1) * SA::size + C2::base(col), C2::stride);
   }
   __syncthreads();                                   // half A consumed
   if (tid == 0 && e_next >= 0) div3q_issue_a<N>(A, stg, &bar[0], e_next);
@@ -619,7 +470,7 @@ __device__ __noinline__ double div3q_element(const DivQArgs* __restrict__ A, dou
   return rho;
 }
 
-template <int N, int PERM>
+template <int N>
 __global__ void __launch_bounds__(PK_TPB, 3)
 k_div3q(DivQArgs args, CGState* __restrict__ cgs, double* __restrict__ part, unsigned* counter, double* __restrict__ red_out,
         int finalize, int nel) {
@@ -651,7 +502,7 @@ k_div3q(DivQArgs args, CGState* __restrict__ cgs, double* __restrict__ part, uns
   int it = 0;
   for (int e = blockIdx.x; e < nel; e += gridDim.x, ++it) {
     const int en = (e + (int)gridDim.x < nel) ? e + (int)gridDim.x : -1;
-    rho[0] += div3q_element<N, PERM>(&sargs, stg, sa, sbuf, bar, e, en, (uint32_t)(it & 1), tid);
+    rho[0] += div3q_element<N>(&sargs, stg, sa, sbuf, bar, e, en, (uint32_t)(it & 1), tid);
   }
   if (grid_sum_finish<1>(rho, part, counter, red_out, sred) && finalize && tid == 0) {
     cgs->rho = red_out[0];
@@ -844,7 +695,7 @@ __device__ __forceinline__ void ax3p_issue_g(const AxPArgs* A, double* stg, uint
 }
 
 // One element (not inlined: inside the element loop nvcc would hoist the constant-bank operator matrices into registers, see
-// div3_element).  actmask: bit f = component f still iterating.
+// div3q_element).  actmask: bit f = component f still iterating.
 template <int N>
 __device__ __noinline__ Rho3 ax3p_element(const AxPArgs* __restrict__ A, double* __restrict__ stg, double* __restrict__ su,
                                           double* __restrict__ sr, uint64_t* bar, int e, int e_next, uint32_t parity, int actmask,
@@ -992,7 +843,7 @@ int pk_upload_constants(const ConstMats& h) {
   } while (0)
 
 int pk_gradt(Ctx* c, const double* p, double* w) {
-  DISPATCH_N(c, k_gradt3<N, 0, 0><<<c->nel, PK_TPB, 0, c->stream>>>(p, w, c->RW2, nullptr, nullptr, nullptr, c->n, c->n2, nullptr, nullptr, nullptr, nullptr, nullptr));
+  DISPATCH_N(c, k_gradt3<N, 0><<<c->nel, PK_TPB, 0, c->stream>>>(p, w, c->RW2, nullptr, nullptr, nullptr, c->n, c->n2, nullptr, nullptr, nullptr, nullptr, nullptr));
   nsb_count_launch();
   NSB_CUDA(cudaGetLastError());
   return 0;
@@ -1012,18 +863,13 @@ int pk_pcg_dir_gradt(Ctx* c, int adj) {
   const double* zscale = c->pc_kind ? c->ones2 : c->dinvE[adj];
   if (c->pc_kind == 1 && c->pcg_fused) {          // fused preconditioner: pz holds the element-block part, the coarse parts are added here
     const PMG& m = c->pmg[(adj && c->has_adj_masks) ? 1 : 0];
-    if (perm_p_active(c, adj)) {
-      DISPATCH_N(c, k_gradt3<N, 2, 1><<<c->nel, PK_TPB, 0, c->stream>>>(c->pz, c->wk[2], c->RW2, nullptr, c->pk[2], c->cgs + 3, c->n, c->n2,
-                                                                     m.xc, nullptr, m.hat, nullptr, c->pk[1]));
-    } else {
-      DISPATCH_N(c, k_gradt3<N, 2, 0><<<c->nel, PK_TPB, 0, c->stream>>>(c->pz, c->wk[2], c->RW2, nullptr, c->pk[2], c->cgs + 3, c->n, c->n2,
-                                                                     m.xc, nullptr, m.hat, nullptr, c->pk[1]));
-    }
+    DISPATCH_N(c, k_gradt3<N, 2><<<c->nel, PK_TPB, 0, c->stream>>>(c->pz, c->wk[2], c->RW2, nullptr, c->pk[2], c->cgs + 3, c->n, c->n2,
+                                                                m.xc, nullptr, m.hat, nullptr, c->pk[1]));
     nsb_count_launch();
     NSB_CUDA(cudaGetLastError());
     return 0;
   }
-  DISPATCH_N(c, k_gradt3<N, 1, 0><<<c->nel, PK_TPB, 0, c->stream>>>(zsrc, c->wk[2], c->RW2, zscale, c->pk[2], c->cgs + 3,
+  DISPATCH_N(c, k_gradt3<N, 1><<<c->nel, PK_TPB, 0, c->stream>>>(zsrc, c->wk[2], c->RW2, zscale, c->pk[2], c->cgs + 3,
                                                               c->n, c->n2, nullptr, nullptr, nullptr, nullptr, nullptr));
   nsb_count_launch();
   NSB_CUDA(cudaGetLastError());
@@ -1056,29 +902,13 @@ int pk_pcg_div(Ctx* c, int adj, int fused) {
   const double* s0 = c->mbinv[adj][0];
   const double* s1 = c->mask_same[adj] ? nullptr : c->mbinv[adj][1];
   const double* s2 = c->mask_same[adj] ? nullptr : c->mbinv[adj][2];
-  if (c->persistent_pcg && !fused && c->mask_same[adj] && c->divq) {      // single staging buffer with early refill, 3 CTAs per SM
+  if (c->persistent_pcg && !fused && c->mask_same[adj]) {      // single staging buffer with early refill, 3 CTAs per SM (NSB_PERSISTENT=0: k_div3)
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-    if (perm_p_active(c, adj)) {                                  // w produced by k_gradt3<N,2,1> in the surface-first layout
-      DISPATCH_N(c, DivQArgs a{c->wk[2], c->mbinv_p[(adj && c->has_adj_masks) ? 1 : 0], c->RW2, c->pk[2], c->pk[3], c->n, c->n2};
-                 NSB_TRY(set_smem(k_div3q<N, 1>, DivQ<N>::smem));
-                 k_div3q<N, 1><<<std::min(c->nel, 3 * sms), PK_TPB, DivQ<N>::smem, c->stream>>>(a, c->cgs + 3, c->red_part, c->red_count,
-                                                                                              c->red_out, c->nranks == 1, c->nel));
-    } else {
-      DISPATCH_N(c, DivQArgs a{c->wk[2], s0, c->RW2, c->pk[2], c->pk[3], c->n, c->n2};
-                 NSB_TRY(set_smem(k_div3q<N, 0>, DivQ<N>::smem));
-                 k_div3q<N, 0><<<std::min(c->nel, 3 * sms), PK_TPB, DivQ<N>::smem, c->stream>>>(a, c->cgs + 3, c->red_part, c->red_count,
-                                                                                              c->red_out, c->nranks == 1, c->nel));
-    }
-    nsb_count_launch();
-    NSB_CUDA(cudaGetLastError());
-    return 0;
-  }
-  if (c->persistent_pcg && !fused && c->mask_same[adj]) {
-    DISPATCH_N(c, NSB_TRY(set_smem(k_div3p<N>, DivP<N>::smem));
-               k_div3p<N><<<persistent_grid(c), PK_TPB, DivP<N>::smem, c->stream>>>(c->wk[2], s0, c->pk[3], c->RW2, c->pk[2], c->cgs + 3,
-                                                                                    c->red_part, c->red_count, c->red_out,
-                                                                                    c->nranks == 1, c->n, c->n2, c->nel));
+    DISPATCH_N(c, DivQArgs a{c->wk[2], s0, c->RW2, c->pk[2], c->pk[3], c->n, c->n2};
+               NSB_TRY(set_smem(k_div3q<N>, DivQ<N>::smem));
+               k_div3q<N><<<std::min(c->nel, 3 * sms), PK_TPB, DivQ<N>::smem, c->stream>>>(a, c->cgs + 3, c->red_part, c->red_count, c->red_out,
+                                                                                         c->nranks == 1, c->nel));
     nsb_count_launch();
     NSB_CUDA(cudaGetLastError());
     return 0;

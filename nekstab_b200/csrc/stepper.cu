@@ -251,7 +251,7 @@ int st_pressure(Ctx* c, int adj, int* iters) {
       prof_mark(c, sm, 4);
       NSB_TRY(ek_pcg_dir_gradt(c, adj));
       prof_mark(c, sm, 5);
-      NSB_TRY(gs_dssum_w(c, c->wk[2], c->ldim, perm_p_active(c, adj), sp));
+      NSB_TRY(gs_dssum(c, c->wk[2], c->ldim, c->n, sp));
       prof_mark(c, sm, 6);
       NSB_TRY(ek_pcg_div(c, adj));
       if (c->nranks > 1) NSB_TRY(vk_cg_finalize_multi(c, sp, 1, 2));

@@ -100,20 +100,6 @@ int vk_sponge_dns(Ctx* c, double* f, const double* u) {
   return 0;
 }
 
-// dst[e][pos(q)] = src[e][q]: natural -> surface-first element layout (elem_common.cuh), 3-D
-__global__ void k_permute_sf(double* __restrict__ dst, const double* __restrict__ src, long long n, int N) {
-  const int np = N * N * N;
-  GSTRIDE(i, n) {
-    const long long e = i / np;
-    const int q = (int)(i - e * np);
-    dst[e * np + surf_first_pos(N, q)] = src[i];
-  }
-}
-int vk_permute_surf_first(Ctx* c, double* dst, const double* src) {
-  LAUNCH1(k_permute_sf, c->n, dst, src, c->n, c->lx1);
-  return 0;
-}
-
 // ---------------------------------------------------------------------------------------- stepper pointwise
 // b_c = sum_j ab_j f_j,c + (bm1/dt) sum_j bd_j u_j,c     (makextp + makebdfp; vtrans = rho folded into bdr)
 struct RhsArgs {
@@ -291,11 +277,12 @@ __global__ void k_hcg_init(const double* __restrict__ r, double* __restrict__ x,
   }
   if (grid_sum_finish<6>(v, part, counter, out, sred) && finalize && threadIdx.x == 0) hcg_finalize_init(cgs, out, ncomp);
 }
+template <int PN>   // PN = lx1 when w arrives in the surface-first element layout (compile-time: the index map is all shifts and masks), else 0
 __global__ void k_hcg_update(double* __restrict__ r, double* __restrict__ x, const double* __restrict__ p,
                              const double* __restrict__ w, const double* __restrict__ m0, const double* __restrict__ m1,
                              const double* __restrict__ m2, const double* __restrict__ dinv,
                              const double* __restrict__ mult, const double* __restrict__ binv, long long n, int ncomp,
-                             CGState* cgs, double* part, unsigned* counter, double* out, int finalize, int permN) {
+                             CGState* cgs, double* part, unsigned* counter, double* out, int finalize) {
   __shared__ double sred[6 * 32];
   double v[6] = {0, 0, 0, 0, 0, 0};
   bool active[3];
@@ -307,14 +294,14 @@ __global__ void k_hcg_update(double* __restrict__ r, double* __restrict__ x, con
     any |= active[f];
   }
   if (!any) return;
-  const int np = permN * permN * permN;
+  constexpr int np = PN * PN * PN;
   GSTRIDE(i, n) {
     const double m = mult[i], di = dinv[i] * m, bi = binv[i] * m;
-    // w = H p arrives from k_axhelm3p / dssum in the surface-first element layout (permN = lx1), everything else is natural
+    // w = H p arrives from k_axhelm3p / dssum in the surface-first element layout (PN = lx1), everything else is natural
     long long iw = i;
-    if (permN) {
+    if (PN) {
       const long long e = i / np;
-      iw = e * np + surf_first_pos(permN, (int)(i - e * np));
+      iw = e * np + SurfFirst<(PN ? PN : 4)>::pos_lin((int)(i - e * np));
     }
     for (int f = 0; f < ncomp; ++f) {
       if (!active[f]) continue;
@@ -336,9 +323,15 @@ int vk_hcg_init(Ctx* c, int ncomp) {
   return 0;
 }
 int vk_hcg_update(Ctx* c, int ncomp, int adj) {
-  LAUNCH1(k_hcg_update, c->n, c->rk, c->wk[3], c->wk[1], c->wk[2], c->mask[adj][0], c->mask[adj][1],
-          c->mask[adj][c->ldim == 3 ? 2 : 1], c->dinvH, c->mult, c->binv, c->n, ncomp, c->cgs, c->red_part, c->red_count,
-          c->red_out, c->nranks == 1, (ncomp == 3 && perm_h_active(c)) ? c->lx1 : 0);
+  if (ncomp == 3 && perm_h_active(c)) {           // lx1 = 8 (perm_h_active)
+    LAUNCH1(k_hcg_update<8>, c->n, c->rk, c->wk[3], c->wk[1], c->wk[2], c->mask[adj][0], c->mask[adj][1],
+            c->mask[adj][c->ldim == 3 ? 2 : 1], c->dinvH, c->mult, c->binv, c->n, ncomp, c->cgs, c->red_part, c->red_count,
+            c->red_out, c->nranks == 1);
+  } else {
+    LAUNCH1(k_hcg_update<0>, c->n, c->rk, c->wk[3], c->wk[1], c->wk[2], c->mask[adj][0], c->mask[adj][1],
+            c->mask[adj][c->ldim == 3 ? 2 : 1], c->dinvH, c->mult, c->binv, c->n, ncomp, c->cgs, c->red_part, c->red_count,
+            c->red_out, c->nranks == 1);
+  }
   if (c->nranks > 1) NSB_TRY(vk_cg_finalize_multi(c, c->cgs, ncomp, 1));
   return 0;
 }

@@ -1,7 +1,10 @@
 #!/usr/bin/env python
 """Turn an `ncu --set full` report into the two small files kept under profiles/: per-kernel DRAM traffic per launch
 (JSON, read by bench.py for `roofline.traffic`) and a one-line-per-metric text summary.
-Usage: python tools/ncu_summarise.py report.ncu-rep profiles/rXX   (writes rXX_ncu_dram_traffic.json, rXX_ncu_metrics.txt)"""
+Usage: python tools/ncu_summarise.py profiles/rXX report1.ncu-rep [report2.ncu-rep ...] [--source-hash HASH]
+       (writes rXX_ncu_dram_traffic.json, rXX_ncu_metrics.txt; the JSON carries `_meta` = report names + the hash of the CUDA sources
+        the capture was taken from -- pass the hash printed by the capture run, default: the current tree -- so that bench.py can tell a
+        stale capture from a current one)"""
 import csv
 import json
 import re
@@ -21,12 +24,33 @@ METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.
 
 
 def main():
-    rep, prefix = sys.argv[1], sys.argv[2]
+    args = [a for a in sys.argv[1:]]
+    src_hash = None
+    if "--source-hash" in args:
+        i = args.index("--source-hash")
+        src_hash = args[i + 1]
+        del args[i:i + 2]
+    prefix, reps = args[0], args[1:]
+    if src_hash is None:
+        import os
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        import bench
+        src_hash = bench.kernel_source_hash()
+    traffic, lines, seen = {"_meta": {"report": [r.split("/")[-1] for r in reps], "source_hash": src_hash}}, [], set()
+    for rep in reps:
+        summarise(rep, traffic, lines, seen)
+    with open(prefix + "_ncu_dram_traffic.json", "w") as f:
+        json.dump(traffic, f, indent=1)
+    with open(prefix + "_ncu_metrics.txt", "w") as f:
+        f.write("\n".join(lines) + "\n")
+    print("kernels:", ", ".join(seen))
+
+
+def summarise(rep, traffic, lines, seen):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     idx = {h: i for i, h in enumerate(hdr)}
-    traffic, lines, seen = {}, [], set()
     for r in rows[2:]:
         name = re.sub(r"\(.*", "", r[idx["Kernel Name"]]).replace("void ", "").replace("<unnamed>::", "").strip()
         dur = float(r[idx["gpu__time_duration.sum"]])
@@ -44,11 +68,6 @@ def main():
         for m in METRICS:
             if m in idx:
                 lines.append("    %-80s %s %s" % (m, r[idx[m]], units[idx[m]]))
-    with open(prefix + "_ncu_dram_traffic.json", "w") as f:
-        json.dump(traffic, f, indent=1)
-    with open(prefix + "_ncu_metrics.txt", "w") as f:
-        f.write("\n".join(lines) + "\n")
-    print("kernels:", ", ".join(seen))
 
 
 if __name__ == "__main__":

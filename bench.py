@@ -154,8 +154,8 @@ def kernel_source_hash():
     return h.hexdigest()[:16]
 
 
-NCU_NAMES = {"pcg_div": "k_div3p", "pcg_gradt": "k_gradt3", "dssum": "k_gs_sum", "pcg_update": "k_pcg_update",
-             "hcg_axhelm": "k_axhelm3", "hcg_update": "k_hcg_update", "pcg_pc_apply": "k_pm_apply2", "pcg_fused": "k_pcg_fused"}
+NCU_NAMES = {"pcg_div": "k_div3q", "pcg_gradt": "k_gradt3<8, 2>", "dssum": "k_gs_sum", "pcg_update": "k_pcg_update",
+             "hcg_axhelm": "k_axhelm3p", "hcg_update": "k_hcg_update", "pcg_pc_apply": "k_pm_apply2", "pcg_fused": "k_pcg_fused_p"}
 
 
 def ncu_traffic(kernel_kind):
@@ -164,12 +164,12 @@ def ncu_traffic(kernel_kind):
         with open(os.path.join(ROOT, "profiles", "ncu_dram_traffic.json")) as f:
             d = json.load(f)
         meta = d.get("_meta", {})
-        key = next(k for k in d if k.startswith(NCU_NAMES[kernel_kind]))
-        rec = d[key][0]
-        mult = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}.get(rec.get("unit", "Mbyte"), 1e6)
-        src = {"report": meta.get("report"), "source_hash": meta.get("source_hash"),
+        key = next(k for k in d if k != "_meta" and k.startswith(NCU_NAMES[kernel_kind]))
+        recs = d[key]
+        nbytes = float(np.median([r["dram_bytes"] for r in recs]))
+        src = {"report": meta.get("report"), "source_hash": meta.get("source_hash"), "kernel": key, "launches_in_capture": len(recs),
                "stale": meta.get("source_hash") not in (None, kernel_source_hash())}
-        return (rec["dram_read"] + rec["dram_write"]) * mult, src
+        return nbytes, src
     except Exception:
         return None, None
 

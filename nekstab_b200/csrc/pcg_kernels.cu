@@ -92,7 +92,7 @@ __device__ __forceinline__ void apply2_store(const double* __restrict__ M1, cons
 // vertex-mesh part (trilinear interpolation of the element's 8 corner values) and the aggregate value are added here; in this mode the
 // argument `xv` is the per-element table xc[nel][9] (k_pm_corner_values) and `x2` the table of hat-function values at the GL points.
 template <int N, int MODE>
-__global__ void __launch_bounds__(PK_TPB, 4)      // 40 registers: FOUR CTAs per SM (r2: MODE 2 at 54 registers / 3 CTAs per SM cost 0.03 ms)
+__global__ void __launch_bounds__(PK_TPB, 3)      // MODE 0/1: 36-40 registers (4 CTAs per SM fit); MODE 2: 54 registers, 3 CTAs per SM
 k_gradt3(const double* __restrict__ p, double* __restrict__ w, const double* __restrict__ RW2,
          const double* __restrict__ dinvE, double* __restrict__ pdir, const CGState* __restrict__ cgs, long long n,
          long long n2, const double* __restrict__ xv, const int* __restrict__ vid, const double* __restrict__ x2,
@@ -202,19 +202,17 @@ k_gradt3(const double* __restrict__ p, double* __restrict__ w, const double* __r
   }
   __syncthreads();
   // ---- t stage: w_c = J12^T sb[c*2] + D12^T sb[c*2+1], stored straight to global memory (coalesced in (j,i))
-  //      Every column is shared by two threads (outputs k < N/2 and k >= N/2): 6 N^2 = 384 equal tasks instead of 192 tasks of twice
-  //      the length with half the CTA waiting at the exit (r2 ncu: barrier stalls 6.7 warps per issue, 48 % of the warp slots active).
-  static_assert(6 * C2::ncol <= TPB && N % 2 == 0, "one task per thread");
-  if (tid < 6 * C2::ncol) {
-    const int half = tid / (3 * C2::ncol), t = tid - half * 3 * C2::ncol;
+  //      (r2, measured: sharing every column between two threads -- 384 equal tasks instead of 192 -- balanced the stage but doubled
+  //      its shared-memory loads; the kernel is LSU-bound and got 9 % slower: 0.173 -> 0.189 ms.  Not kept.)
+  static_assert(3 * C2::ncol <= TPB, "one task per thread");
+  if (tid < 3 * C2::ncol) {
+    const int t = tid;
     const int c = t / C2::ncol, col = t - c * C2::ncol;
     const int bi = C2::base(col);
     double v[N2], v2[N2];
 #pragma unroll
     for (int l = 0; l < N2; ++l) { v[l] = sb[c * 2][bi + l * C2::stride]; v2[l] = sb[c * 2 + 1][bi + l * C2::stride]; }
-    double* po = w + (long long)c * n + e1 + col + (long long)half * (N / 2) * N * N;
-    if (half == 0) apply2_store<N / 2, N2>(cm.J12t, v, cm.D12t, v2, po, N * N);
-    else apply2_store<N / 2, N2>(cm.J12t + (N / 2) * N2, v, cm.D12t + (N / 2) * N2, v2, po, N * N);
+    apply2_store<N, N2>(cm.J12t, v, cm.D12t, v2, w + (long long)c * n + e1 + col, N * N);
   }
 }
 
@@ -418,16 +416,13 @@ __device__ __noinline__ double div3q_element(const DivQArgs* __restrict__ A, dou
   const double* inrw = stg + 4 * NP1;
   const double pd = (tid < NP2) ? A->pdir[(long long)e * NP2 + tid] : 0.0;      // needed in the final stage only: latency hidden
   mbar_wait(&bar[0], parity);
-  // t stage: every column is shared by two threads (the J12 and the D12 product): 6 N^2 = 384 equal tasks instead of 192 tasks of
-  // twice the length with half the CTA waiting at the barrier (r2 ncu: barrier stalls 7.6 warps per issue)
-  if (tid < 6 * C2::ncol) {
-    const int which = tid / (3 * C2::ncol), t = tid - which * 3 * C2::ncol;
-    const int c = t / C2::ncol, col = t - c * C2::ncol;
+  if (tid < 3 * C2::ncol) {
+    const int c = tid / C2::ncol, col = tid - c * C2::ncol;
     double v[N];
 #pragma unroll
     for (int l = 0; l < N; ++l) v[l] = stg[c * NP1 + l * N * N + col] * inmb[l * N * N + col];
-    if (which == 0) apply_store<N2, N>(cm.J12, v, sa + (c * 2) * SA::size + C2::base(col), C2::stride);
-    else apply_store<N2, N>(cm.D12, v, sa + (c * 2 + 1) * SA::size + C2::base(col), C2::stride);
+    apply_store<N2, N>(cm.J12, v, sa + (c * 2) * SA::size + C2::base(col), C2::stride);
+    apply_store<N2, N>(cm.D12, v, sa + (c * 2 + 1) * SA::size + C2::base(col), C2::stride);
   }
   __syncthreads();                                   // half A consumed
   if (tid == 0 && e_next >= 0) div3q_issue_a<N>(A, stg, &bar[0], e_next);

@@ -91,8 +91,8 @@ __device__ __forceinline__ void apply2_store(const double* __restrict__ M1, cons
 // three-level preconditioner of pmg.cu in its fused form: `p` holds the element-block part zloc of z = M^-1 r (k_pcg_fused); the Q1
 // vertex-mesh part (trilinear interpolation of the element's 8 corner values) and the aggregate value are added here; in this mode the
 // argument `xv` is the per-element table xc[nel][9] (k_pm_corner_values) and `x2` the table of hat-function values at the GL points.
-template <int N, int MODE>
-__global__ void __launch_bounds__(PK_TPB, 3)      // MODE 0/1: 36-40 registers (4 CTAs per SM fit); MODE 2: 54 registers, 3 CTAs per SM
+template <int N, int MODE, int MINB = 3>
+__global__ void __launch_bounds__(PK_TPB, MINB)   // MODE 0/1: 36-40 registers (4 CTAs per SM fit); MODE 2: 54 registers at MINB = 3, 40 at MINB = 4
 k_gradt3(const double* __restrict__ p, double* __restrict__ w, const double* __restrict__ RW2,
          const double* __restrict__ dinvE, double* __restrict__ pdir, const CGState* __restrict__ cgs, long long n,
          long long n2, const double* __restrict__ xv, const int* __restrict__ vid, const double* __restrict__ x2,
@@ -858,8 +858,14 @@ int pk_pcg_dir_gradt(Ctx* c, int adj) {
   const double* zscale = c->pc_kind ? c->ones2 : c->dinvE[adj];
   if (c->pc_kind == 1 && c->pcg_fused) {          // fused preconditioner: pz holds the element-block part, the coarse parts are added here
     const PMG& m = c->pmg[(adj && c->has_adj_masks) ? 1 : 0];
-    DISPATCH_N(c, k_gradt3<N, 2><<<c->nel, PK_TPB, 0, c->stream>>>(c->pz, c->wk[2], c->RW2, nullptr, c->pk[2], c->cgs + 3, c->n, c->n2,
-                                                                m.xc, nullptr, m.hat, nullptr, c->pk[1]));
+    static const bool lb4 = [] { const char* e = getenv("NSB_GRADT_LB"); return e && e[0] == '4'; }();   // A/B switch (r2 final batch)
+    if (lb4) {
+      DISPATCH_N(c, (k_gradt3<N, 2, 4><<<c->nel, PK_TPB, 0, c->stream>>>(c->pz, c->wk[2], c->RW2, nullptr, c->pk[2], c->cgs + 3, c->n, c->n2,
+                                                                      m.xc, nullptr, m.hat, nullptr, c->pk[1])));
+    } else {
+      DISPATCH_N(c, (k_gradt3<N, 2, 3><<<c->nel, PK_TPB, 0, c->stream>>>(c->pz, c->wk[2], c->RW2, nullptr, c->pk[2], c->cgs + 3, c->n, c->n2,
+                                                                      m.xc, nullptr, m.hat, nullptr, c->pk[1])));
+    }
     nsb_count_launch();
     NSB_CUDA(cudaGetLastError());
     return 0;

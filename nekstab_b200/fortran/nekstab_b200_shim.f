@@ -202,6 +202,13 @@
       if (.not. init) then
 !        prepare_linearized_solver, core/matvec.f:1-52,115-118
          call nsb_b200_check(nsb_set_baseflow(ubase, vbase, wbase), 'nsb_set_baseflow')
+!        Floquet (uparam(1) = 3.11 / 3.21, core/matvec.f:192,278): ifbase co-evolution + orbit storage on the device;
+!        the co-evolving base flow feels the DNS branch of nekStab_forcing (core/utils.f:166-171)
+         if (uparam(1) .eq. 3.11 .or. uparam(1) .eq. 3.21) then
+            if (spng_str .ne. 0) call nsb_b200_check(nsb_set_dns_sponge(spng_str, spng_vr(1,1), spng_vr(1,2),
+     $           spng_vr(1,ndim)), 'nsb_set_dns_sponge')
+            call nsb_b200_check(nsb_set_floquet(1, pr), 'nsb_set_floquet')
+         endif
          call nsb_b200_check(nsb_prepare_linearized_solver(param(10), param(26), ddt, nst, ct),
      $        'prepare_linearized_solver')
          dt = ddt

@@ -1119,51 +1119,28 @@ int ek_pcg_div(Ctx* c, int adj) {
 
 template <int D, int N, int ADJ>
 static int launch_advab(Ctx* c, const double* up, const double* ub, const double* spng, double* f) {
-  using A = AdvSmem<D, N>;
-  static const int gen = [] { const char* e = getenv("NSB_ADV_GEN"); return (e && e[0] == '1') ? 1 : 2; }();
-  if constexpr (D == 3) {
-    if (gen == 2) {
-      using A2 = Adv2<N>;
-      const size_t smem2 = (size_t)A2::TOTAL * sizeof(double);
-      static bool attr2 = false;
-      if (!attr2) {
-        NSB_CUDA(cudaFuncSetAttribute(k_advab2<N, ADJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-        attr2 = true;
-      }
-      k_advab2<N, ADJ><<<c->nel, A2::NT, smem2, c->stream>>>(up, ub, c->Rd, c->bm1, spng, f, c->n, c->nd);
-      return 0;
+  if constexpr (D == 3) {          // plane-streaming second generation (r1d: 11.4 -> 2.65 ms; the first-generation 3-D path was removed in r2)
+    using A2 = Adv2<N>;
+    const size_t smem2 = (size_t)A2::TOTAL * sizeof(double);
+    static bool attr2 = false;
+    if (!attr2) {
+      NSB_CUDA(cudaFuncSetAttribute(k_advab2<N, ADJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      attr2 = true;
     }
-  }
-  static const bool scr_env = [] { const char* e = getenv("NSB_ADV_SCRATCH"); return !(e && e[0] == '0'); }();
-  if (D == 3 && scr_env) {
-    const size_t smem = (size_t)A::work * sizeof(double);
-    static int grid = 0;
-    if (!grid) {
-      NSB_CUDA(cudaFuncSetAttribute(k_advab<D, N, ADJ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      int per_sm = 0, sms = 148;
-      NSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_advab<D, N, ADJ, true>, 256, smem));
-      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-      grid = std::max(1, per_sm) * sms;
+    k_advab2<N, ADJ><<<c->nel, A2::NT, smem2, c->stream>>>(up, ub, c->Rd, c->bm1, spng, f, c->n, c->nd);
+    return 0;
+  } else {                         // 2-D: first-generation kernel (correctness path of the shipped 2-D configs)
+    using A = AdvSmem<D, N>;
+    size_t smem = (size_t)(A::work + (ADJ ? A::fine_adj : (A::fine_direct + Cfg<D, N>::NPD))) * sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set) {
+      NSB_CUDA(cudaFuncSetAttribute(k_advab<D, N, ADJ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_set = true;
     }
-    const int g = std::min(grid, c->nel);
-    const size_t need = (size_t)g * 3 * D * Cfg<D, N>::NPD;
-    if (c->adv_scratch_words < need) {
-      if (c->adv_scratch) cudaFree(c->adv_scratch);
-      NSB_CUDA(cudaMalloc(&c->adv_scratch, need * sizeof(double)));
-      c->adv_scratch_words = need;
-    }
-    k_advab<D, N, ADJ, true><<<g, 256, smem, c->stream>>>(up, ub, c->Rd, c->bm1, spng, f, c->n, c->nd, c->adv_scratch, c->nel);
+    k_advab<D, N, ADJ, false><<<c->nel, Cfg<D, N>::TPB_ADV, smem, c->stream>>>(up, ub, c->Rd, c->bm1, spng, f, c->n, c->nd, nullptr,
+                                                                              c->nel);
     return 0;
   }
-  size_t smem = (size_t)(A::work + (ADJ ? A::fine_adj : (A::fine_direct + Cfg<D, N>::NPD))) * sizeof(double);
-  static bool attr_set = false;
-  if (!attr_set) {
-    NSB_CUDA(cudaFuncSetAttribute(k_advab<D, N, ADJ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
-  k_advab<D, N, ADJ, false><<<c->nel, Cfg<D, N>::TPB_ADV, smem, c->stream>>>(up, ub, c->Rd, c->bm1, spng, f, c->n, c->nd, nullptr,
-                                                                            c->nel);
-  return 0;
 }
 
 int ek_advab(Ctx* c, int adjoint, const double* up, const double* ub, const double* spng, double* f) {

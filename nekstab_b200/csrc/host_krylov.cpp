@@ -326,7 +326,10 @@ extern "C" int nsb_newton_krylov(int q_slot, int f_slot, int dq_slot, int work_s
   for (it = 1; it <= maxiter_newton; ++it) {
     double dt = 0, ct = 0;
     int nsteps = 0;
-    NSB_TRY(nsb_prepare_solver_from_slot(q_slot, end_time, cfl_target, &dt, &nsteps, &ct));   // :69
+    // :69.  The reference's prepare_linearized_solver takes the CFL of whatever Nek holds in vx,vy,vz: the initial q at iteration 1, from
+    // iteration 2 on the base flow of the LAST matvec (= the previous iterate, core/matvec.f:103).  Here it is the CURRENT iterate; the
+    // two differ by the Newton update, i.e. they can give a different integer nsteps only far from convergence.
+    NSB_TRY(nsb_prepare_solver_from_slot(q_slot, end_time, cfl_target, &dt, &nsteps, &ct));
     NSB_TRY(nsb_nonlinear_forward_map(q_slot, f_slot));                                        // :90
     calls_counter += nsteps;
     NSB_TRY(nsb_vec_norm(f_slot, &residual));

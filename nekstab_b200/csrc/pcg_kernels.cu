@@ -91,8 +91,8 @@ __device__ __forceinline__ void apply2_store(const double* __restrict__ M1, cons
 // three-level preconditioner of pmg.cu in its fused form: `p` holds the element-block part zloc of z = M^-1 r (k_pcg_fused); the Q1
 // vertex-mesh part (trilinear interpolation of the element's 8 corner values) and the aggregate value are added here; in this mode the
 // argument `xv` is the per-element table xc[nel][9] (k_pm_corner_values) and `x2` the table of hat-function values at the GL points.
-template <int N, int MODE, int MINB = 3>
-__global__ void __launch_bounds__(PK_TPB, MINB)   // MODE 0/1: 36-40 registers (4 CTAs per SM fit); MODE 2: 54 registers at MINB = 3, 40 at MINB = 4
+template <int N, int MODE>
+__global__ void __launch_bounds__(PK_TPB, 3)      // MODE 0/1: 36-40 registers (4 CTAs per SM fit); MODE 2: 54 registers, 3 CTAs per SM
 k_gradt3(const double* __restrict__ p, double* __restrict__ w, const double* __restrict__ RW2,
          const double* __restrict__ dinvE, double* __restrict__ pdir, const CGState* __restrict__ cgs, long long n,
          long long n2, const double* __restrict__ xv, const int* __restrict__ vid, const double* __restrict__ x2,
@@ -858,14 +858,9 @@ int pk_pcg_dir_gradt(Ctx* c, int adj) {
   const double* zscale = c->pc_kind ? c->ones2 : c->dinvE[adj];
   if (c->pc_kind == 1 && c->pcg_fused) {          // fused preconditioner: pz holds the element-block part, the coarse parts are added here
     const PMG& m = c->pmg[(adj && c->has_adj_masks) ? 1 : 0];
-    static const bool lb4 = [] { const char* e = getenv("NSB_GRADT_LB"); return e && e[0] == '4'; }();   // A/B switch (r2 final batch)
-    if (lb4) {
-      DISPATCH_N(c, (k_gradt3<N, 2, 4><<<c->nel, PK_TPB, 0, c->stream>>>(c->pz, c->wk[2], c->RW2, nullptr, c->pk[2], c->cgs + 3, c->n, c->n2,
-                                                                      m.xc, nullptr, m.hat, nullptr, c->pk[1])));
-    } else {
-      DISPATCH_N(c, (k_gradt3<N, 2, 3><<<c->nel, PK_TPB, 0, c->stream>>>(c->pz, c->wk[2], c->RW2, nullptr, c->pk[2], c->cgs + 3, c->n, c->n2,
-                                                                      m.xc, nullptr, m.hat, nullptr, c->pk[1])));
-    }
+    // (r2 final batch, measured: the same kernel compiled for 4 CTAs per SM / 40 registers: 0.1764 vs 0.1758 ms -- no gain, not kept)
+    DISPATCH_N(c, k_gradt3<N, 2><<<c->nel, PK_TPB, 0, c->stream>>>(c->pz, c->wk[2], c->RW2, nullptr, c->pk[2], c->cgs + 3, c->n, c->n2,
+                                                                m.xc, nullptr, m.hat, nullptr, c->pk[1]));
     nsb_count_launch();
     NSB_CUDA(cudaGetLastError());
     return 0;
@@ -946,7 +941,7 @@ static int launch_axhelm3(Ctx* c, int mode, const double* u, double* w, const do
 }
 
 int pk_axhelm(Ctx* c, int mode, const double* u, double* w, const double* b, int nfields, double h1, double h2) {
-  static const bool pf = [] { const char* e = getenv("NSB_AX_PREFETCH"); return !(e && e[0] == '0'); }();
+  const bool pf = true;      // G and bm1 prefetched with cp.async (r1d: 0.580 -> 0.563 ms); the non-prefetching instantiation is gone
   if (mode == 2 && nfields == 3 && c->ax_persistent && c->lx1 == 8) {      // Helmholtz-CG head: persistent, TMA-pipelined (lx1 = 8: 112 KB per CTA)
     constexpr int N = 8;
     AxPArgs a{c->rk, c->dinvH, c->G, c->bm1, c->wk[1], c->wk[2], c->n, h1, h2, perm_h_active(c) ? 1 : 0};
@@ -957,8 +952,8 @@ int pk_axhelm(Ctx* c, int mode, const double* u, double* w, const double* b, int
     NSB_CUDA(cudaGetLastError());
     return 0;
   }
-  if (pf) DISPATCH_N(c, NSB_TRY((launch_axhelm3<N, true>(c, mode, u, w, b, nfields, h1, h2))));
-  else DISPATCH_N(c, NSB_TRY((launch_axhelm3<N, false>(c, mode, u, w, b, nfields, h1, h2))));
+  (void)pf;
+  DISPATCH_N(c, NSB_TRY((launch_axhelm3<N, true>(c, mode, u, w, b, nfields, h1, h2))));
   nsb_count_launch();
   NSB_CUDA(cudaGetLastError());
   return 0;

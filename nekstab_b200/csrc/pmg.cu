@@ -1236,8 +1236,7 @@ int pm_pcg_tail(Ctx* c, int set, int init, int prof_slot) {
   CGState* sp = c->cgs + 3;
   double* sc = m.ra + m.nagg;
   const bool multi = c->nranks > 1;
-  static const bool pers = [] { const char* e = getenv("NSB_PCG_FUSED_P"); return !(e && e[0] == '0'); }();
-  if (pers && c->ldim == 3 && c->lx2 == 6) {               // persistent, TMA-pipelined (lx1 = 8)
+  if (c->ldim == 3 && c->lx2 == 6) {                       // persistent, TMA-pipelined (lx1 = 8); other orders: one group per CTA
     constexpr int L = 6;
     static bool attr = false;
     if (!attr) {

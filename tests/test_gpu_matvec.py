@@ -198,3 +198,17 @@ def test_step_callback():
         assert len(calls) == nsteps
     finally:
         g.close()
+
+
+def test_fallback_kernel_paths_through_the_environment_switches():
+    """The documented switches (README "Environment switches") select the generic kernels that are the ONLY path for other
+    configurations (2-D, lx1 != 8, unequal component masks): one-element-per-CTA axhelm / div, separate CG update + preconditioner
+    kernels, natural layout, no CUDA graphs.  Here they are forced on the 3-D lx1 = 8 case and must give the same matvec parity."""
+    import os
+    import subprocess
+    import sys
+    from util import ROOT
+    env = dict(os.environ, NSB_PERSISTENT="0", NSB_PCG_FUSED="0", NSB_AX_PERSISTENT="0", NSB_PERM="0", NSB_GRAPHS="0")
+    r = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], capture_output=True, text=True, timeout=600,
+                       env=env, cwd=ROOT)
+    assert r.returncode == 0 and r.stdout.count("rel err vs oracle") == 2, r.stdout[-1500:] + r.stderr[-1500:]

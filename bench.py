@@ -142,15 +142,17 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows), "how": self.how}
 
 
+KERNEL_FILES = ("elem_common.cuh", "elem_kernels.cu", "pcg_kernels.cu", "pmg.cu", "vec_kernels.cu", "gs.cu")
+
+
 def kernel_source_hash():
-    """sha1 of the CUDA sources the ncu traffic capture refers to (stamped into profiles/ncu_dram_traffic.json by
-    tools/ncu_summarise.py); a mismatch means the committed capture predates the current kernels."""
+    """sha1 of the CUDA files that hold the single-GPU kernels of the step (what the ncu captures profile); stamped into
+    profiles/ncu_dram_traffic.json by tools/ncu_summarise.py: a mismatch means the committed capture predates the current kernels."""
     h = hashlib.sha1()
     d = os.path.join(ROOT, "nekstab_b200", "csrc")
-    for f in sorted(os.listdir(d)):
-        if f.endswith((".cu", ".cuh", ".h", ".cpp")):
-            with open(os.path.join(d, f), "rb") as fh:
-                h.update(fh.read())
+    for f in KERNEL_FILES:
+        with open(os.path.join(d, f), "rb") as fh:
+            h.update(fh.read())
     return h.hexdigest()[:16]
 
 
@@ -625,7 +627,7 @@ def main():
         cfg.update({"dt": dt, "nsteps_per_matvec_T1": nsteps_full, "residual_projection_mxprev": args.mxprev,
                     "pres_iters_per_step": tm["pres_iters"] / K, "helm_iters_per_comp_per_step": tm["helm_iters"] / K / 3,
                     "l2": "per-iteration working set (2 GB) >> L2 (126 MB): no flush needed", "parallelism": f"elements/{world}",
-                    "timing": "sampling profiler off, CUDA-graph replay " + ("on" if world == 1 else "off (multi-rank)"),
+                    "timing": "sampling profiler off, CUDA-graph replay on" + ("" if world == 1 or plane == "p2p" else " for single-rank only (NCCL data plane)"),
                     "setup_s": t_setup, "wall_s_timed": tm["wall_s"]})
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": tm["dev_ms"] / K,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,

@@ -627,7 +627,8 @@ def main():
         cfg.update({"dt": dt, "nsteps_per_matvec_T1": nsteps_full, "residual_projection_mxprev": args.mxprev,
                     "pres_iters_per_step": tm["pres_iters"] / K, "helm_iters_per_comp_per_step": tm["helm_iters"] / K / 3,
                     "l2": "per-iteration working set (2 GB) >> L2 (126 MB): no flush needed", "parallelism": f"elements/{world}",
-                    "timing": "sampling profiler off, CUDA-graph replay on" + ("" if world == 1 or plane == "p2p" else " for single-rank only (NCCL data plane)"),
+                    "timing": "sampling profiler off, CUDA-graph replay " + ("on" if os.environ.get("NSB_GRAPHS", "1") != "0" and (world == 1 or plane == "p2p")
+                                                                             else "off" + (" (NCCL data plane)" if world > 1 and plane != "p2p" else "")),
                     "setup_s": t_setup, "wall_s_timed": tm["wall_s"]})
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": tm["dev_ms"] / K,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,

@@ -91,7 +91,7 @@ struct P2P {
   int* d_send_nbr = nullptr;
   int* d_send_j = nullptr;
   int* d_err = nullptr;
-  unsigned long long epoch_halo = 0, epoch_red = 0;
+  unsigned long long* d_epoch = nullptr;         // device-resident exchange counters: [0] halo, [1] all-reduce
 };
 
 // Three-level additive pressure preconditioner (pmg.cu), one instance per mask set (direct / adjoint)

@@ -9,7 +9,8 @@
 //     every arena, raises a flag, waits for all flags and adds the slots in rank order; for the CG loops the scalar
 //     update (alpha, beta, convergence flag) happens in the same one-CTA kernel.
 // Replaces grouped ncclSend/ncclRecv + ncclAllReduce (two host-enqueued collectives and two extra kernels per pressure
-// iteration) by remote stores issued from the producing kernels.  Flow control: two parity copies of every buffer; a rank
+// iteration) by remote stores issued from the producing kernels.  The exchange counters (epochs) live in device memory, so no kernel
+// argument changes between exchanges and whole CG batches replay as CUDA graphs on every rank.  Flow control: two parity copies of every buffer; a rank
 // can never be more than one exchange ahead of a rank it exchanges with, because each exchange needs the partner's
 // data of the same epoch.  Every spin-wait has a time-out that raises an error flag instead of hanging the GPU.
 #include <algorithm>
@@ -51,7 +52,7 @@ int p2p_free(Ctx* c, P2P& p) {
   for (int r = 0; r < c->nranks; ++r)
     if (r != c->rank && p.peer[r]) cudaIpcCloseMemHandle(p.peer[r]);
   cudaFree(p.arena); cudaFree(p.d_peer_dst); cudaFree(p.d_peer_flag); cudaFree(p.d_nbr_rank); cudaFree(p.d_err);
-  cudaFree(p.d_send_nbr); cudaFree(p.d_send_j); cudaFree(p.d_cnt); cudaFree(p.d_peer_base);
+  cudaFree(p.d_send_nbr); cudaFree(p.d_send_j); cudaFree(p.d_cnt); cudaFree(p.d_peer_base); cudaFree(p.d_epoch);
   p = P2P();
   return 0;
 }
@@ -154,6 +155,8 @@ int p2p_setup(Ctx* c, P2P& p, const GSMap& m, const std::vector<int>& send_nbr, 
   }
   NSB_CUDA(cudaMalloc(&p.d_err, 4 * sizeof(int)));
   NSB_CUDA(cudaMemset(p.d_err, 0, 4 * sizeof(int)));
+  NSB_CUDA(cudaMalloc(&p.d_epoch, 2 * sizeof(unsigned long long)));       // [0] halo, [1] all-reduce exchange counters
+  NSB_CUDA(cudaMemset(p.d_epoch, 0, 2 * sizeof(unsigned long long)));
   // peer table of arena bases for the all-reduce kernel
   NSB_CUDA(cudaMalloc(&p.d_peer_base, 16 * sizeof(double*)));
   NSB_CUDA(cudaMemcpy(p.d_peer_base, p.peer, 16 * sizeof(double*), cudaMemcpyHostToDevice));
@@ -169,13 +172,20 @@ int p2p_setup(Ctx* c, P2P& p, const GSMap& m, const std::vector<int>& send_nbr, 
 }
 
 // ------------------------------------------------------------------------------------------------ halo
+// The epoch of every exchange lives in DEVICE memory (ep[0]: halo, ep[1]: all-reduce): the first kernel of an exchange uses ep + 1 and
+// its last CTA stores it back, the consumer kernel reads the stored value.  No kernel argument changes from one exchange to the next,
+// so whole CG batches can be captured in a CUDA graph and replayed on several ranks (r2; r1 passed the epoch as an argument).
 template <int NF>
 __global__ void k_gs_pack_p2p(int nshared, const int* __restrict__ send_seg, const int* __restrict__ send_nbr,
                               const int* __restrict__ send_j, const int* __restrict__ nbr_cnt, const int* __restrict__ seg_off,
                               const int* __restrict__ seg_idx, const double* __restrict__ u, long long stride,
-                              double* const* __restrict__ peer_dst, unsigned long long* const* __restrict__ peer_flag, int nnbr,
-                              unsigned long long epoch, unsigned* counter, const CGState* skip) {
+                              double* const* __restrict__ peer_dst2, unsigned long long* const* __restrict__ peer_flag2, int nnbr,
+                              unsigned long long* ep, unsigned* counter, const CGState* skip) {
   if (skip && skip->done) return;
+  const unsigned long long epoch = *(volatile unsigned long long*)ep + 1;   // read HERE, before this CTA arrives at the counter below
+  const int par = (int)(epoch & 1);
+  double* const* peer_dst = peer_dst2 + par * nnbr;
+  unsigned long long* const* peer_flag = peer_flag2 + par * nnbr;
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s < nshared) {
     const int seg = send_seg[s];
@@ -202,9 +212,12 @@ __global__ void k_gs_pack_p2p(int nshared, const int* __restrict__ send_seg, con
     s_last = (t == gridDim.x - 1);
   }
   __syncthreads();
-  if (s_last && threadIdx.x < nnbr) {
-    __threadfence_system();
-    st_flag(peer_flag[threadIdx.x], epoch);
+  if (s_last) {
+    if (threadIdx.x < nnbr) {
+      __threadfence_system();
+      st_flag(peer_flag[threadIdx.x], epoch);
+    }
+    if (threadIdx.x == 0) ep[0] = epoch;                 // every CTA has read ep[0] before arriving at the counter
   }
 }
 
@@ -235,9 +248,14 @@ template <int NF>
 __global__ void k_gs_sum_p2p(int nseg, const int* __restrict__ seg_off, const int* __restrict__ seg_idx,
                              const int* __restrict__ rseg_off, const int* __restrict__ rseg_pos, const int* __restrict__ rseg_cnt,
                              const int* __restrict__ rseg_nbefore, const double* __restrict__ recvbuf, double* __restrict__ u,
-                             long long stride, const unsigned long long* __restrict__ flags, const int* __restrict__ nbr_rank,
-                             int nnbr, unsigned long long epoch, int* err, const CGState* skip, int seg0) {
+                             long long stride, const unsigned long long* __restrict__ flags2, const int* __restrict__ nbr_rank,
+                             int nnbr, const unsigned long long* ep, long long halo_stride, int nranks, int* err,
+                             const CGState* skip, int seg0) {
   if (skip && skip->done) return;
+  const unsigned long long epoch = *(const volatile unsigned long long*)ep;   // stored by the pack kernel of this exchange
+  const int par = (int)(epoch & 1);
+  recvbuf += (long long)par * halo_stride;              // parity copy of the halo block and of its flags
+  const unsigned long long* flags = flags2 + (long long)par * nranks;
   __shared__ int ok;
   if (threadIdx.x == 0) ok = 1;
   __syncthreads();
@@ -279,12 +297,10 @@ static int dssum_p2p_nf(Ctx* c, P2P& p, GSMap& m, double* u, long long stride, c
   const int* d_send_seg = m.send_seg;
   const int* d_rseg_cnt = m.rseg_cnt;
   const int T = 128, R = c->nranks;
-  const unsigned long long epoch = ++p.epoch_halo;
-  const int par = (int)(epoch & 1);
   if (m.nshared > 0) {
     k_gs_pack_p2p<NF><<<(m.nshared + T - 1) / T, T, 0, c->stream>>>(m.nshared, d_send_seg, p.d_send_nbr, p.d_send_j, p.d_cnt, m.seg_off,
-                                                                   m.seg_idx, u, stride, p.d_peer_dst + par * m.nnbr,
-                                                                   p.d_peer_flag + par * m.nnbr, m.nnbr, epoch, c->red_count + 2, skip);
+                                                                   m.seg_idx, u, stride, p.d_peer_dst, p.d_peer_flag, m.nnbr, p.d_epoch,
+                                                                   c->red_count + 2, skip);
     nsb_count_launch();
   }
   // interior segments (no copy on another rank) are summed while the partial sums travel over NVLink ...
@@ -294,12 +310,12 @@ static int dssum_p2p_nf(Ctx* c, P2P& p, GSMap& m, double* u, long long stride, c
   }
   // ... and only the shared segments wait for the neighbours' flags
   if (m.nseg > m.nseg_int) {
-    const double* recv = p.arena + off_halo(R) + par * p.halo_stride;
-    const unsigned long long* flags = (const unsigned long long*)(p.arena + off_haloflag(par, 0, R));
+    const double* recv = p.arena + off_halo(R);                                                     // parity 0; the kernel adds par * stride
+    const unsigned long long* flags = (const unsigned long long*)(p.arena + off_haloflag(0, 0, R));
     const int ns = m.nseg - m.nseg_int;
     k_gs_sum_p2p<NF><<<(ns + T - 1) / T, T, 0, c->stream>>>(m.nseg, m.seg_off, m.seg_idx, m.rseg_off, m.rseg_pos, d_rseg_cnt,
-                                                           m.rseg_nbefore, recv, u, stride, flags, p.d_nbr_rank, m.nnbr, epoch,
-                                                           p.d_err, skip, m.nseg_int);
+                                                           m.rseg_nbefore, recv, u, stride, flags, p.d_nbr_rank, m.nnbr, p.d_epoch,
+                                                           p.halo_stride, R, p.d_err, skip, m.nseg_int);
     nsb_count_launch();
   }
   NSB_CUDA(cudaGetLastError());
@@ -349,10 +365,16 @@ __device__ void cg_apply(CGState* s, const double* sums, int ncomp, int kind) {
 
 // one CTA; op 0: sum, 1: max.  vals (count <= RSLOT) are reduced in place over all ranks, in rank order.
 __global__ void k_p2p_allreduce(double* vals, int count, int op, double* const* __restrict__ peer_base, double* arena, int rank,
-                                int nranks, int parity, unsigned long long epoch, long long slot_off, long long flag_off,
-                                int* err, CGState* cgs, int ncomp, int kind, const CGState* skip) {
+                                int nranks, unsigned long long* ep, int* err, CGState* cgs, int ncomp, int kind, const CGState* skip) {
   if (skip && skip->done) return;
   __shared__ int ok;
+  __shared__ unsigned long long s_epoch;
+  if (threadIdx.x == 0) { s_epoch = ep[1] + 1; ep[1] = s_epoch; }        // one CTA: the epoch of this exchange
+  __syncthreads();
+  const unsigned long long epoch = s_epoch;
+  const int parity = (int)(epoch & 1);
+  const long long slot_off = ((long long)parity * nranks) * RSLOT;                       // off_red(parity, 0, nranks)
+  const long long flag_off = 2LL * nranks * RSLOT + (long long)parity * nranks;          // off_redflag(parity, 0, nranks)
   if (threadIdx.x == 0) ok = 1;
   // 1) publish my values in slot [rank] of every arena
   for (int i = threadIdx.x; i < count * nranks; i += blockDim.x) {
@@ -390,8 +412,11 @@ __global__ void k_p2p_allreduce(double* vals, int count, int op, double* const* 
 // pushes this rank's values into peer b's slot and the last CTA to finish raises the flags; the second kernel waits for the peers'
 // flags and adds the slots in rank order with one thread per value.
 __global__ void __launch_bounds__(512) k_p2p_ar_publish(const double* __restrict__ vals, int count, double* const* __restrict__ peer_base,
-                                                        int rank, int nranks, unsigned long long epoch, long long slot_off,
-                                                        long long flag_off, unsigned* counter) {
+                                                        int rank, int nranks, unsigned long long* ep, unsigned* counter) {
+  const unsigned long long epoch = *((volatile unsigned long long*)ep + 1) + 1;   // read HERE, before this CTA arrives at the counter
+  const int parity = (int)(epoch & 1);
+  const long long slot_off = ((long long)parity * nranks) * RSLOT;
+  const long long flag_off = 2LL * nranks * RSLOT + (long long)parity * nranks;
   double* dst = peer_base[blockIdx.x] + slot_off + (long long)rank * RSLOT;
   for (int k = threadIdx.x; k < count; k += blockDim.x) dst[k] = vals[k];          // remote stores over NVLink (local for b == rank)
   __threadfence_system();
@@ -402,14 +427,20 @@ __global__ void __launch_bounds__(512) k_p2p_ar_publish(const double* __restrict
     s_last = (t == gridDim.x - 1);
   }
   __syncthreads();
-  if (s_last && threadIdx.x < nranks) {
-    __threadfence_system();
-    st_flag((unsigned long long*)(peer_base[threadIdx.x] + flag_off + rank), epoch);
+  if (s_last) {
+    if (threadIdx.x < nranks) {
+      __threadfence_system();
+      st_flag((unsigned long long*)(peer_base[threadIdx.x] + flag_off + rank), epoch);
+    }
+    if (threadIdx.x == 0) ep[1] = epoch;
   }
 }
 __global__ void __launch_bounds__(256) k_p2p_ar_combine(double* __restrict__ vals, int count, int op, const double* __restrict__ arena,
-                                                        int nranks, unsigned long long epoch, long long slot_off, long long flag_off,
-                                                        int* err) {
+                                                        int nranks, const unsigned long long* ep, int* err) {
+  const unsigned long long epoch = *((const volatile unsigned long long*)ep + 1);   // stored by the publish kernel of this exchange
+  const int parity = (int)(epoch & 1);
+  const long long slot_off = ((long long)parity * nranks) * RSLOT;
+  const long long flag_off = 2LL * nranks * RSLOT + (long long)parity * nranks;
   __shared__ int ok;
   if (threadIdx.x == 0) ok = 1;
   __syncthreads();
@@ -433,12 +464,8 @@ int p2p_allreduce(Ctx* c, double* dev, int count, int op, CGState* cgs, int ncom
   if (!cgs && count > 64) {
     for (int done = 0; done < count; done += RSLOT) {
       const int cnt = std::min(RSLOT, count - done);
-      const unsigned long long epoch = ++p.epoch_red;
-      const int par = (int)(epoch & 1);
-      k_p2p_ar_publish<<<R, 512, 0, c->stream>>>(dev + done, cnt, p.d_peer_base, c->rank, R, epoch, off_red(par, 0, R),
-                                                 off_redflag(par, 0, R), c->red_count + 3);
-      k_p2p_ar_combine<<<(cnt + 255) / 256, 256, 0, c->stream>>>(dev + done, cnt, op, p.arena, R, epoch, off_red(par, 0, R),
-                                                                off_redflag(par, 0, R), p.d_err);
+      k_p2p_ar_publish<<<R, 512, 0, c->stream>>>(dev + done, cnt, p.d_peer_base, c->rank, R, p.d_epoch, c->red_count + 3);
+      k_p2p_ar_combine<<<(cnt + 255) / 256, 256, 0, c->stream>>>(dev + done, cnt, op, p.arena, R, p.d_epoch, p.d_err);
       nsb_count_launch(2);
     }
     NSB_CUDA(cudaGetLastError());
@@ -446,11 +473,8 @@ int p2p_allreduce(Ctx* c, double* dev, int count, int op, CGState* cgs, int ncom
   }
   for (int done = 0; done < count; done += RSLOT) {
     const int cnt = std::min(RSLOT, count - done);
-    const unsigned long long epoch = ++p.epoch_red;
-    const int par = (int)(epoch & 1);
-    k_p2p_allreduce<<<1, 256, 0, c->stream>>>(dev + done, cnt, op, p.d_peer_base, p.arena, c->rank, R, par, epoch, off_red(par, 0, R),
-                                              off_redflag(par, 0, R), p.d_err, (done + RSLOT >= count) ? cgs : nullptr, ncomp, kind,
-                                              nullptr);
+    k_p2p_allreduce<<<1, 256, 0, c->stream>>>(dev + done, cnt, op, p.d_peer_base, p.arena, c->rank, R, p.d_epoch, p.d_err,
+                                              (done + RSLOT >= count) ? cgs : nullptr, ncomp, kind, nullptr);
     nsb_count_launch();
   }
   NSB_CUDA(cudaGetLastError());

@@ -83,9 +83,14 @@ static void prof_collect(Ctx* c, const int* kinds, int nk, int first_slot) {
   }
 }
 
-// ---- CUDA-graph replay of one CG batch (single rank, profiler off).  The first batches of a context run un-captured so
+// ---- CUDA-graph replay of one CG batch (profiler off; multi-rank when the data plane is peer memory).  The first batches of a context run un-captured so
 //      that one-time function attributes are set outside any capture.
-static bool graphs_ok(Ctx* c) { return c->use_graphs && c->nranks == 1 && !c->prof_on && c->graph_warm; }
+static bool graphs_ok(Ctx* c) {
+  // multi-rank: every collective inside a batch must be a peer-memory kernel (device-resident epochs, csrc/p2p.cu); the NCCL fallback
+  // is enqueued from the host and is not captured
+  const bool all_p2p = c->p2p.on && (!c->gsv_ready || c->p2pv.on) && (!c->gsp_ready || c->p2pp.on);
+  return c->use_graphs && (c->nranks == 1 || all_p2p) && !c->prof_on && c->graph_warm;
+}
 template <class F>
 static int run_batch_graph(Ctx* c, Ctx::GraphEntry* ge, F&& batch) {
   if (!ge->exec) {

@@ -5,7 +5,7 @@ cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out
 ( time timeout 900 python -m pytest tests/test_gpu_multirank.py -x -q -s 2>&1 ) > gpurun_out/bg${N}_pytest.log 2>&1
 tail -4 gpurun_out/bg${N}_pytest.log
-for G in 1 0; do
+for G in ${GRAPH_MODES:-1 0}; do
   echo "== NSB_GRAPHS=$G"
   ( time NSB_GRAPHS=$G timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2961$G bench.py --gpus $N --steps 20 --warmup 5 --arnoldi 0 --no-cpu-baseline ) > gpurun_out/bg${N}_bench_g$G.json 2> gpurun_out/bg${N}_bench_g$G.err
   python - <<PY

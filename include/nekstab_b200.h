@@ -151,6 +151,20 @@ int nsb_matvec(int mode, int slot_in, int slot_out);
 typedef void (*nsb_step_callback)(int istep, double time, void* user);
 int nsb_set_step_callback(nsb_step_callback cb, void* user);
 int nsb_nonlinear_forward_map(int slot_q, int slot_f);
+/* Newton-GMRES for unstable periodic orbits (uparam(1) = 2.1).  With enable != 0:
+ *  - every slot carries the `time` member of type krylov_vector (core/krylov_subspace.f:8-15; nsb_vec_set_time / nsb_vec_get_time); it
+ *    follows copy / zero / cmult / add2 / sub2 / normalize / basis_gemv / basis_rotate / orthonormalize and enters
+ *    krylov_inner_product as p%time * q%time (core/krylov_subspace.f:47-50);
+ *  - nsb_nonlinear_forward_map stores the orbit uor, vor, wor(lv, nsteps) in device memory (core/newton_krylov.f:77-86, 364-368) and the two
+ *    border vectors compute_bvec(fc_nwt), compute_bvec(ic_nwt) = one first-order Navier-Stokes step, (q1 - q0)/dt (core/matvec.f:435-475);
+ *    the reference recomputes them in every matvec, here they are computed once per Newton iterate and stay resident;
+ *  - nsb_matvec(NSB_NEWTON) replays the orbit as the base flow of the linearised steps (core/matvec.f:187-199, 228-231) and returns
+ *    f = (exp(TL) - I) q + bvec(fc) * q%time, f%time = <bvec(ic), q> (core/matvec.f:397-419);
+ *  - nsb_newton_krylov treats end_time as the first guess of the period and updates it with the Newton correction
+ *    (core/newton_krylov.f:63-67, 122); read the period found with nsb_vec_get_time(q_slot). */
+int nsb_set_upo(int enable);
+int nsb_vec_set_time(int slot, double time);
+int nsb_vec_get_time(int slot, double* NSB_SCALAR time);
 /* prepare_linearized_solver evaluated on the velocity in `slot` (newton_krylov re-prepares on every iterate, :69). */
 int nsb_prepare_solver_from_slot(int slot, double end_time, double cfl_target, double* NSB_SCALAR dt, int* NSB_SCALAR nsteps, double* NSB_SCALAR ctarg);
 /* Adjoint problems may use different Dirichlet masks (outflow 'O' -> 'v', 1cyl.usr:126-132). NULL = same. */

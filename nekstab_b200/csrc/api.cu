@@ -464,6 +464,7 @@ extern "C" int nsb_vec_alloc(int nslots) {
   c->slab = nullptr;
   NSB_TRY(dalloc(&c->slab, (long long)nslots * c->vlen));
   c->nslots = nslots;
+  c->slot_time.assign(nslots, 0.0);
   return 0;
 }
 extern "C" int nsb_vec_upload(int slot, const double* vx, const double* vy, const double* vz, const double* pr) {
@@ -477,8 +478,30 @@ extern "C" int nsb_vec_upload(int slot, const double* vx, const double* vy, cons
   if (pr) NSB_TRY(h2d(c, v + c->ldim * c->n, pr, c->n2));
   else NSB_TRY(vk_fill(c, v + c->ldim * c->n, 0.0, c->n2));
   NSB_CUDA(cudaStreamSynchronize(c->stream));
+  c->slot_time[slot] = 0.0;
   return 0;
 }
+// q%time of a slot (core/krylov_subspace.f:14): the period unknown of the UPO Newton; part of the inner product only when nsb_set_upo(1)
+extern "C" int nsb_vec_set_time(int slot, double t) { REQUIRE_CTX(); CHECK_SLOT(slot); c->slot_time[slot] = t; return 0; }
+extern "C" int nsb_vec_get_time(int slot, double* t) {
+  REQUIRE_CTX(); CHECK_SLOT(slot);
+  if (!t) { nsb_set_error("nsb_vec_get_time: NULL output"); return 1; }
+  *t = c->slot_time[slot];
+  return 0;
+}
+// uparam(1) = 2.1 (Newton-GMRES for unstable periodic orbits): the time component enters krylov_inner_product (core/krylov_subspace.f:47-50),
+// nsb_nonlinear_forward_map keeps the orbit uor, vor, wor in HBM (core/newton_krylov.f:364-368) together with the two border vectors
+// of compute_bvec, and the Newton matvec adds the border terms (core/matvec.f:407-419).
+extern "C" int nsb_set_upo(int enable) {
+  REQUIRE_CTX();
+  c->upo = enable != 0;
+  c->bvec_ready = false;
+  c->orbit_ready = false;
+  if (!enable && c->bvec) { cudaFree(c->bvec); c->bvec = nullptr; }
+  if (!enable && !c->floquet && c->orbit) { cudaFree(c->orbit); c->orbit = nullptr; c->orbit_steps = 0; }
+  return 0;
+}
+bool upo_active() { return g_ctx && g_ctx->upo; }
 extern "C" int nsb_vec_download(int slot, double* vx, double* vy, double* vz, double* pr) {
   REQUIRE_CTX(); CHECK_SLOT(slot);
   double* v = slot_ptr(c, slot);
@@ -491,17 +514,27 @@ extern "C" int nsb_vec_download(int slot, double* vx, double* vy, double* vz, do
 extern "C" int nsb_vec_copy(int dst, int src) {
   REQUIRE_CTX(); CHECK_SLOT(dst); CHECK_SLOT(src);
   if (dst != src) NSB_TRY(vk_copy(c, slot_ptr(c, dst), slot_ptr(c, src), c->vlen));
+  c->slot_time[dst] = c->slot_time[src];
   return 0;
 }
-extern "C" int nsb_vec_zero(int slot) { REQUIRE_CTX(); CHECK_SLOT(slot); return vk_fill(c, slot_ptr(c, slot), 0.0, c->vlen); }
-extern "C" int nsb_vec_cmult(int slot, double a) { REQUIRE_CTX(); CHECK_SLOT(slot); return vk_scale(c, slot_ptr(c, slot), a, c->vlen); }
-extern "C" int nsb_vec_add2(int p, int q) { REQUIRE_CTX(); CHECK_SLOT(p); CHECK_SLOT(q); return vk_axpy(c, slot_ptr(c, p), 1.0, slot_ptr(c, q), c->vlen); }
-extern "C" int nsb_vec_sub2(int p, int q) { REQUIRE_CTX(); CHECK_SLOT(p); CHECK_SLOT(q); return vk_axpy(c, slot_ptr(c, p), -1.0, slot_ptr(c, q), c->vlen); }
+extern "C" int nsb_vec_zero(int slot) { REQUIRE_CTX(); CHECK_SLOT(slot); c->slot_time[slot] = 0.0; return vk_fill(c, slot_ptr(c, slot), 0.0, c->vlen); }
+extern "C" int nsb_vec_cmult(int slot, double a) { REQUIRE_CTX(); CHECK_SLOT(slot); c->slot_time[slot] *= a; return vk_scale(c, slot_ptr(c, slot), a, c->vlen); }
+extern "C" int nsb_vec_add2(int p, int q) {
+  REQUIRE_CTX(); CHECK_SLOT(p); CHECK_SLOT(q);
+  c->slot_time[p] += c->slot_time[q];
+  return vk_axpy(c, slot_ptr(c, p), 1.0, slot_ptr(c, q), c->vlen);
+}
+extern "C" int nsb_vec_sub2(int p, int q) {
+  REQUIRE_CTX(); CHECK_SLOT(p); CHECK_SLOT(q);
+  c->slot_time[p] -= c->slot_time[q];
+  return vk_axpy(c, slot_ptr(c, p), -1.0, slot_ptr(c, q), c->vlen);
+}
 
 extern "C" int nsb_vec_inner_product(int p, int q, double* alpha) {
   REQUIRE_CTX(); CHECK_SLOT(p); CHECK_SLOT(q);
   NSB_TRY(vk_multidot(c, 1, q, p, c->hbuf));
   NSB_TRY(d2h(c, alpha, c->hbuf, 1));
+  if (c->upo) *alpha += c->slot_time[p] * c->slot_time[q];          // time component (core/krylov_subspace.f:47-50)
   if (std::isnan(*alpha)) { nsb_set_error("krylov_inner_product: NaN (core/krylov_subspace.f:53 -> nek_end)"); return 2; }
   return 0;
 }
@@ -518,6 +551,9 @@ extern "C" int nsb_basis_gemv(int k, int first, const double* y, int out) {
   REQUIRE_CTX(); CHECK_SLOT(first); CHECK_SLOT(first + k - 1); CHECK_SLOT(out);
   if (out >= first && out < first + k) { nsb_set_error("basis_gemv: output slot inside the basis range"); return 1; }
   NSB_TRY(h2d(c, c->hbuf, y, k));
+  double t = 0.0;
+  for (int i = 0; i < k; ++i) t += y[i] * c->slot_time[first + i];
+  c->slot_time[out] = t;
   return vk_gemv_out(c, k, first, c->hbuf, out);
 }
 extern "C" int nsb_basis_gemv_complex(int k, int first, const double* yre, const double* yim, int sre, int sim) {
@@ -532,6 +568,10 @@ extern "C" int nsb_basis_rotate(int k, int first, const double* S, int lds) {
   int rc = vk_rotate(c, k, first, dS, lds);
   cudaStreamSynchronize(c->stream);
   cudaFree(dS);
+  std::vector<double> t(k, 0.0);
+  for (int j = 0; j < k; ++j)
+    for (int i = 0; i < k; ++i) t[j] += c->slot_time[first + i] * S[(size_t)j * lds + i];
+  for (int j = 0; j < k; ++j) c->slot_time[first + j] = t[j];
   return rc;
 }
 extern "C" int nsb_orthonormalize(int k, int first, int slot_f, double* hcol) {
@@ -540,6 +580,27 @@ extern "C" int nsb_orthonormalize(int k, int first, int slot_f, double* hcol) {
   double* h1 = c->hbuf;
   double* h2 = c->hbuf + (1 << 15);
   std::vector<double> a(k), b(k);
+  if (c->upo) {
+    // vectors with a time component: the coefficients need t_i * t_f from the host before the update, so the two passes make a
+    // host round trip each (the UPO Newton basis is small next to the ~1e3-step matvec it orthogonalises)
+    for (int pass = 0; pass < 2; ++pass) {
+      std::vector<double>& h = pass ? b : a;
+      double* hd = pass ? h2 : h1;
+      NSB_TRY(vk_multidot(c, k, first, slot_f, hd));
+      NSB_TRY(d2h(c, h.data(), hd, k));
+      double tf = c->slot_time[slot_f];
+      for (int i = 0; i < k; ++i) h[i] += c->slot_time[first + i] * tf;
+      for (int i = 0; i < k; ++i) tf -= h[i] * c->slot_time[first + i];
+      NSB_TRY(h2d(c, hd, h.data(), k));
+      NSB_TRY(vk_multiaxpy(c, k, first, slot_f, hd, -1.0));
+      c->slot_time[slot_f] = tf;
+    }
+    for (int i = 0; i < k; ++i) {
+      hcol[i] = a[i] + b[i];
+      if (std::isnan(hcol[i])) { nsb_set_error("orthonormalize: NaN coefficient"); return 2; }
+    }
+    return nsb_vec_normalize(slot_f, &hcol[k]);
+  }
   const bool pr = c->prof_on != 0;                          // sampling profiler: kinds 11 (multidot) and 12 (multiaxpy)
   if (pr) cudaEventRecord(c->prof_ev[16], c->stream);
   NSB_TRY(vk_multidot(c, k, first, slot_f, h1));            // h1 = Q^T W f
@@ -619,7 +680,15 @@ extern "C" int nsb_matvec(int mode, int sin, int sout) {
     }
     case NSB_NEWTON:                                 // (exp(TL) - I) q : core/matvec.f:397-400
       NSB_TRY(st_linearized_map(c, 0, q, f));
-      return vk_axpy(c, f, -1.0, q, c->vlen);
+      NSB_TRY(vk_axpy(c, f, -1.0, q, c->vlen));
+      c->slot_time[sout] = 0.0;                      // :421
+      if (c->upo) {                                  // Newton for UPOs, :407-419
+        if (!c->bvec_ready) { nsb_set_error("UPO Newton matvec: call nsb_nonlinear_forward_map first (it computes the border vectors)"); return 1; }
+        NSB_TRY(vk_axpy(c, f, c->slot_time[sin], c->bvec, c->vlen));                                  // f += bvec(fc_nwt) * q%time
+        NSB_TRY(vk_multidot_raw(c, 1, c->bvec + c->vlen, c->vlen, q, c->bm1s, c->n, c->n * c->ldim, c->hbuf));
+        NSB_TRY(d2h(c, &c->slot_time[sout], c->hbuf, 1));                                             // f%time = <bvec(ic_nwt), q>
+      }
+      return 0;
     case NSB_FORCE_SENS:                             // (I - exp(TL+)) q : core/matvec.f:366-371
       NSB_TRY(st_linearized_map(c, 1, q, f));
       NSB_TRY(vk_axpy(c, f, -1.0, q, c->vlen));
@@ -629,6 +698,17 @@ extern "C" int nsb_matvec(int mode, int sin, int sout) {
   return 1;
 }
 
+// compute_bvec (core/matvec.f:435-475): one first-order step of the full Navier-Stokes stepper from qbase approximates its time derivative
+static int compute_bvec(Ctx* c, const double* qbase, double* out) {
+  const int ns = c->nsteps;
+  const bool upo = c->upo;
+  c->nsteps = 1; c->upo = false;                    // a single step, no orbit storage
+  int rc = st_linearized_map(c, 2, qbase, out);
+  c->nsteps = ns; c->upo = upo;
+  if (rc) return rc;
+  NSB_TRY(vk_axpy(c, out, -1.0, qbase, c->vlen));
+  return vk_scale(c, out, 1.0 / c->dt, c->vlen);
+}
 // nonlinear_forward_map (core/newton_krylov.f:336-378): f = phi_T(q) - q with the full Navier-Stokes stepper (q carries its
 // Dirichlet data); afterwards q becomes the base flow of the linearised maps (ubase <- q, :374-375).
 extern "C" int nsb_nonlinear_forward_map(int sq, int sf) {
@@ -636,11 +716,18 @@ extern "C" int nsb_nonlinear_forward_map(int sq, int sf) {
   if (sq == sf) { nsb_set_error("nonlinear_forward_map: input and output slots must differ"); return 1; }
   double* q = slot_ptr(c, sq);
   double* f = slot_ptr(c, sf);
-  NSB_TRY(st_linearized_map(c, 2, q, f));
+  NSB_TRY(st_linearized_map(c, 2, q, f));           // upo: the orbit U^1..U^nsteps is stored on the way (:364-368)
+  if (c->upo) {                                     // ic_nwt = q, fc_nwt = phi_T(q) (:346, :373): their border vectors, once per Newton iterate
+    if (!c->bvec) NSB_TRY(dalloc(&c->bvec, 2 * c->vlen));
+    NSB_TRY(compute_bvec(c, f, c->bvec));
+    NSB_TRY(compute_bvec(c, q, c->bvec + c->vlen));
+    c->bvec_ready = true;
+  }
   NSB_TRY(vk_axpy(c, f, -1.0, q, c->vlen));
+  c->slot_time[sf] = 0.0;                           // :375
   if (!c->ub0) NSB_TRY(dalloc(&c->ub0, c->n * c->ldim));
   c->ub = c->ub0;
-  c->orbit_ready = false;
+  if (!c->upo) c->orbit_ready = false;
   return vk_copy(c, c->ub0, q, c->n * c->ldim);
 }
 // prepare_linearized_solver on the velocity of a Krylov vector instead of the stored base flow (newton_krylov calls it on

@@ -313,7 +313,7 @@ extern "C" int nsb_ts_gmres(int mode, int rhs_slot, int sol_slot, int first_slot
   return 0;
 }
 
-// ------------------------------------------------------------------ core/newton_krylov.f:5-168 (fixed points, uparam(1) = 2)
+// ------------------------------------------------------------------ core/newton_krylov.f:5-168 (fixed points, uparam(1) = 2; UPOs, 2.1, after nsb_set_upo(1))
 // q_slot: current estimate (in/out).  Slots used: f_slot, dq_slot, work_slot, and first_slot..first_slot+k_dim for the GMRES
 // basis.  Residuals are SQUARED norms compared with tol, as in the reference (:99,:109).  hist (optional, maxiter_newton
 // entries) receives the residual of every Newton iteration (residu_newton.dat).
@@ -323,9 +323,15 @@ extern "C" int nsb_newton_krylov(int q_slot, int f_slot, int dq_slot, int work_s
   double residual = 0.0;
   long long calls_counter = 0;
   int it = 0;
+  const bool upo = upo_active();                           // uparam(1) = 2.1: q%time is the period, an unknown of the iteration
   for (it = 1; it <= maxiter_newton; ++it) {
     double dt = 0, ct = 0;
     int nsteps = 0;
+    if (upo) {                                             // :63-67 first guess = endTime, later guesses travel in q%time
+      if (it == 1) NSB_TRY(nsb_vec_set_time(q_slot, end_time));
+      else NSB_TRY(nsb_vec_get_time(q_slot, &end_time));
+      if (!(end_time > 0)) { nsb_set_error("UPO Newton: the period became %g", end_time); return 2; }
+    }
     // :69.  The reference's prepare_linearized_solver takes the CFL of whatever Nek holds in vx,vy,vz: the initial q at iteration 1, from
     // iteration 2 on the base flow of the LAST matvec (= the previous iterate, core/matvec.f:103).  Here it is the CURRENT iterate; the
     // two differ by the Newton update, i.e. they can give a different integer nsteps only far from convergence.

@@ -191,6 +191,11 @@ struct Ctx {
   bool floquet = false, orbit_ready = false;
   double* orbit = nullptr;  // [orbit_steps][d][n]  uor, vor, wor (core/krylov_subspace.f:18)
   int orbit_steps = 0;
+  // UPO Newton (uparam(1) = 2.1): Krylov vectors carry a time component (the period unknown, core/krylov_subspace.f:8-15, :47-50); the
+  // border vectors compute_bvec(fc_nwt), compute_bvec(ic_nwt) (core/matvec.f:407-419, 435-475) stay resident next to the orbit
+  bool upo = false, bvec_ready = false;
+  std::vector<double> slot_time;   // [nslots] host: q%time of every slot
+  double* bvec = nullptr;          // [2][vlen]: bvec(fc_nwt), bvec(ic_nwt)
   struct StepState { double* u = nullptr; double* ulag[2] = {nullptr, nullptr}; double* f[3] = {nullptr, nullptr, nullptr}; double* pr = nullptr; double* prlag = nullptr; };
   StepState base_state;     // time-stepper state of the co-evolving base flow
   double* spng = nullptr;   // [n] or null
@@ -252,6 +257,7 @@ struct Ctx {
 };
 
 extern Ctx* g_ctx;
+bool upo_active();          // nsb_set_upo(1) in effect (api.cu)
 inline double* slot_ptr(Ctx* c, int s) { return c->slab + (long long)s * c->vlen; }
 // The loop vector w = H p of the Helmholtz CG travels k_axhelm3p -> dssum -> k_hcg_update in the surface-first element layout
 // (elem_common.cuh).  (r2, measured: the same layout in the pressure loop made the dssum 0.022 ms faster but k_gradt3's strided stores

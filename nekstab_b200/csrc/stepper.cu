@@ -351,6 +351,17 @@ static void swap_state(Ctx* c, Ctx::StepState& s) {
   std::swap(c->f[0], s.f[0]); std::swap(c->f[1], s.f[1]); std::swap(c->f[2], s.f[2]);
   std::swap(c->pr, s.pr); std::swap(c->prlag, s.prlag);
 }
+static int orbit_alloc(Ctx* c) {
+  const long long dn = c->n * c->ldim;
+  if (c->orbit_steps != c->nsteps || !c->orbit) {
+    if (c->orbit) cudaFree(c->orbit);
+    c->orbit = nullptr;
+    NSB_TRY(dalloc(&c->orbit, (long long)c->nsteps * dn));      // "ALLOCATING ORBIT WITH NSTEPS" core/matvec.f:201-209, core/newton_krylov.f:77-86
+    c->orbit_steps = c->nsteps;
+    c->orbit_ready = false;
+  }
+  return 0;
+}
 static int floquet_prepare(Ctx* c) {
   const long long dn = c->n * c->ldim;
   Ctx::StepState& b = c->base_state;
@@ -359,13 +370,7 @@ static int floquet_prepare(Ctx* c) {
     for (int j = 0; j < 3; ++j) NSB_TRY(dalloc(&b.f[j], dn));
     NSB_TRY(dalloc(&b.pr, c->n2)); NSB_TRY(dalloc(&b.prlag, c->n2));
   }
-  if (c->orbit_steps != c->nsteps || !c->orbit) {
-    if (c->orbit) cudaFree(c->orbit);
-    c->orbit = nullptr;
-    NSB_TRY(dalloc(&c->orbit, (long long)c->nsteps * dn));      // "ALLOCATING ORBIT WITH NSTEPS" core/matvec.f:201-209
-    c->orbit_steps = c->nsteps;
-    c->orbit_ready = false;
-  }
+  NSB_TRY(orbit_alloc(c));
   if (!c->orbit_ready) {                                       // the base flow starts from the given field (opcopy(vx.. <- ubase), core/matvec.f:103)
     NSB_TRY(vk_copy(c, b.u, c->ub0, dn));
     if (c->pb0) NSB_TRY(vk_copy(c, b.pr, c->pb0, c->n2));
@@ -380,7 +385,14 @@ int st_linearized_map(Ctx* c, int adjoint, const double* vin, double* vout) {
   if (!c->ub && adjoint != 2) { nsb_set_error("base flow not set: call nsb_set_baseflow"); return 1; }
   const long long dn = c->n * c->ldim;
   const bool flq = c->floquet && adjoint != 2;
+  // UPO Newton (uparam(1) = 2.1, ifstorebase): the nonlinear map stores the orbit (core/newton_krylov.f:364-368), the linearised maps replay it
+  const bool upo_store = c->upo && adjoint == 2, upo_replay = c->upo && adjoint != 2 && !flq;
   if (flq) NSB_TRY(floquet_prepare(c));
+  if (upo_store) { NSB_TRY(orbit_alloc(c)); c->orbit_ready = false; }
+  if (upo_replay && (!c->orbit_ready || c->orbit_steps != c->nsteps)) {
+    nsb_set_error("UPO: no stored orbit for %d steps (call nsb_nonlinear_forward_map with the current time step first)", c->nsteps);
+    return 1;
+  }
   NSB_CUDA(cudaEventRecord(c->ev0, c->stream));
   NSB_TRY(vk_copy(c, c->u, vin, dn));            // nopcopy(vxp,..,prp <- q)   core/matvec.f:212
   NSB_TRY(vk_copy(c, c->pr, vin + dn, c->n2));
@@ -398,12 +410,16 @@ int st_linearized_map(Ctx* c, int adjoint, const double* vin, double* vout) {
       // the perturbation's explicit terms of step istep see U^{istep-1}: the given field at step 1, then the stored orbit (:228-231)
       c->ub = (istep == 1) ? c->ub0 : c->orbit + (long long)(istep - 2) * dn;
     }
+    if (upo_replay) c->ub = (istep == 1) ? c->ub0 : c->orbit + (long long)(istep - 2) * dn;     // "using stored baseflow" (:228-231)
     rc = one_step(c, istep, adjoint);
+    if (upo_store && !rc) NSB_TRY(vk_copy(c, c->orbit + (long long)(istep - 1) * dn, c->u, dn));
   }
   if (flq) {
     c->ub = c->ub0;
     if (!rc) c->orbit_ready = true;              // ifbase = .false.; init = .true.  (:234-236)
   }
+  if (upo_replay) c->ub = c->ub0;
+  if (upo_store && !rc) c->orbit_ready = true;
   if (rc) return rc;
   NSB_TRY(vk_copy(c, vout, c->u, dn));           // nopcopy(f <- vxp,..,prp)   core/matvec.f:239
   NSB_TRY(vk_copy(c, vout + dn, c->pr, c->n2));

@@ -57,10 +57,13 @@
 !     kind 0 keeps Jacobi.  nagg = 0: automatic number of coarse aggregates.
       call nsb_b200_check(nsb_set_pressure_preconditioner(1, 0), 'nsb_set_pressure_preconditioner')
       call nsb_b200_check(nsb_vec_alloc(k_dim + 8), 'nsb_vec_alloc')
+!     Newton-GMRES for UPOs: time component in the inner product, orbit storage and border vectors on the device
+      if (uparam(1) .eq. 2.1) call nsb_b200_check(nsb_set_upo(1), 'nsb_set_upo')
       end subroutine nsb_b200_setup
 
       subroutine krylov_inner_product(alpha, p, q)
-!     core/krylov_subspace.f:24 ; the uparam(1) = 2.1 (UPO) time term of :48-50 stays here on the host
+!     core/krylov_subspace.f:24 ; uparam(1) = 2.1 (UPO): after nsb_set_upo(1) (nsb_b200_setup) the library adds the
+!     time term of :48-50 itself -- every slot carries q%time, kept equal to the host member by the routines below
       use nekstab_b200_c
       use krylov_subspace
       implicit none
@@ -69,7 +72,6 @@
       type(krylov_vector), intent(in) :: p, q
       real, intent(out) :: alpha
       call nsb_b200_check(nsb_vec_inner_product(p%slot, q%slot, alpha), 'krylov_inner_product')
-      if (uparam(1) .eq. 2.1) alpha = alpha + p%time * q%time
       end subroutine krylov_inner_product
 
       subroutine krylov_norm(alpha, p)
@@ -82,7 +84,6 @@
       type(krylov_vector), intent(in) :: p
       real, intent(out) :: alpha
       call nsb_b200_check(nsb_vec_norm(p%slot, alpha), 'krylov_norm')
-      if (uparam(1) .eq. 2.1) alpha = sqrt(alpha**2 + p%time**2)
       end subroutine krylov_norm
 
       subroutine krylov_normalize(p, alpha)
@@ -169,7 +170,10 @@
       real, dimension(k+1, k), intent(inout) :: H
       type(krylov_vector), dimension(k) :: q
       type(krylov_vector) :: f
+      real(c_double) :: tt
       call nsb_b200_check(nsb_orthonormalize(k, q(1)%slot, f%slot, H(1, k)), 'update_hessenberg_matrix')
+      call nsb_b200_check(nsb_vec_get_time(f%slot, tt), 'update_hessenberg_matrix')
+      f%time = tt
       end subroutine update_hessenberg_matrix
 
 !     The per-step host hook: the reference calls nekstab_usrchk() before every nek_advance (core/matvec.f:221,304).
@@ -236,8 +240,15 @@
          mode = NSB_NEWTON
          init = .false.
       endif
+!     newton_linearized_map for UPOs (core/matvec.f:407-419): the border terms bvec(fc_nwt) * q%time and
+!     f%time = <bvec(ic_nwt), q> are evaluated on the device (nsb_set_upo); f%time = 0 otherwise (:421)
+      call nsb_b200_check(nsb_vec_set_time(q%slot, real(q%time, c_double)), 'matvec')
       call nsb_b200_check(nsb_matvec(mode, q%slot, f%slot), 'matvec')
       f%time = 0.0d0
+      if (mode .eq. NSB_NEWTON) then
+         call nsb_b200_check(nsb_vec_get_time(f%slot, ddt), 'matvec')
+         f%time = ddt
+      endif
       end subroutine matvec
 
       subroutine nonlinear_forward_map(f, q)
@@ -269,6 +280,7 @@
       implicit none
       type(krylov_vector) :: p
       call nsb_b200_check(nsb_vec_upload(p%slot, p%vx, p%vy, p%vz, p%pr), 'krylov_to_device')
+      call nsb_b200_check(nsb_vec_set_time(p%slot, real(p%time, c_double)), 'krylov_to_device')
       end subroutine krylov_to_device
 
       subroutine krylov_to_host(p)
@@ -276,5 +288,8 @@
       use krylov_subspace
       implicit none
       type(krylov_vector) :: p
+      real(c_double) :: tt
       call nsb_b200_check(nsb_vec_download(p%slot, p%vx, p%vy, p%vz, p%pr), 'krylov_to_host')
+      call nsb_b200_check(nsb_vec_get_time(p%slot, tt), 'krylov_to_host')
+      p%time = tt
       end subroutine krylov_to_host

@@ -61,6 +61,9 @@ _SIGS = {
     "nsb_set_baseflow": [_dp] * 3,
     "nsb_set_sponge": [_dp],
     "nsb_set_floquet": [C.c_int, _dp],
+    "nsb_set_upo": [C.c_int],
+    "nsb_vec_set_time": [C.c_int, C.c_double],
+    "nsb_vec_get_time": [C.c_int, _dp],
     "nsb_set_dns_sponge": [C.c_double, _dp, _dp, _dp],
     "nsb_get_orbit": [C.c_int, _dp, _dp, _dp],
     "nsb_prepare_linearized_solver": [C.c_double, C.c_double, _dp, _ip, _dp],
@@ -265,6 +268,19 @@ class NekStabB200:
         """Floquet / UPO mode: base-flow co-evolution + orbit storage (core/matvec.f:187-236)."""
         pb = None if pbase is None else _arr(pbase).reshape(self.n2)
         _ck(self.lib.nsb_set_floquet(int(enable), _p(pb)))
+
+    def set_upo(self, enable):
+        """Newton-GMRES for UPOs (uparam(1) = 2.1): time component of the Krylov vectors, orbit storage in the nonlinear map, border
+        terms of newton_linearized_map (core/matvec.f:407-419)."""
+        _ck(self.lib.nsb_set_upo(int(enable)))
+
+    def vec_set_time(self, slot, t):
+        _ck(self.lib.nsb_vec_set_time(int(slot), float(t)))
+
+    def vec_get_time(self, slot):
+        t = C.c_double()
+        _ck(self.lib.nsb_vec_get_time(int(slot), C.byref(t)))
+        return t.value
 
     def set_dns_sponge(self, spng_str, ref=None):
         r = [None] * 3 if ref is None else self._vec3(ref)

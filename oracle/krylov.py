@@ -8,8 +8,9 @@ The Krylov layer of nekStab restated 1:1 in numpy/scipy:
   select_eigenvalues        core/eigensolvers.f:729-795
   eig/schur/ordschur/lstsq  core/lapack_wrapper.f:7-339 (scipy's dgeev/dgees/dtrsen/dgels)
   ts_gmres                  core/newton_krylov.f:175-297
-A Krylov vector is a tuple (v, p): v (ldim, ...) velocity, p pressure.  The inner product is the reference's
-semi-norm: velocity only, weight bm1s (core/krylov_subspace.f:37-45).
+A Krylov vector is a tuple (v, p) or (v, p, time): v (ldim, ...) velocity, p pressure, time the period unknown of the UPO Newton
+(core/krylov_subspace.f:8-15).  The inner product is the reference's semi-norm: velocity only, weight bm1s (:37-45), plus
+time * time in the UPO case (:47-50).
 """
 from __future__ import annotations
 
@@ -19,15 +20,18 @@ from scipy.linalg import lapack
 
 
 def inner(a, b, w):
-    return float(sum(np.sum(a[0][d] * w * b[0][d]) for d in range(a[0].shape[0])))
+    """krylov_inner_product (core/krylov_subspace.f:24-56): velocity under bm1s, plus the product of the time components when the
+    vectors carry one (third tuple entry; uparam(1) = 2.1, :47-50)."""
+    v = float(sum(np.sum(a[0][d] * w * b[0][d]) for d in range(a[0].shape[0])))
+    return v + float(a[2]) * float(b[2]) if len(a) > 2 else v
 
 
 def axpy(a, alpha, b):
-    return (a[0] + alpha * b[0], a[1] + alpha * b[1])
+    return tuple(x + alpha * y for x, y in zip(a, b))
 
 
 def scale(a, alpha):
-    return (a[0] * alpha, a[1] * alpha)
+    return tuple(x * alpha for x in a)
 
 
 def update_hessenberg_matrix(H, f, Q, k, w):
@@ -147,7 +151,7 @@ def krylov_schur(matvec, q0, k_dim, schur_tgt, w, eigen_tol=1e-6, schur_del=0.1,
 
 def ts_gmres(matvec, rhs, maxiter, ksize, tol, w):
     """core/newton_krylov.f:175-297; squared residual norms are compared with tol (:268,:288)."""
-    sol = (np.zeros_like(rhs[0]), np.zeros_like(rhs[1]))
+    sol = tuple(np.zeros_like(x) if isinstance(x, np.ndarray) else 0.0 for x in rhs)
     beta = np.sqrt(inner(rhs, rhs, w))
     q1 = scale(rhs, 1.0 / beta)
     calls = 0
@@ -164,7 +168,7 @@ def ts_gmres(matvec, rhs, maxiter, ksize, tol, w):
                 calls += k
                 kk = k
                 break
-        dq = (sum(y[j] * Q[j][0] for j in range(kk)), sum(y[j] * Q[j][1] for j in range(kk)))
+        dq = tuple(sum(y[j] * Q[j][m] for j in range(kk)) for m in range(len(rhs)))          # krylov_matmul (:275)
         sol = axpy(sol, 1.0, dq)
         f = matvec(sol)
         f = scale(axpy(f, -1.0, rhs), -1.0)

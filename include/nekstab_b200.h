@@ -163,6 +163,21 @@ int nsb_nonlinear_forward_map(int slot_q, int slot_f);
  *  - nsb_newton_krylov treats end_time as the first guess of the period and updates it with the Newton correction
  *    (core/newton_krylov.f:63-67, 122); read the period found with nsb_vec_get_time(q_slot). */
 int nsb_set_upo(int enable);
+/* Scalar transport (`ifheat`, one scalar: ldimt = 1).  After nsb_set_scalar(1, ..) a Krylov vector is [vx|vy|(vz)|theta|pr]
+ * (type krylov_vector, core/krylov_subspace.f:8-15): theta enters krylov_inner_product with the weight bm1s (:41-45), follows all the
+ * vector algebra, and is advanced by nsb_matvec(NSB_DIRECT / NSB_NEWTON) and nsb_nonlinear_forward_map next to the velocity
+ * [UPSTREAM perturb.f heatp / cdscalp / convabp: rhocp (d/dt + U.grad) theta' + rhocp u'.grad Theta = conductivity lap theta'
+ * - spng_fun theta' (nekStab_forcing_temp, core/utils.f:182-203); full equation: heat / cdscal / convab] with the velocity's BDF3/EXT3
+ * scheme and Jacobi-PCG Helmholtz solver (tolerance tol_v).  conductivity = param(8), rhocp = param(7); tmask = Dirichlet mask of the
+ * scalar (tmask of Nek5000); ri: the momentum equation feels f_gdir += ri * theta (ffy = temp * uparam(6) in the shipped Boussinesq
+ * cases, e.g. examples/thersyphon/baseflow/tsyphon.usr), gdir 0-based.  Not built: the adjoint scalar equation (nsb_matvec(NSB_ADJOINT)
+ * returns an error while the scalar is on), ldimt > 1, the scalar in Floquet / UPO orbit storage (tor).  The layout change discards
+ * the slots: call nsb_vec_alloc afterwards.  nsb_set_scalar_base = tbase (core/eigensolvers.f:195-199; nsb_nonlinear_forward_map
+ * sets it to slot_q's theta, core/newton_krylov.f:375). */
+int nsb_set_scalar(int enable, double conductivity, double rhocp, const double* tmask, double ri, int gdir);
+int nsb_set_scalar_base(const double* tbase);
+int nsb_vec_upload_scalar(int slot, const double* theta);
+int nsb_vec_download_scalar(int slot, double* theta);
 int nsb_vec_set_time(int slot, double time);
 int nsb_vec_get_time(int slot, double* NSB_SCALAR time);
 /* prepare_linearized_solver evaluated on the velocity in `slot` (newton_krylov re-prepares on every iterate, :69). */
@@ -194,6 +209,7 @@ int nsb_fp64_peak(double* NSB_SCALAR tflops);
  * [UPSTREAM] hmholtz.f axhelm; dssum.f dssum; math.f glsc3; navier1.f opgradt, opdiv, cdabdtp;
  * perturb.f advabp/advabp_adjoint; hmholtz.f hmholtz (Jacobi-PCG); navier1.f esolver (here Jacobi-PCG). */
 int nsb_op_axhelm(const double* u, double h1, double h2, double* w);
+int nsb_op_conv_scalar(const double* ax, const double* ay, const double* az, const double* phi, double* out); /* B (a.grad) phi, dealiased [UPSTREAM convect.f convop] */
 int nsb_op_dssum(double* u);
 int nsb_op_glsc3(const double* a, const double* b, const double* c, double* NSB_SCALAR out);
 int nsb_op_opgradt(const double* p, double* wx, double* wy, double* wz);

@@ -9,7 +9,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libnekstab_b200.so")
-SOURCES = ["elem_kernels.cu", "pcg_kernels.cu", "vec_kernels.cu", "gs.cu", "p2p.cu", "pmg.cu", "stepper.cu", "api.cu", "host_krylov.cpp", "sem_host.cpp"]
+SOURCES = ["elem_kernels.cu", "pcg_kernels.cu", "vec_kernels.cu", "gs.cu", "p2p.cu", "pmg.cu", "scalar.cu", "stepper.cu", "api.cu", "host_krylov.cpp", "sem_host.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--extended-lambda",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xcompiler", "-Wno-unused-function"]

@@ -419,6 +419,28 @@ def cavity_case(g: dict) -> Case:
     return case
 
 
+def thermosyphon_case(g: dict, ra: float = 400.0) -> Case:
+    """Scalar-transport fixture: examples/thersyphon/baseflow (2-D annulus 1 <= r <= 2, periodic in theta, 256 elements, lx1 = 6).
+    tsyphon.par: viscosity = 5 (the Prandtl number, positive => taken as is), conductivity = 1, rhocp = 1, endTime 0.1, tolerances 1e-11;
+    tsyphon.usr userf: ffy = T * Pr * Ra.  Walls 'W' (velocity) / 't' (temperature, 0.5 (1 + tanh(-20 y)), carried by the field itself)
+    at both radii => all-Dirichlet velocity, singular E.  `g` = tests/golden/tsyphon.npz; the shipped field is the Newton solution at
+    Ra = 400.  case.extra: "T" the base temperature, "tmask" its Dirichlet mask, "ri" = Pr * Ra, "cond", "rhocp", "P"."""
+    lx1 = int(g["lx1"])
+    X = g["X"].reshape(-1, 2, lx1 * lx1).transpose(1, 0, 2).astype(np.float64)
+    U = g["U"].reshape(-1, 2, lx1 * lx1).transpose(1, 0, 2).astype(np.float64)
+    glo = global_numbering_2d(g["vert"], lx1)
+    codes = {c: i for i, c in enumerate([s.decode() if isinstance(s, bytes) else str(s) for s in g["bc_names"]])}
+    pr = 5.0
+    case = Case("thermosyphon_ra%g" % ra, 2, lx1, X.shape[1], X, glo, _mask_from_faces(g["bc"] == codes["W  "], glo, lx1, 2),
+                g["key"].astype(np.int64), int(g["d2"]), U, re=1.0 / pr, end_time=0.1, tol_p=1e-11, tol_v=1e-11)
+    case.ifvcor = case.ifvcor_adjoint = True
+    case.extra["T"] = g["T"].reshape(-1, lx1 * lx1).astype(np.float64)
+    case.extra["P"] = g["P"].reshape(-1, lx1 * lx1).astype(np.float64)
+    case.extra["tmask"] = _mask_from_faces(g["bct"] == codes["t  "], glo, lx1, 2)[0]
+    case.extra["ri"], case.extra["cond"], case.extra["rhocp"] = np.float64(pr * ra), np.float64(1.0), np.float64(1.0)
+    return case
+
+
 def extrude(c2: Case, nz: int, lz: float, name: Optional[str] = None, compress_ids: bool = True) -> Case:
     """Config 5 recipe (SURVEY 8d): extrude a 2-D case into nz uniform periodic layers over [0,lz];
     element eg3 = layer*nel2 + eg2, key3 = key2, z-invariant base flow with W=0."""

@@ -124,6 +124,11 @@ extern "C" int nsb_finalize(void) {
     for (double* q : bp) if (q) cudaFree(q);
   }
   pm_free(c->pmg[0]); pm_free(c->pmg[1]);
+  {
+    Ctx::Scalar& z = c->scal;
+    double* sp[] = {z.tmask, z.tb, z.th, z.thlag[0], z.thlag[1], z.q[0], z.q[1], z.q[2], z.wk[0], z.wk[1], z.mats, c->bvec};
+    for (double* q : sp) if (q) cudaFree(q);
+  }
   if (c->adv_scratch) cudaFree(c->adv_scratch);
   if (c->pz) cudaFree(c->pz);
   if (c->ones2) cudaFree(c->ones2);
@@ -165,6 +170,7 @@ extern "C" int nsb_init(int ldim, int lx1, int lxd, int lx2, int nelv, long long
   c->n = (long long)nelv * c->np1; c->n2 = (long long)nelv * c->np2; c->nd = (long long)nelv * c->npd;
   c->n2_glob = nelgv * c->np2;
   c->vlen = c->n * ldim + c->n2;
+  c->poff = c->n * ldim;
   c->rank = g_rank; c->nranks = g_nranks; c->comm = g_comm;
   NSB_CUDA(cudaStreamCreate(&c->stream));
   NSB_CUDA(cudaEventCreate(&c->ev0));
@@ -457,6 +463,12 @@ extern "C" int nsb_prepare_linearized_solver(double end_time, double cfl_target,
 #define CHECK_SLOT(s)                                                                     \
   if ((s) < 0 || (s) >= c->nslots) { nsb_set_error("slot %d out of range [0,%d)", (s), c->nslots); return 1; }
 
+// h_j = <Q_j, f> under bm1s over the velocity -- and the scalar when it travels with the vector (core/krylov_subspace.f:37-45)
+static int multidot(Ctx* c, int k, int first, int slot_f, double* h_dev) {
+  if (!c->scal.on) return vk_multidot(c, k, first, slot_f, h_dev);
+  return vk_multidot_raw(c, k, slot_ptr(c, first), c->vlen, slot_ptr(c, slot_f), c->bm1s, c->n, c->n * (c->ldim + 1), h_dev);
+}
+
 extern "C" int nsb_vec_alloc(int nslots) {
   REQUIRE_CTX();
   if (nslots <= 0) { nsb_set_error("nslots must be positive"); return 1; }
@@ -475,8 +487,9 @@ extern "C" int nsb_vec_upload(int slot, const double* vx, const double* vy, cons
     if (!h[d]) { nsb_set_error("vec_upload: component %d is NULL", d); return 1; }
     NSB_TRY(h2d(c, v + d * c->n, h[d], c->n));
   }
-  if (pr) NSB_TRY(h2d(c, v + c->ldim * c->n, pr, c->n2));
-  else NSB_TRY(vk_fill(c, v + c->ldim * c->n, 0.0, c->n2));
+  if (pr) NSB_TRY(h2d(c, v + c->poff, pr, c->n2));
+  else NSB_TRY(vk_fill(c, v + c->poff, 0.0, c->n2));
+  if (c->scal.on) NSB_TRY(vk_fill(c, v + c->ldim * c->n, 0.0, c->n));       // theta: nsb_vec_upload_scalar
   NSB_CUDA(cudaStreamSynchronize(c->stream));
   c->slot_time[slot] = 0.0;
   return 0;
@@ -502,13 +515,64 @@ extern "C" int nsb_set_upo(int enable) {
   return 0;
 }
 bool upo_active() { return g_ctx && g_ctx->upo; }
+
+// Scalar transport (`ifheat`, ldimt = 1).  After nsb_set_scalar(1, ..) every Krylov vector is [vx|vy|(vz)|theta|pr]
+// (core/krylov_subspace.f:8-15), theta enters the inner product with the weight bm1s (:41-45) and is advanced by the direct and the
+// full Navier-Stokes maps [UPSTREAM perturb.f heatp / convabp; heat / convab].  conductivity = param(8), rhocp = param(7); tmask = the
+// scalar's Dirichlet mask; ri: buoyancy f_gdir += ri * theta (uparam(6) in the shipped Boussinesq .usr files), gdir 0-based.
+// The layout change discards the slots: call nsb_vec_alloc afterwards.
+extern "C" int nsb_set_scalar(int enable, double conductivity, double rhocp, const double* tmask, double ri, int gdir) {
+  REQUIRE_CTX();
+  Ctx::Scalar& z = c->scal;
+  drop_graphs(c);
+  if (c->slab) { cudaFree(c->slab); c->slab = nullptr; c->nslots = 0; c->slot_time.clear(); }
+  z.on = enable != 0;
+  c->poff = c->n * (c->ldim + (z.on ? 1 : 0));
+  c->vlen = c->poff + c->n2;
+  if (c->bvec) { cudaFree(c->bvec); c->bvec = nullptr; c->bvec_ready = false; }
+  if (!z.on) return 0;
+  if (!tmask) { nsb_set_error("nsb_set_scalar: tmask is NULL"); return 1; }
+  if (gdir < 0 || gdir >= c->ldim) { nsb_set_error("nsb_set_scalar: gdir %d out of range", gdir); return 1; }
+  if (!(rhocp > 0) || conductivity < 0) { nsb_set_error("nsb_set_scalar: rhocp must be positive, conductivity non-negative"); return 1; }
+  z.cond = conductivity; z.rhocp = rhocp; z.ri = ri; z.gdir = gdir;
+  if (!z.tmask) {
+    NSB_TRY(dalloc(&z.tmask, c->n)); NSB_TRY(dalloc(&z.th, c->n));
+    for (int j = 0; j < 2; ++j) { NSB_TRY(dalloc(&z.thlag[j], c->n)); NSB_TRY(dalloc(&z.wk[j], c->n)); }
+    for (int j = 0; j < 3; ++j) NSB_TRY(dalloc(&z.q[j], c->n));
+  }
+  NSB_TRY(h2d(c, z.tmask, tmask, c->n));
+  NSB_CUDA(cudaStreamSynchronize(c->stream));
+  return sk_setup(c);
+}
+// tbase (core/NEKSTAB /nStab_bflows/, loaded at core/eigensolvers.f:195-199): the scalar field the perturbation is linearised about
+extern "C" int nsb_set_scalar_base(const double* tbase) {
+  REQUIRE_CTX();
+  if (!c->scal.on) { nsb_set_error("nsb_set_scalar_base: call nsb_set_scalar(1, ..) first"); return 1; }
+  if (!tbase) { nsb_set_error("nsb_set_scalar_base: NULL field"); return 1; }
+  if (!c->scal.tb) NSB_TRY(dalloc(&c->scal.tb, c->n));
+  NSB_TRY(h2d(c, c->scal.tb, tbase, c->n));
+  NSB_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+extern "C" int nsb_vec_upload_scalar(int slot, const double* theta) {
+  REQUIRE_CTX(); CHECK_SLOT(slot);
+  if (!c->scal.on || !theta) { nsb_set_error("nsb_vec_upload_scalar: scalar transport is off or NULL field"); return 1; }
+  NSB_TRY(h2d(c, slot_ptr(c, slot) + c->ldim * c->n, theta, c->n));
+  NSB_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+extern "C" int nsb_vec_download_scalar(int slot, double* theta) {
+  REQUIRE_CTX(); CHECK_SLOT(slot);
+  if (!c->scal.on || !theta) { nsb_set_error("nsb_vec_download_scalar: scalar transport is off or NULL field"); return 1; }
+  return d2h(c, theta, slot_ptr(c, slot) + c->ldim * c->n, c->n);
+}
 extern "C" int nsb_vec_download(int slot, double* vx, double* vy, double* vz, double* pr) {
   REQUIRE_CTX(); CHECK_SLOT(slot);
   double* v = slot_ptr(c, slot);
   double* h[3] = {vx, vy, vz};
   for (int d = 0; d < c->ldim; ++d)
     if (h[d]) NSB_TRY(d2h(c, h[d], v + d * c->n, c->n));
-  if (pr) NSB_TRY(d2h(c, pr, v + c->ldim * c->n, c->n2));
+  if (pr) NSB_TRY(d2h(c, pr, v + c->poff, c->n2));
   return 0;
 }
 extern "C" int nsb_vec_copy(int dst, int src) {
@@ -532,7 +596,7 @@ extern "C" int nsb_vec_sub2(int p, int q) {
 
 extern "C" int nsb_vec_inner_product(int p, int q, double* alpha) {
   REQUIRE_CTX(); CHECK_SLOT(p); CHECK_SLOT(q);
-  NSB_TRY(vk_multidot(c, 1, q, p, c->hbuf));
+  NSB_TRY(multidot(c, 1, q, p, c->hbuf));
   NSB_TRY(d2h(c, alpha, c->hbuf, 1));
   if (c->upo) *alpha += c->slot_time[p] * c->slot_time[q];          // time component (core/krylov_subspace.f:47-50)
   if (std::isnan(*alpha)) { nsb_set_error("krylov_inner_product: NaN (core/krylov_subspace.f:53 -> nek_end)"); return 2; }
@@ -586,7 +650,7 @@ extern "C" int nsb_orthonormalize(int k, int first, int slot_f, double* hcol) {
     for (int pass = 0; pass < 2; ++pass) {
       std::vector<double>& h = pass ? b : a;
       double* hd = pass ? h2 : h1;
-      NSB_TRY(vk_multidot(c, k, first, slot_f, hd));
+      NSB_TRY(multidot(c, k, first, slot_f, hd));
       NSB_TRY(d2h(c, h.data(), hd, k));
       double tf = c->slot_time[slot_f];
       for (int i = 0; i < k; ++i) h[i] += c->slot_time[first + i] * tf;
@@ -603,11 +667,11 @@ extern "C" int nsb_orthonormalize(int k, int first, int slot_f, double* hcol) {
   }
   const bool pr = c->prof_on != 0;                          // sampling profiler: kinds 11 (multidot) and 12 (multiaxpy)
   if (pr) cudaEventRecord(c->prof_ev[16], c->stream);
-  NSB_TRY(vk_multidot(c, k, first, slot_f, h1));            // h1 = Q^T W f
+  NSB_TRY(multidot(c, k, first, slot_f, h1));            // h1 = Q^T W f
   if (pr) cudaEventRecord(c->prof_ev[17], c->stream);
   NSB_TRY(vk_multiaxpy(c, k, first, slot_f, h1, -1.0));     // f -= Q h1
   if (pr) cudaEventRecord(c->prof_ev[18], c->stream);
-  NSB_TRY(vk_multidot(c, k, first, slot_f, h2));            // re-orthogonalisation (DGKS)
+  NSB_TRY(multidot(c, k, first, slot_f, h2));            // re-orthogonalisation (DGKS)
   if (pr) cudaEventRecord(c->prof_ev[19], c->stream);
   NSB_TRY(vk_multiaxpy(c, k, first, slot_f, h2, -1.0));
   if (pr) cudaEventRecord(c->prof_ev[20], c->stream);
@@ -728,6 +792,10 @@ extern "C" int nsb_nonlinear_forward_map(int sq, int sf) {
   if (!c->ub0) NSB_TRY(dalloc(&c->ub0, c->n * c->ldim));
   c->ub = c->ub0;
   if (!c->upo) c->orbit_ready = false;
+  if (c->scal.on) {                                 // tbase <- q%theta (:375)
+    if (!c->scal.tb) NSB_TRY(dalloc(&c->scal.tb, c->n));
+    NSB_TRY(vk_copy(c, c->scal.tb, q + c->n * c->ldim, c->n));
+  }
   return vk_copy(c, c->ub0, q, c->n * c->ldim);
 }
 // prepare_linearized_solver on the velocity of a Krylov vector instead of the stored base flow (newton_krylov calls it on
@@ -775,6 +843,19 @@ extern "C" long long nsb_n(void) { return g_ctx ? g_ctx->n : 0; }
 extern "C" long long nsb_n2(void) { return g_ctx ? g_ctx->n2 : 0; }
 
 // ------------------------------------------------------------------------------------------ operator-level entry points
+// out = B (a.grad) phi, dealiased (convop; needs nsb_set_scalar(1, ..) for the kernel's matrices)
+extern "C" int nsb_op_conv_scalar(const double* ax, const double* ay, const double* az, const double* phi, double* out) {
+  REQUIRE_CTX();
+  if (!c->scal.on) { nsb_set_error("nsb_op_conv_scalar: call nsb_set_scalar(1, ..) first"); return 1; }
+  const double* h[3] = {ax, ay, az};
+  for (int d = 0; d < c->ldim; ++d) {
+    if (!h[d]) { nsb_set_error("nsb_op_conv_scalar: component %d is NULL", d); return 1; }
+    NSB_TRY(h2d(c, c->wk[0] + d * c->n, h[d], c->n));
+  }
+  NSB_TRY(h2d(c, c->scal.wk[0], phi, c->n));
+  NSB_TRY(sk_conv(c, c->wk[0], c->scal.wk[0], nullptr, nullptr, c->scal.wk[1]));
+  return d2h(c, out, c->scal.wk[1], c->n);
+}
 extern "C" int nsb_op_axhelm(const double* u, double h1, double h2, double* w) {
   REQUIRE_CTX();
   NSB_TRY(h2d(c, c->wk[0], u, c->n));

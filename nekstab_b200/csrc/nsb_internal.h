@@ -191,6 +191,22 @@ struct Ctx {
   bool floquet = false, orbit_ready = false;
   double* orbit = nullptr;  // [orbit_steps][d][n]  uor, vor, wor (core/krylov_subspace.f:18)
   int orbit_steps = 0;
+  // Scalar transport (ifheat, ldimt = 1; core/krylov_subspace.f:13,41-45): theta travels in every Krylov vector between the velocity
+  // and the pressure, [vx|vy|(vz)|theta|pr]; advanced next to the velocity by the same BDF/EXT scheme (csrc/scalar.cu, stepper.cu)
+  struct Scalar {
+    bool on = false;
+    double cond = 0.0, rhocp = 1.0;      // param(8), param(7): Helmholtz h1 and the factor of the time derivative / convection
+    double ri = 0.0;                     // buoyancy f_g += ri * theta (uparam(6) of the shipped .usr files)
+    int gdir = 1;                        // component that feels the buoyancy (y)
+    double* tmask = nullptr;             // [n] Dirichlet mask of the scalar
+    double* tb = nullptr;                // [n] base scalar field (tbase)
+    double* th = nullptr;                // [n] current
+    double* thlag[2] = {nullptr, nullptr};
+    double* q[3] = {nullptr, nullptr, nullptr};   // explicit terms ring
+    double* wk[2] = {nullptr, nullptr};  // [n] work
+    double* mats = nullptr;              // Jd, Dd, Jdt (lxd x lx1 each) for the convection kernel
+  } scal;
+  long long poff = 0;                    // offset of the pressure inside a Krylov vector: n * (ldim + nscal)
   // UPO Newton (uparam(1) = 2.1): Krylov vectors carry a time component (the period unknown, core/krylov_subspace.f:8-15, :47-50); the
   // border vectors compute_bvec(fc_nwt), compute_bvec(ic_nwt) (core/matvec.f:407-419, 435-475) stay resident next to the orbit
   bool upo = false, bvec_ready = false;
@@ -360,7 +376,10 @@ int vk_cg_finalize_multi(Ctx* c, CGState* s, int ncomp, int kind);
 
 // ---- solvers / stepper (stepper.cu)
 int st_alloc(Ctx* c);
-int st_helmholtz(Ctx* c, int adj, double h1, double h2, int* iters);   // solves for wk[3] (x) from rk (r, assembled+masked)
+int st_helmholtz(Ctx* c, int adj, double h1, double h2, int* iters, int ncomp = 0, int graph_key = -1);
+// scalar.cu: out = J^T [ (Rd J a).grad(J phi) + (Rd J b).grad(J psi) ]  (dealiased convection of a scalar; b, psi may be null)
+int sk_setup(Ctx* c);
+int sk_conv(Ctx* c, const double* a, const double* phi, const double* b, const double* psi, double* out);   // solves for wk[3] (x) from rk (r, assembled+masked)
 int st_pressure(Ctx* c, int adj, int* iters);                          // solves E pk[1] = pk[0]
 int st_linearized_map(Ctx* c, int adjoint, const double* vin, double* vout);   // vin/vout device krylov vectors
 

@@ -115,8 +115,11 @@ static int run_batch_graph(Ctx* c, Ctx::GraphEntry* ge, F&& batch) {
 
 // Solve (h1 A + h2 B) x_c = r_c for the ldim velocity components at once (independent CG recurrences sharing
 // every kernel launch) [UPSTREAM hmholtz.f hmholtz/cggo].  In: c->rk (assembled, masked). Out: c->wk[3].
-int st_helmholtz(Ctx* c, int adj, double h1, double h2, int* iters) {
-  const int nc = c->ldim;
+// ncomp = 0: the ldim velocity components; ncomp = 1 solves a single field held in component 0 of rk / wk (the scalar, whose mask the
+// caller has swapped into mask[adj][0]); graph_key keeps its captured batches apart from the velocity's.
+int st_helmholtz(Ctx* c, int adj, double h1, double h2, int* iters, int ncomp, int graph_key) {
+  const int nc = ncomp > 0 ? ncomp : c->ldim;
+  const int gkey = graph_key >= 0 ? graph_key : adj;
   NSB_TRY(vk_dinvH(c, h1, h2));
   NSB_TRY(cg_state_setup(c, 0, nc, c->tol_v, c->vol, c->maxit_v));
   NSB_TRY(vk_hcg_init(c, nc));
@@ -125,10 +128,10 @@ int st_helmholtz(Ctx* c, int adj, double h1, double h2, int* iters) {
   Ctx::GraphEntry* ge = nullptr;
   if (graphs_ok(c)) {
     for (auto& g : c->graph_h)
-      if (g.exec && g.adj == adj && g.h1 == h1 && g.h2 == h2) ge = &g;
+      if (g.exec && g.adj == gkey && g.h1 == h1 && g.h2 == h2) ge = &g;
     if (!ge)
       for (auto& g : c->graph_h)
-        if (!g.exec) { ge = &g; ge->adj = adj; ge->h1 = h1; ge->h2 = h2; break; }
+        if (!g.exec) { ge = &g; ge->adj = gkey; ge->h1 = h1; ge->h2 = h2; break; }
   }
   auto batch = [&](bool sample) -> int {
     for (int it = 0; it < c->check_every_v; ++it) {
@@ -298,6 +301,55 @@ int st_pressure(Ctx* c, int adj, int* iters) {
   return 0;
 }
 
+// ---- scalar transport (ifheat): theta' advanced next to the velocity [UPSTREAM perturb.f heatp / cdscalp / makeqp / convabp; full
+//      equation: heat / cdscal / makeq / convab].  Explicit term of step n (all fields at level n):
+//        q = -rhocp * B [ (U.grad) theta' + (u'.grad) Theta ] - B spng_fun theta'      perturbation (nekStab_forcing_temp jp = 1, core/utils.f:199)
+//        q = -rhocp * B (u.grad) theta                                                 full equation
+//      and the momentum feels  f_g += B ri theta  (userf of the shipped Boussinesq cases: ffy = temp * uparam(6)).
+static int scalar_explicit(Ctx* c, int kind, double* fvel) {
+  Ctx::Scalar& z = c->scal;
+  double* qnew = z.q[2];
+  if (kind == 2) NSB_TRY(sk_conv(c, c->u, z.th, nullptr, nullptr, qnew));
+  else NSB_TRY(sk_conv(c, c->ub, z.th, c->u, z.tb, qnew));
+  NSB_TRY(vk_scale(c, qnew, -z.rhocp, c->n));
+  NSB_TRY(vk_copy(c, z.wk[0], z.th, c->n));
+  NSB_TRY(vk_mul(c, z.wk[0], c->bm1, c->n));                         // B theta
+  if (z.ri != 0.0) NSB_TRY(vk_axpy(c, fvel + (long long)z.gdir * c->n, z.ri, z.wk[0], c->n));
+  if (kind != 2 && c->spng) {
+    NSB_TRY(vk_mul(c, z.wk[0], c->spng, c->n));
+    NSB_TRY(vk_axpy(c, qnew, -1.0, z.wk[0], c->n));
+  }
+  z.q[2] = z.q[1]; z.q[1] = z.q[0]; z.q[0] = qnew;
+  return 0;
+}
+// implicit part: (cond A + rhocp bd0/dt B) dtheta = b - H theta^n, theta^{n+1} = theta^n + dtheta (cdscalp), Jacobi-PCG of st_helmholtz
+static int scalar_solve(Ctx* c, int k) {
+  Ctx::Scalar& z = c->scal;
+  const double h1 = z.cond, h2 = z.rhocp * BD[k][0] / c->dt;
+  double* b = z.wk[1];
+  NSB_TRY(vk_fill(c, z.wk[0], 0.0, c->n));
+  NSB_TRY(vk_fill(c, b, 0.0, c->n));
+  const double* lag[3] = {z.th, z.thlag[0], z.thlag[1]};
+  for (int j = 0; j < k; ++j) {
+    NSB_TRY(vk_axpy(c, b, AB[k][j], z.q[j], c->n));
+    NSB_TRY(vk_axpy(c, z.wk[0], BD[k][j + 1], lag[j], c->n));
+  }
+  NSB_TRY(vk_mul(c, z.wk[0], c->bm1, c->n));
+  NSB_TRY(vk_axpy(c, b, z.rhocp / c->dt, z.wk[0], c->n));
+  NSB_TRY(vk_fill(c, c->rk, 0.0, c->n));
+  NSB_TRY(ek_axhelm_resid(c, z.th, b, c->rk, 1, h1, h2));             // r = b + r - H theta^n
+  NSB_TRY(gs_dssum(c, c->rk, 1, c->n, nullptr));
+  NSB_TRY(vk_mul(c, c->rk, z.tmask, c->n));
+  std::swap(c->mask[0][0], z.tmask);                                  // the CG update masks component 0 with mask[adj][0]
+  int rc = st_helmholtz(c, 0, h1, h2, nullptr, 1, 2);
+  std::swap(c->mask[0][0], z.tmask);
+  if (rc) return rc;
+  double* tn = z.thlag[1];
+  NSB_TRY(vk_lin2(c, tn, 1.0, z.th, 1.0, c->wk[3], c->n));
+  z.thlag[1] = z.thlag[0]; z.thlag[0] = z.th; z.th = tn;
+  return 0;
+}
+
 // kind: 0 direct, 1 adjoint perturbation step; 2 full Navier-Stokes step (nonlinear_forward_map, core/newton_krylov.f:336-378)
 static int one_step(Ctx* c, int istep, int kind) {
   const int adj = (kind == 1) ? 1 : 0;
@@ -317,6 +369,7 @@ static int one_step(Ctx* c, int istep, int kind) {
     NSB_TRY(ek_advab(c, adj, c->u, c->ub, c->spng, fnew));
   }
   prof_mark(c, c->prof_on, 11);
+  if (c->scal.on) NSB_TRY(scalar_explicit(c, kind, fnew));
   c->f[2] = c->f[1]; c->f[1] = c->f[0]; c->f[0] = fnew;
   double* b = c->wk[0];
   NSB_TRY(vk_make_rhs(c, b, k, AB[k], BD[k]));
@@ -336,6 +389,7 @@ static int one_step(Ctx* c, int istep, int kind) {
   NSB_TRY(ek_gradt(c, c->pk[1], c->wk[2]));
   NSB_TRY(gs_dssum(c, c->wk[2], D, c->n, nullptr));
   NSB_TRY(vk_final_update(c, adj, h2));
+  if (c->scal.on) NSB_TRY(scalar_solve(c, k));
   // rotate: velocity (u -> ulag0 -> ulag1), pressure (pr <-> prlag)
   double* t = c->ulag[1]; c->ulag[1] = c->ulag[0]; c->ulag[0] = c->u; c->u = t;
   double* tp = c->prlag; c->prlag = c->pr; c->pr = tp;
@@ -394,8 +448,14 @@ int st_linearized_map(Ctx* c, int adjoint, const double* vin, double* vout) {
     return 1;
   }
   NSB_CUDA(cudaEventRecord(c->ev0, c->stream));
+  if (c->scal.on) {
+    if (adjoint == 1) { nsb_set_error("scalar transport: the adjoint equations are not built (direct and full Navier-Stokes maps only)"); return 1; }
+    if (flq || c->upo) { nsb_set_error("scalar transport: Floquet / UPO orbit storage does not carry the scalar yet (tor)"); return 1; }
+    if (adjoint != 2 && !c->scal.tb) { nsb_set_error("scalar transport: base scalar field not set (nsb_set_scalar_base)"); return 1; }
+    NSB_TRY(vk_copy(c, c->scal.th, vin + dn, c->n));
+  }
   NSB_TRY(vk_copy(c, c->u, vin, dn));            // nopcopy(vxp,..,prp <- q)   core/matvec.f:212
-  NSB_TRY(vk_copy(c, c->pr, vin + dn, c->n2));
+  NSB_TRY(vk_copy(c, c->pr, vin + c->poff, c->n2));
   int rc = 0;
   for (int istep = 1; istep <= c->nsteps && !rc; ++istep) {
     if (c->step_cb) c->step_cb(istep, (istep - 1) * c->dt, c->step_cb_user);     // nekstab_usrchk(), core/matvec.f:221,304
@@ -422,7 +482,8 @@ int st_linearized_map(Ctx* c, int adjoint, const double* vin, double* vout) {
   if (upo_store && !rc) c->orbit_ready = true;
   if (rc) return rc;
   NSB_TRY(vk_copy(c, vout, c->u, dn));           // nopcopy(f <- vxp,..,prp)   core/matvec.f:239
-  NSB_TRY(vk_copy(c, vout + dn, c->pr, c->n2));
+  if (c->scal.on) NSB_TRY(vk_copy(c, vout + dn, c->scal.th, c->n));
+  NSB_TRY(vk_copy(c, vout + c->poff, c->pr, c->n2));
   NSB_CUDA(cudaEventRecord(c->ev1, c->stream));
   NSB_CUDA(cudaStreamSynchronize(c->stream));
   float ms = 0;

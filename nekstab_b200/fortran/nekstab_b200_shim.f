@@ -37,6 +37,8 @@
       integer vertex
       common /ivrtx/ vertex((2**ldim)*lelt)
       integer ierr, ldev
+      real nsb_ri
+      common /nsb_buoy/ nsb_ri
       ldev = mod(nid, 8)
 !     global GLL node numbers of the velocity mesh, exactly what setupds hands to gs_setup: Nek5000's own set_vert
 !     (navier8.f -> setvert2d / setvert3d).  No Nek5000 patch is needed; INTEGRATION.md 1.3 shows the 5-line
@@ -56,9 +58,13 @@
 !     [PRESSURE] preconditioner = semg_xxt in every shipped .par (1cyl.par:28): the multilevel Schwarz class (kind 1);
 !     kind 0 keeps Jacobi.  nagg = 0: automatic number of coarse aggregates.
       call nsb_b200_check(nsb_set_pressure_preconditioner(1, 0), 'nsb_set_pressure_preconditioner')
-      call nsb_b200_check(nsb_vec_alloc(k_dim + 8), 'nsb_vec_alloc')
+!     Scalar transport (ifheat, ldimt = 1): theta joins every device vector; conductivity = param(8), rhocp = param(7), Nek5000's
+!     tmask; the buoyancy coefficient is the case's own (userf: ffy = temp * uparam(6) in examples/cylinder/baseflow/newton_dyn_temp,
+!     temp * Pr * Ra in examples/thersyphon) -- set nsb_ri accordingly before this call.  Must precede nsb_vec_alloc (layout change).
+      if (ifheat) call nsb_b200_check(nsb_set_scalar(1, param(8), param(7), tmask(1,1,1,1,1), nsb_ri, 1), 'nsb_set_scalar')
 !     Newton-GMRES for UPOs: time component in the inner product, orbit storage and border vectors on the device
       if (uparam(1) .eq. 2.1) call nsb_b200_check(nsb_set_upo(1), 'nsb_set_upo')
+      call nsb_b200_check(nsb_vec_alloc(k_dim + 8), 'nsb_vec_alloc')
       end subroutine nsb_b200_setup
 
       subroutine krylov_inner_product(alpha, p, q)
@@ -206,6 +212,7 @@
       if (.not. init) then
 !        prepare_linearized_solver, core/matvec.f:1-52,115-118
          call nsb_b200_check(nsb_set_baseflow(ubase, vbase, wbase), 'nsb_set_baseflow')
+         if (ifheat) call nsb_b200_check(nsb_set_scalar_base(tbase), 'nsb_set_scalar_base')
 !        Floquet (uparam(1) = 3.11 / 3.21, core/matvec.f:192,278): ifbase co-evolution + orbit storage on the device;
 !        the co-evolving base flow feels the DNS branch of nekStab_forcing (core/utils.f:166-171)
          if (uparam(1) .eq. 3.11 .or. uparam(1) .eq. 3.21) then
@@ -278,8 +285,11 @@
       use nekstab_b200_c
       use krylov_subspace
       implicit none
+      include 'SIZE'
+      include 'TOTAL'
       type(krylov_vector) :: p
       call nsb_b200_check(nsb_vec_upload(p%slot, p%vx, p%vy, p%vz, p%pr), 'krylov_to_device')
+      if (ifheat) call nsb_b200_check(nsb_vec_upload_scalar(p%slot, p%theta(1,1)), 'krylov_to_device')
       call nsb_b200_check(nsb_vec_set_time(p%slot, real(p%time, c_double)), 'krylov_to_device')
       end subroutine krylov_to_device
 
@@ -287,9 +297,12 @@
       use nekstab_b200_c
       use krylov_subspace
       implicit none
+      include 'SIZE'
+      include 'TOTAL'
       type(krylov_vector) :: p
       real(c_double) :: tt
       call nsb_b200_check(nsb_vec_download(p%slot, p%vx, p%vy, p%vz, p%pr), 'krylov_to_host')
+      if (ifheat) call nsb_b200_check(nsb_vec_download_scalar(p%slot, p%theta(1,1)), 'krylov_to_host')
       call nsb_b200_check(nsb_vec_get_time(p%slot, tt), 'krylov_to_host')
       p%time = tt
       end subroutine krylov_to_host

@@ -62,6 +62,11 @@ _SIGS = {
     "nsb_set_sponge": [_dp],
     "nsb_set_floquet": [C.c_int, _dp],
     "nsb_set_upo": [C.c_int],
+    "nsb_set_scalar": [C.c_int, C.c_double, C.c_double, _dp, C.c_double, C.c_int],
+    "nsb_set_scalar_base": [_dp],
+    "nsb_vec_upload_scalar": [C.c_int, _dp],
+    "nsb_vec_download_scalar": [C.c_int, _dp],
+    "nsb_op_conv_scalar": [_dp] * 5,
     "nsb_vec_set_time": [C.c_int, C.c_double],
     "nsb_vec_get_time": [C.c_int, _dp],
     "nsb_set_dns_sponge": [C.c_double, _dp, _dp, _dp],
@@ -281,6 +286,28 @@ class NekStabB200:
         t = C.c_double()
         _ck(self.lib.nsb_vec_get_time(int(slot), C.byref(t)))
         return t.value
+
+    def set_scalar(self, enable, conductivity=0.0, rhocp=1.0, tmask=None, ri=0.0, gdir=1):
+        """Scalar transport (`ifheat`): theta travels in the Krylov vectors ([v|theta|pr]); discards the slots (vec_alloc again)."""
+        tm = None if tmask is None else _arr(tmask).reshape(self.n)
+        _ck(self.lib.nsb_set_scalar(int(enable), float(conductivity), float(rhocp), _p(tm), float(ri), int(gdir)))
+
+    def set_scalar_base(self, tbase):
+        _ck(self.lib.nsb_set_scalar_base(_p(_arr(tbase).reshape(self.n))))
+
+    def vec_upload_scalar(self, slot, theta):
+        _ck(self.lib.nsb_vec_upload_scalar(int(slot), _p(_arr(theta).reshape(self.n))))
+
+    def vec_download_scalar(self, slot):
+        t = np.empty(self.n)
+        _ck(self.lib.nsb_vec_download_scalar(int(slot), _p(t)))
+        return t
+
+    def op_conv_scalar(self, a, phi):
+        a3 = self._vec3(a)
+        out = np.empty(self.n)
+        _ck(self.lib.nsb_op_conv_scalar(_p(a3[0]), _p(a3[1]), _p(a3[2]), _p(_arr(phi).reshape(self.n)), _p(out)))
+        return out
 
     def set_dns_sponge(self, spng_str, ref=None):
         r = [None] * 3 if ref is None else self._vec3(ref)

@@ -122,12 +122,13 @@ class Re2:
     nel: int
     xyz: np.ndarray        # (nel, ldim, 2**ldim) vertex coordinates, Nek "preprocessor" vertex order
     curves: List[tuple]    # (elem(1-based), face(1-based), p1..p5, type)
-    bcs: List[tuple]       # (elem, face, p1..p5, code)
+    bcs: List[tuple]       # (elem, face, p1..p5, code)  -- velocity
+    bcs_more: List[list] = field(default_factory=list)   # the same for the temperature and every passive scalar the file carries
 
-    def bc_codes(self) -> np.ndarray:
-        """(nel, 2*ldim) array of 3-char codes, 'E  ' where no record exists."""
+    def bc_codes(self, ifield: int = 0) -> np.ndarray:
+        """(nel, 2*ldim) array of 3-char codes, 'E  ' where no record exists.  ifield 0: velocity, 1: temperature, ..."""
         out = np.full((self.nel, 2 * self.ldim), "E  ", dtype="<U3")
-        for (e, f, *_p, code) in self.bcs:
+        for (e, f, *_p, code) in (self.bcs if ifield == 0 else self.bcs_more[ifield - 1]):
             out[e - 1, f - 1] = code
         return out
 
@@ -154,7 +155,7 @@ def read_re2(path: str) -> Re2:
         for _ in range(ncurve):
             raw = f.read(64)
             v = struct.unpack(e + "7d", raw[:56])
-            curves.append((int(v[0]), int(v[1]), *v[2:7], raw[56:64].decode("ascii").strip()))
+            curves.append((int(v[0]), int(v[1]), *v[2:7], raw[56:57].decode("ascii", errors="replace")))   # 1 character, the rest of the word is padding
         nbc = int(np.fromfile(f, dtype=e + "f8", count=1)[0])
         bcs = []
         for _ in range(nbc):
@@ -162,7 +163,21 @@ def read_re2(path: str) -> Re2:
             v = struct.unpack(e + "7d", raw[:56])
             code = raw[56:64].decode("ascii")[:3]
             bcs.append((int(v[0]), int(v[1]), *v[2:7], code))
-    return Re2(ldim, nel, xyz, curves, bcs)
+        # further fields (temperature, passive scalars): one more block each, same record format
+        more = []
+        while True:
+            cnt = np.fromfile(f, dtype=e + "f8", count=1)
+            if cnt.size == 0:
+                break
+            blk = []
+            for _ in range(int(cnt[0])):
+                raw = f.read(64)
+                v = struct.unpack(e + "7d", raw[:56])
+                blk.append((int(v[0]), int(v[1]), *v[2:7], raw[56:64].decode("ascii", errors="replace")[:3]))
+            more.append(blk)
+    r = Re2(ldim, nel, xyz, curves, bcs)
+    r.bcs_more = more
+    return r
 
 
 @dataclass

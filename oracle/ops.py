@@ -276,8 +276,9 @@ class SEM:
         eye = np.eye(nin)
         return out, eye
 
-    def helm_sparse(self, h1, h2, comp=0):
-        """Assembled, masked Helmholtz matrix on global nodes (Dirichlet rows/cols replaced by identity)."""
+    def helm_sparse(self, h1, h2, comp=0, mask=None):
+        """Assembled, masked Helmholtz matrix on global nodes (Dirichlet rows/cols replaced by identity).  mask: an explicit
+        Dirichlet mask (the scalar's tmask) instead of the velocity component's."""
         d = self.ldim
         npt = self.lx1 ** d
         # element matrices via tensor structure: apply axhelm to unit vectors, one basis fn at a time
@@ -289,7 +290,7 @@ class SEM:
         cols = np.repeat(self.glo[:, None, :], npt, axis=1).ravel()
         K = sp.coo_matrix((Ke.ravel(), (rows, cols)), shape=(self.nglob, self.nglob)).tocsr()
         free = np.zeros(self.nglob)
-        np.maximum.at(free, self.glo.ravel(), self.mask[comp].ravel())
+        np.maximum.at(free, self.glo.ravel(), (self.mask[comp] if mask is None else mask).ravel())
         Fm = sp.diags(free)
         K = Fm @ K @ Fm + sp.diags(1.0 - free)
         return K.tocsc(), free

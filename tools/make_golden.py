@@ -11,6 +11,8 @@ What is extracted (SURVEY.md 8c "golden vectors"):
   cav.npz : examples/lid_driven/{BF_cav0.f00001, cav.ma2, cav.re2} (config 3; the shipped base flow lives on y in [0, 1.2]
             although cav.par:9 sets the aspect ratio 1.5 that cav.usr:107-109 rescales the mesh to: the fixture's own
             coordinates are kept, SURVEY.md 8 cfg-3 caveat)
+  tsyphon.npz : examples/thersyphon/baseflow/{BF_Ra400_tsyphon0.f00001, tsyphon.ma2, tsyphon.re2} (scalar transport: the shipped
+            Boussinesq base flow with temperature)
 All element data are re-ordered to ascending global element id.
 """
 import os
@@ -115,6 +117,27 @@ def cav():
     print("cav.npz", os.path.getsize(f"{OUT}/cav.npz") / 1e6, "MB")
 
 
+def tsyphon():
+    """examples/thersyphon/baseflow: the Newton-converged steady thermosyphon at Ra = 400 (annulus r in [1, 2], periodic in theta,
+    walls 'W' / 't' at both radii; Pr = 5: tsyphon.par viscosity = 5, conductivity = 1, rhocp = 1; buoyancy ffy = T * Pr * Ra,
+    tsyphon.usr userf).  A double-precision field file with coordinates: the curved-element GLL points are taken from it."""
+    d = f"{REF}/examples/thersyphon/baseflow"
+    bf = nekio.read_field(f"{d}/BF_Ra400_tsyphon0.f00001").sort_global()
+    re2 = nekio.read_re2(f"{d}/tsyphon.re2")
+    ma2 = nekio.read_ma2(f"{d}/tsyphon.ma2")
+    names = np.array(["E  ", "P  ", "W  ", "t  "])
+    out = dict(lx1=bf.nx, X=bf.data["X"][:, :, 0], U=bf.data["U"][:, :, 0], P=bf.data["P"][:, 0], T=bf.data["T"][:, 0], time=bf.time,
+               istep=bf.istep, vert=ma2.vert.astype(np.int32), key=ma2.key.astype(np.int32), d2=ma2.d2, bc_names=names.astype("S3"))
+    for nm, ifield in (("bc", 0), ("bct", 1)):
+        codes = re2.bc_codes(ifield)
+        bc = np.zeros(codes.shape, dtype=np.uint8)
+        for i, nme in enumerate(names):
+            bc[codes == nme] = i
+        out[nm] = bc
+    np.savez_compressed(f"{OUT}/tsyphon.npz", **out)
+    print("tsyphon.npz", os.path.getsize(f"{OUT}/tsyphon.npz") / 1e6, "MB")
+
+
 def cyl_upo():
     """examples/cylinder/stability/direct_Floquet: the periodic orbit snapshot the Floquet example starts from (`startFrom =
     BF_1cyl0.f00001 # here UPO file`, 1cyl.par:2; time = the period 7.9213, istep = 796) and its shipped Floquet spectrum."""
@@ -142,9 +165,13 @@ if __name__ == "__main__":
     if "--upo-only" in sys.argv:
         cyl_upo()
         sys.exit(0)
+    if "--tsyphon-only" in sys.argv:
+        tsyphon()
+        sys.exit(0)
     if "--spectrum-only" not in sys.argv:
         cyl()
         bfs()
         cav()
         cyl_upo()
+        tsyphon()
     spectrum_text()

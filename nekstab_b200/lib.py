@@ -291,6 +291,7 @@ class NekStabB200:
         """Scalar transport (`ifheat`): theta travels in the Krylov vectors ([v|theta|pr]); discards the slots (vec_alloc again)."""
         tm = None if tmask is None else _arr(tmask).reshape(self.n)
         _ck(self.lib.nsb_set_scalar(int(enable), float(conductivity), float(rhocp), _p(tm), float(ri), int(gdir)))
+        self.scalar_on = bool(enable)
 
     def set_scalar_base(self, tbase):
         _ck(self.lib.nsb_set_scalar_base(_p(_arr(tbase).reshape(self.n))))

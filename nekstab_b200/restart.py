@@ -124,7 +124,7 @@ def _is_partial(case) -> bool:
 
 
 def write_krylov_vector(path: str, case, v: np.ndarray, p: np.ndarray, *, time: float = 0.0, istep: int = 0, wdsize: int = 8,
-                        comm: "GatherComm | None" = None) -> None:
+                        comm: "GatherComm | None" = None, theta: "np.ndarray | None" = None) -> None:
     """One Krylov vector as ONE global Nek field file (velocity + pressure on mesh 1), like the reference's `outpost`: element
     order = rank-major, ascending global id within a rank, `nelg` = the global element count.  A case that holds
     only one rank's share of the mesh needs `comm` (every rank calls; rank 0 writes); without it this raises instead of writing
@@ -133,24 +133,27 @@ def write_krylov_vector(path: str, case, v: np.ndarray, p: np.ndarray, *, time: 
     shp = (nel,) + ((L,) * 3 if d == 3 else (1, L, L))
     U = np.asarray(v, float).reshape(d, nel, -1).transpose(1, 0, 2).reshape((nel, d) + shp[1:])
     P = pressure_to_mesh1(np.asarray(p, float).reshape(nel, -1), L, d).reshape(shp)
+    T = None if theta is None else np.asarray(theta, float).reshape(shp)          # the vector's scalar (`ifheat`): field T of the file
     elmap = np.asarray(case.lglel if case.lglel is not None else np.arange(1, nel + 1), dtype=np.int32)
     if _is_partial(case):
         if comm is None:
             raise ValueError(f"write_krylov_vector: the case holds {nel} of {case.nelg} elements (one rank's share); pass comm= "
                              "(restart.GatherComm) so that rank 0 can write one global file")
-        parts = comm.gather((elmap, U, P))
+        parts = comm.gather((elmap, U, P, T))
         if comm.rank != 0:
             return
         elmap = np.concatenate([q[0] for q in parts])
         U = np.concatenate([q[1] for q in parts])
         P = np.concatenate([q[2] for q in parts])
+        T = None if T is None else np.concatenate([q[3] for q in parts])
         if elmap.size != int(case.nelg) or np.unique(elmap).size != elmap.size:
             raise ValueError(f"write_krylov_vector: gathered {elmap.size} elements, expected {case.nelg} distinct ones")
-    nekio.write_field(path, U=U, P=P, time=time, istep=istep, wdsize=wdsize, elmap=elmap)
+    nekio.write_field(path, U=U, P=P, T=T, time=time, istep=istep, wdsize=wdsize, elmap=elmap)
 
 
-def read_krylov_vector(path: str, case) -> Tuple[np.ndarray, np.ndarray]:
-    """Inverse of `write_krylov_vector`: (ldim, nel, npts) velocity and (nel, lx2^ldim) pressure in the case's element order."""
+def read_krylov_vector(path: str, case, with_theta: bool = False):
+    """Inverse of `write_krylov_vector`: (ldim, nel, npts) velocity and (nel, lx2^ldim) pressure in the case's element order;
+    with_theta: also the scalar (nel, npts) (zeros when the file has no T field)."""
     ff = nekio.read_field(path)
     d, nel, L = case.ldim, case.nel, case.lx1
     if ff.nx != L or ff.ldim != d or ff.nel < nel:
@@ -163,6 +166,9 @@ def read_krylov_vector(path: str, case) -> Tuple[np.ndarray, np.ndarray]:
         raise ValueError(f"{path}: global element {e} not in the file") from None
     v = ff.data["U"][order].reshape(nel, d, -1).transpose(1, 0, 2).copy()
     p = pressure_to_mesh2(ff.data["P"][order].reshape(nel, -1), L, d) if "P" in ff.data else np.zeros((nel, (L - 2) ** d))
+    if with_theta:
+        t = ff.data["T"][order].reshape(nel, -1).copy() if "T" in ff.data else np.zeros((nel, L ** d))
+        return v, p, t
     return v, p
 
 
@@ -173,7 +179,9 @@ def arnoldi_checkpoint(ctx, case, session: str, H: np.ndarray, k: int, slot: int
     Multi-rank: every rank calls with `comm`; the KRY file is gathered into one global file and, like the reference
     (`if (nid .eq. 0)` :866-889), only rank 0 writes the HES and Spectre files."""
     v, p = ctx.vec_download(slot)
-    write_krylov_vector(os.path.join(outdir, kry_filename(session, k + 1)), case, v, p, time=tau * k, istep=k, wdsize=wdsize, comm=comm)
+    theta = ctx.vec_download_scalar(slot) if getattr(ctx, "scalar_on", False) else None
+    write_krylov_vector(os.path.join(outdir, kry_filename(session, k + 1)), case, v, p, time=tau * k, istep=k, wdsize=wdsize, comm=comm,
+                        theta=theta)
     vals, vecs = np.linalg.eig(H[:k, :k])
     order = np.argsort(-np.abs(vals), kind="stable")          # `eig` sorts by decreasing magnitude (core/lapack_wrapper.f:129)
     vals, vecs = vals[order], vecs[:, order]

@@ -72,6 +72,15 @@ def test_krylov_vector_file_round_trip(tmp_path):
         v3, p3 = restart.read_krylov_vector(path, part)
         sel = part.lglel - 1
         assert np.array_equal(v3, v[:, sel]) and np.abs(p3 - p[sel]).max() < 1e-12
+        # the vector's scalar (`ifheat`) travels as the T field; files without one read back zeros
+        th = rng.standard_normal((c.nel, c.npts))
+        restart.write_krylov_vector(path, c, v, p, theta=th)
+        v5, p5, t5 = restart.read_krylov_vector(path, c, with_theta=True)
+        assert np.array_equal(v5, v) and np.array_equal(t5, th) and np.abs(p5 - p).max() < 1e-12
+        _, _, t6 = restart.read_krylov_vector(path, part, with_theta=True)
+        assert np.array_equal(t6, th[sel])
+        restart.write_krylov_vector(path, c, v, p)
+        assert not restart.read_krylov_vector(path, c, with_theta=True)[2].any()
         # single precision files (writeDoublePrecision = no, 1cyl.par:20) lose digits but keep the layout
         restart.write_krylov_vector(path, c, v, p, wdsize=4)
         v4, _ = restart.read_krylov_vector(path, c)

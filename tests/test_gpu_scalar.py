@@ -143,3 +143,37 @@ def test_kat_thermal_thermosyphon_fixed_point_on_gpu():
         assert rel(f, uo - U) < 1e-3 and rel(ft, to - T) < 1e-3                  # the 1e-5-sized residual itself, to 3 digits
     finally:
         g.close()
+
+
+def test_thermosyphon_newton_end_to_end():
+    """examples/thersyphon/baseflow as shipped: Newton-Krylov (uparam(1) = 2) from the Ra = 400 solution to the steady state at Ra = 500
+    (tsyphon.par: startfrom BF_Ra400_tsyphon0.f00001, userparam06 = 500, endTime 0.1, tolerances 1e-11), velocity + temperature in the
+    Krylov vectors, driven by nsb_newton_krylov on the device.  Fixture: the same run on the CPU oracle (tools/run_tsyphon_oracle.py:
+    3 Newton iterations, residuals 8.539e-01, 1.415e-04, 9.210e-12)."""
+    import os
+    from nekstab_b200 import cases, lib, restart
+    from util import GOLD
+    ref = np.load(os.path.join(GOLD, "tsyphon_oracle.npz"))
+    c = cases.thermosyphon_case(np.load(os.path.join(GOLD, "tsyphon.npz")), ra=500.0)
+    s = make_oracle(c)
+    U, T, tm = c.ubase.reshape((2,) + s.eshape), c.extra["T"].reshape(s.eshape), c.extra["tmask"].reshape(s.eshape)
+    p2 = restart.pressure_to_mesh2(c.extra["P"], c.lx1, 2).reshape(s.eshape2)
+    k_dim = 40
+    g = lib.NekStabB200(c)
+    try:
+        g.set_params(1.0 / c.re, 1.0, 1e-13, 1e-13, 5000, 100000)              # Jacobi-PCG like the oracle: same attainable accuracy
+        g.set_scalar(1, 1.0, 1.0, tm, float(c.extra["ri"]), 1)
+        g.vec_alloc(k_dim + 6)
+        g.vec_upload(0, U, p2)
+        g.vec_upload_scalar(0, T)
+        ok, it, res, hist, calls = g.newton_krylov(0, 1, 2, 3, 4, k_dim, c.end_time, 1e-11, maxiter_newton=12, maxiter_gmres=10)
+        print("thermosyphon Newton on the GPU: %d iterations, residuals %s (oracle %s), %d linearised steps" % (it, hist, ref["hist"], calls))
+        assert ok and int(ref["iters"]) == 3 and it in (3, 4)                    # the oracle's third residual is 9.2e-12, just under the 1e-11 exit test
+        assert np.allclose(np.log10(hist[:2]), np.log10(ref["hist"][:2]), atol=0.02) and hist[-1] < 1e-11
+        u, _ = g.vec_download(0)
+        t = g.vec_download_scalar(0)
+        print("  converged fields vs oracle:", rel(u, ref["U"]), rel(t, ref["T"]))
+        assert rel(u, ref["U"]) < 1e-5 and rel(t, ref["T"]) < 1e-6
+        assert rel(u, U) > 0.1                                                   # Ra 400 -> 500 is a different flow (|dU|/|U| = 0.26)
+    finally:
+        g.close()

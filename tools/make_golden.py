@@ -11,6 +11,7 @@ What is extracted (SURVEY.md 8c "golden vectors"):
   cav.npz : examples/lid_driven/{BF_cav0.f00001, cav.ma2, cav.re2} (config 3; the shipped base flow lives on y in [0, 1.2]
             although cav.par:9 sets the aspect ratio 1.5 that cav.usr:107-109 rescales the mesh to: the fixture's own
             coordinates are kept, SURVEY.md 8 cfg-3 caveat)
+  cyl_re40.npz : examples/cylinder/baseflow/newton/BFRe40_1cyl0.f00001 (config 2: the Newton-Krylov case's initial condition)
   tsyphon.npz : examples/thersyphon/baseflow/{BF_Ra400_tsyphon0.f00001, tsyphon.ma2, tsyphon.re2} (scalar transport: the shipped
             Boussinesq base flow with temperature)
 All element data are re-ordered to ascending global element id.
@@ -138,6 +139,16 @@ def tsyphon():
     print("tsyphon.npz", os.path.getsize(f"{OUT}/tsyphon.npz") / 1e6, "MB")
 
 
+def cyl_re40():
+    """examples/cylinder/baseflow/newton: the Re = 40 steady flow the shipped Newton-Krylov case (config 2) starts from
+    (`startFrom = BFRe40_1cyl0.f00001`, 1cyl.par:2; target Re = 50, endTime 1, k_dim 100, tolerances 1e-11)."""
+    d = f"{REF}/examples/cylinder/baseflow/newton"
+    bf = nekio.read_field(f"{d}/BFRe40_1cyl0.f00001").sort_global()
+    out = dict(lx1=bf.nx, U=bf.data["U"][:, :, 0].astype(np.float32), P=bf.data["P"][:, 0].astype(np.float32), time=bf.time, istep=bf.istep)
+    np.savez_compressed(f"{OUT}/cyl_re40.npz", **out)
+    print("cyl_re40.npz", os.path.getsize(f"{OUT}/cyl_re40.npz") / 1e6, "MB")
+
+
 def cyl_upo():
     """examples/cylinder/stability/direct_Floquet: the periodic orbit snapshot the Floquet example starts from (`startFrom =
     BF_1cyl0.f00001 # here UPO file`, 1cyl.par:2; time = the period 7.9213, istep = 796) and its shipped Floquet spectrum."""
@@ -165,6 +176,9 @@ if __name__ == "__main__":
     if "--upo-only" in sys.argv:
         cyl_upo()
         sys.exit(0)
+    if "--re40-only" in sys.argv:
+        cyl_re40()
+        sys.exit(0)
     if "--tsyphon-only" in sys.argv:
         tsyphon()
         sys.exit(0)
@@ -174,4 +188,5 @@ if __name__ == "__main__":
         cav()
         cyl_upo()
         tsyphon()
+        cyl_re40()
     spectrum_text()

@@ -119,3 +119,27 @@ def test_kat_fixed_point_nonlinear_map(cyl):
     res = np.sqrt(_inner(s, fv, fv, s.bm1))
     assert abs(np.sqrt(_inner(s, ub, ub, s.bm1)) - 46.1512) < 1e-3
     assert abs(res - 3.096e-6) < 0.05e-6 and res ** 2 < 1e-11
+
+
+def test_cfg2_newton_result_is_the_shipped_base_flow(cyl):
+    """Config 2 end to end on the oracle (tools/run_newton_cfg2_oracle.py, 15 min of CPU: not repeated here): Newton-Krylov from the shipped
+    Re = 40 flow converges in 4 iterations onto the reference's own Re = 50 base flow -- 1.9e-10 in the energy norm at full precision
+    (profiles/r2_newton_cfg2_oracle.json); the committed float32 fixture of the converged field keeps 3e-8 of that.  The first step of that
+    run is repeated: the Re = 40 start is 6.1e-3 away and its fixed-point residual at Re = 50 is the recorded 2.589e-03."""
+    g, c, s = cyl
+    o = np.load(os.path.join(GOLD, "cyl_newton_oracle.npz"))
+    ub = c.ubase.reshape((2,) + s.eshape)
+    uo = o["U"].astype(np.float64).reshape(ub.shape)
+    nrm = _inner(s, ub, ub, s.bm1)
+    assert np.sqrt(_inner(s, uo - ub, uo - ub, s.bm1) / nrm) < 6e-8
+    assert int(o["iters"]) == 4 and o["hist"][-1] < 1e-11 and abs(o["hist"][0] - 2.5892e-3) < 1e-6
+    g40 = np.load(os.path.join(GOLD, "cyl_re40.npz"))
+    from nekstab_b200 import restart
+    u0 = g40["U"].reshape(-1, 2, 36).transpose(1, 0, 2).astype(np.float64).reshape(ub.shape)
+    assert abs(np.sqrt(_inner(s, u0 - ub, u0 - ub, s.bm1) / nrm) - 6.09e-3) < 1e-4
+    p0 = restart.pressure_to_mesh2(g40["P"].reshape(c.nel, -1).astype(np.float64), c.lx1, 2).reshape(s.eshape2)
+    dt, nsteps, _ = prepare_linearized_solver(s, u0, 1.0)
+    assert nsteps == 98
+    st = LinearizedStepper(s, u0, c.re, None, solver="direct", ifvcor=False)
+    fv, fp, _, _ = st.nonlinear_forward_map(u0, p0, nsteps, dt)
+    assert abs(_inner(s, fv, fv, s.bm1) - o["hist"][0]) < 1e-6 * o["hist"][0]

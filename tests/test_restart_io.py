@@ -129,3 +129,13 @@ def test_multirank_checkpoint_gathers_one_global_file(tmp_path):
     for r in range(2):
         v3, p3 = restart.read_krylov_vector(path, parts[r])
         assert np.array_equal(v3, v[:, sels[r]])
+    # ... and the vector's scalar (`ifheat`) travels through the same gather
+    th = rng.standard_normal((c.nel, c.npts))
+    box.clear()
+    for r in (1, 0):
+        def gather(obj, r=r):
+            box.append((r, obj))
+            return [o for _, o in sorted(box, key=lambda t: t[0])] if r == 0 else None
+        restart.write_krylov_vector(path, parts[r], v[:, sels[r]], p[sels[r]], comm=restart.GatherComm(r, 2, gather), theta=th[sels[r]])
+    assert np.array_equal(restart.read_krylov_vector(path, c, with_theta=True)[2], th)
+    assert np.array_equal(restart.read_krylov_vector(path, parts[1], with_theta=True)[2], th[sels[1]])

@@ -39,7 +39,7 @@ def test_scalar_convection_operator(name):
         g.close()
 
 
-@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("name", CASES[:2])         # (the lx1 = 8 mesh costs the CPU oracle 50 s; its kernel is covered by the operator test)
 def test_direct_map_with_scalar(name):
     from nekstab_b200 import lib
     c, s, g, st, tmask, tb = _setup(name)

@@ -16,7 +16,7 @@ from __future__ import annotations
 import numpy as np
 import scipy.sparse.linalg as spla
 
-from .stepper import AB, BD, LinearizedStepper
+from .stepper import AB, BD, _LU_CACHE, LinearizedStepper, _h, _mesh_key
 
 
 class ScalarStepper(LinearizedStepper):
@@ -42,8 +42,11 @@ class ScalarStepper(LinearizedStepper):
         if self.solver == "direct":
             key = round(h2, 12)
             if key not in self._lu_t:
-                K, free = s.helm_sparse(self.cond, h2, mask=self.tmask)
-                self._lu_t[key] = (spla.splu(K), free)
+                gk = ("T", _mesh_key(s), float(self.cond), key, _h(self.tmask))
+                if gk not in _LU_CACHE:
+                    K, free = s.helm_sparse(self.cond, h2, mask=self.tmask)
+                    _LU_CACHE[gk] = (spla.splu(K), free)
+                self._lu_t[key] = _LU_CACHE[gk]
             lu, free = self._lu_t[key]
             g = np.zeros(s.nglob)
             g[s.glo.ravel()] = rhs.ravel()
